@@ -1,0 +1,210 @@
+/*
+ * pathed_cuda.h — C ABI of the B200-native replacement for Pathed's surface path-tracing hot path.
+ *
+ * This is the drop-in boundary.  Pathed has no plugin loader; the seams a
+ * maintainer binds are (1) the Embree `rtc*` build/query calls, (2) `Material` / `Light` /
+ * `Camera` construction and (3) `Integrator::sampleImage`.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all input pointers are HOST memory unless the name says
+ *    `_device`; inputs are copied during the call (caller keeps ownership);
+ *  - every call returns PTC_OK (0) or a negative status; `ptc_last_error` gives the text;
+ *    no C++ exception crosses the ABI (the reference's `exit(1)` / `throw` sites map to statuses);
+ *  - one context drives ONE GPU and is not thread-safe; multi-GPU = one context per process/GPU;
+ *  - there is no CPU fallback: without a CUDA device `ptc_create` fails.
+ */
+#ifndef PATHED_CUDA_H
+#define PATHED_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ptc_ctx ptc_ctx;
+
+enum {
+    PTC_OK = 0,
+    PTC_ERR_INVALID = -1, /* bad argument (the reference would assert / throw std::runtime_error) */
+    PTC_ERR_CUDA = -2,    /* CUDA runtime failure */
+    PTC_ERR_STATE = -3,   /* call order violated (e.g. render before commit) */
+    PTC_ERR_NOMEM = -4
+};
+
+#define PTC_INVALID_ID 0xFFFFFFFFu /* = RTC_INVALID_GEOMETRY_ID */
+
+/* Material types on the hot path (src/scene_parser.cpp:parseMaterial, :604-700). */
+enum {
+    PTC_LAMBERTIAN = 0, /* src/lambertian.cpp */
+    PTC_OREN_NAYAR = 1, /* src/oren_nayar.cpp */
+    PTC_MIRROR = 2,     /* src/mirror.cpp */
+    PTC_GLASS = 3,      /* src/glass.cpp */
+    PTC_MICROFACET = 4, /* src/microfacet.cpp */
+    PTC_PLASTIC = 5     /* src/plastic.cpp */
+};
+enum { PTC_BECKMANN = 0 /* src/beckmann.cpp */, PTC_GGX = 1 /* src/ggx.cpp */ };
+enum { PTC_ALBEDO_CONSTANT = 0, PTC_ALBEDO_CHECKERBOARD = 1 /* src/checkerboard.cpp */ };
+
+/* Flat form of what the reference's Material constructors receive
+ * (include/lambertian.h, oren_nayar.h, glass.h, microfacet.h, plastic.h, checkerboard.h). */
+typedef struct ptc_material_desc {
+    int32_t type;
+    float diffuse[3];     /* Lambertian / OrenNayar / Plastic diffuseReflectance */
+    float emit[3];        /* Material::m_emit (Lambertian only in the reference's parser) */
+    float sigma;          /* OrenNayar */
+    float ior;            /* Glass (reference default 1.4, src/glass.cpp:16-18) */
+    int32_t distribution; /* Microfacet / Plastic: PTC_BECKMANN | PTC_GGX */
+    float alpha;
+    int32_t albedo_kind;  /* Lambertian: constant colour or checkerboard */
+    float checker_on[3];
+    float checker_off[3];
+    float checker_resolution[2];
+} ptc_material_desc;
+
+/* Ray as Scene::testIntersect / testOcclusion take it (include/ray.h): origin + direction.
+ * tnear = 1e-3 and tfar = 1e5 (closest hit) / maxT - 1e-3 (occlusion) are applied inside,
+ * exactly as src/scene.cpp:102-103 and :366-367 do. */
+typedef struct ptc_ray {
+    float origin[3];
+    float direction[3];
+} ptc_ray;
+
+/* Raw hit record = the RTCHit fields the reference reads (src/scene.cpp:115-176). */
+typedef struct ptc_hit {
+    float t; /* ray.tfar after rtcIntersect1; 1e5 on a miss */
+    float u, v;
+    uint32_t geom_id; /* PTC_INVALID_ID on a miss */
+    uint32_t prim_id;
+    float ng[3]; /* unnormalised geometric normal */
+} ptc_hit;
+
+/* Processed intersection = the reference's `Intersection` (include/intersection.h:13-24). */
+typedef struct ptc_isect {
+    int32_t hit;
+    float t;
+    float point[3];
+    float wo[3];
+    float normal[3];
+    float shading_normal[3];
+    float uv[2];
+    uint32_t material; /* id returned by ptc_add_material */
+} ptc_isect;
+
+/* Result of Light::sample / Scene::sampleDirectLights (include/shape.h:15-20, include/scene.h:46-81). */
+typedef struct ptc_light_sample {
+    float point[3];
+    float normal[3];
+    float inv_pdf;
+    int32_t measure; /* 0 = solid angle, 1 = area */
+    float solid_angle_pdf; /* LightSample::solidAnglePDF(reference point) */
+    float emit[3];         /* light->emit(lightWo) toward the reference point */
+} ptc_light_sample;
+
+typedef struct ptc_stats {
+    uint64_t closest_rays; /* rays traced by the extend stage (one per vertex: the MIS probe and the
+                              continuation ray of src/path_tracer.cpp:44 / :175 are the same ray) */
+    uint64_t shadow_rays;
+    uint64_t samples;
+    uint64_t kernel_launches;
+    uint64_t bvh_nodes;
+    uint64_t bvh_triangles;
+    uint64_t bvh_bytes;
+    float last_render_ms; /* device time of the last ptc_render* call (CUDA events) */
+    float traverse_ms;    /* of which: extend + shadow kernels (only when stage timing is enabled) */
+    float shade_ms;
+} ptc_stats;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+/* replaces rtcNewDevice + rtcNewScene (app/main.cpp:46-56) */
+int ptc_create(int device_ordinal, ptc_ctx **out);
+void ptc_destroy(ptc_ctx *ctx); /* rtcReleaseScene / rtcReleaseDevice (app/main.cpp:122-123) */
+const char *ptc_last_error(ptc_ctx *ctx);
+
+/* ---- scene description (geometry sink = the rtc* build API) -------------------------------- */
+/* replaces GeometryParser::processRTCGeometry (src/geometry_parser.cpp:5-97) and the mesh half of
+ * Quad::parse (src/quad.cpp:34-150): vertices float3, per-vertex normal float3 (zeros = none, Q3),
+ * per-vertex uv float2, indices uint3; material_of_tri = RTCManager's primID -> Surface -> Material
+ * (src/rtc_manager.cpp:64-69).  geom ids are handed out sequentially in call order, like
+ * rtcAttachGeometry. */
+int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *positions, const float *normals, const float *uvs,
+                          uint32_t n_vertices, const uint32_t *indices, const uint32_t *material_of_tri,
+                          uint32_t n_triangles, uint32_t *geom_id_out);
+/* replaces Sphere::create (src/sphere.cpp:16-48): RTC_GEOMETRY_TYPE_SPHERE_POINT, one item */
+int ptc_add_sphere(ptc_ctx *ctx, const float center_radius[4], uint32_t material, uint32_t *geom_id_out);
+/* replaces the Material subclass constructors */
+int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *material_id_out);
+/* replaces EnvironmentLight::EnvironmentLight (src/environment_light.cpp:14-54): RGBA fp32 lat-long
+ * texels as tinyexr's LoadEXR returns them, scale, and both 4x4 row-major matrices of `mapToWorld` */
+int ptc_set_environment(ptc_ctx *ctx, const float *rgba, int width, int height, float scale,
+                        const float map_to_world[16], const float world_to_map[16]);
+/* replaces Camera::Camera (src/camera.cpp:13-30): look-at + vertical fov in radians + resolution */
+int ptc_set_camera(ptc_ctx *ctx, const float origin[3], const float target[3], const float up[3],
+                   float vertical_fov, int width, int height, int flip_handedness);
+/* replaces Scene::Scene -> rtcCommitScene (src/scene.cpp:26-40) and the light list of parseScene
+ * (src/scene_parser.cpp:173-190): builds the BVH, the light table (emissive surfaces in registration
+ * order, environment light last) and the environment CDFs; uploads everything */
+int ptc_commit(ptc_ctx *ctx);
+
+/* ---- hot path ------------------------------------------------------------------------------ */
+/* replaces n_spp iterations of SampleIntegrator::sampleImage (src/sample_integrator.cpp:80-113):
+ * adds, for every pixel, the radiance of samples first_sample .. first_sample+n_spp-1 into
+ * accum_rgb (HOST, 3*W*H floats, index 3*(row*W+col)+c, row 0 = bottom; `+=` like radianceLookup).
+ * start_bounce / last_bounce = BounceController (src/bounce_controller.cpp:14-25; -1 = unbounded,
+ * capped at PTC_MAX_BOUNCES).  seed keys the Philox streams (pixel, sample, bounce). */
+int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
+               int last_bounce, float *accum_rgb);
+/* same, accumulating into a DEVICE buffer on `cuda_stream` (a cudaStream_t; NULL = default stream);
+ * asynchronous: returns after enqueueing.  Used for multi-GPU (NCCL reduce of the buffer) */
+int ptc_render_device(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
+                      int last_bounce, float *accum_rgb_device, void *cuda_stream);
+/* K7 resolve: out[i] = accum[i] / spp on the device (src/integrator.cpp:74-85) */
+int ptc_resolve_device(ptc_ctx *ctx, const float *accum_rgb_device, float *out_rgb_device, uint32_t spp,
+                       void *cuda_stream);
+#define PTC_MAX_BOUNCES 64
+
+/* ---- ray queries (keep Scene::testIntersect / testOcclusion alive for CPU integrators; parity) */
+int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);        /* rtcIntersect1 */
+int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out);  /* Scene::testIntersect */
+int ptc_occluded(ptc_ctx *ctx, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded); /* Scene::testOcclusion */
+/* device-resident variants used by the benchmark (rays/hits already in HBM) */
+int ptc_intersect_device(ptc_ctx *ctx, const ptc_ray *rays_device, uint32_t n, ptc_hit *hits_device, void *cuda_stream);
+int ptc_occluded_device(ptc_ctx *ctx, const ptc_ray *rays_device, const float *max_t_device, uint32_t n,
+                        uint8_t *occluded_device, void *cuda_stream);
+
+/* ---- function-level probes (parity of shading / sampling code against the reference) --------- */
+/* Camera::generateRay(float row, float col) (src/camera.cpp:32-47) */
+int ptc_camera_rays(ptc_ctx *ctx, const float *row_col, uint32_t n, ptc_ray *rays);
+/* Material::f(isect, wi, &pdf) */
+int ptc_bsdf_eval(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *wi, uint32_t n,
+                  float *f_rgb, float *pdf);
+/* Material::sample(isect, random) with the random stream given explicitly: xi[3*i .. 3*i+2] */
+int ptc_bsdf_sample(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *xi, uint32_t n,
+                    float *wi, float *pdf, float *throughput_rgb);
+/* Scene::sampleDirectLights(point, random): xi[3*i] picks the light, xi[3*i+1..2] the point */
+int ptc_light_sample(ptc_ctx *ctx, const float *ref_points, const float *xi, uint32_t n, ptc_light_sample *out);
+/* Scene::lightsPDF / environmentPDF for the ray origin -> direction: >= 0 light pdf when the ray lands on
+ * an emitter, -1 when it contributes nothing, -2 - pdf for an environment miss */
+int ptc_light_pdf(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, float *pdf);
+/* Scene::environmentL(direction) */
+int ptc_environment_radiance(ptc_ctx *ctx, const float *directions, uint32_t n, float *rgb);
+/* body of SampleIntegrator::samplePixel + PathTracer::L for explicit primary rays, the random stream
+ * replayed sequentially from xi[i*stride ...] (test hook: same draws in the same order as the reference) */
+int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n,
+                        int start_bounce, int last_bounce, float *rgb);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int ptc_num_lights(ptc_ctx *ctx, uint32_t *out); /* Scene::lights().size() */
+int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out);
+int ptc_reset_stats(ptc_ctx *ctx);
+int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "paths_per_wave" */
+/* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
+ * visits and triangle tests per ray (algorithmic bytes per ray) */
+int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATHED_CUDA_H */
