@@ -94,14 +94,14 @@ typedef struct ptc_isect {
 } ptc_isect;
 
 /* Result of Light::sample / Scene::sampleDirectLights (include/shape.h:15-20, include/scene.h:46-81). */
-typedef struct ptc_light_sample {
+typedef struct ptc_light_sample_t {
     float point[3];
     float normal[3];
     float inv_pdf;
     int32_t measure; /* 0 = solid angle, 1 = area */
     float solid_angle_pdf; /* LightSample::solidAnglePDF(reference point) */
     float emit[3];         /* light->emit(lightWo) toward the reference point */
-} ptc_light_sample;
+} ptc_light_sample_t;
 
 typedef struct ptc_stats {
     uint64_t closest_rays; /* rays traced by the extend stage (one per vertex: the MIS probe and the
@@ -184,7 +184,7 @@ int ptc_bsdf_eval(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, cons
 int ptc_bsdf_sample(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *xi, uint32_t n,
                     float *wi, float *pdf, float *throughput_rgb);
 /* Scene::sampleDirectLights(point, random): xi[3*i] picks the light, xi[3*i+1..2] the point */
-int ptc_light_sample(ptc_ctx *ctx, const float *ref_points, const float *xi, uint32_t n, ptc_light_sample *out);
+int ptc_light_sample(ptc_ctx *ctx, const float *ref_points, const float *xi, uint32_t n, ptc_light_sample_t *out);
 /* Scene::lightsPDF / environmentPDF for the ray origin -> direction: >= 0 light pdf when the ray lands on
  * an emitter, -1 when it contributes nothing, -2 - pdf for an environment miss */
 int ptc_light_pdf(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, float *pdf);

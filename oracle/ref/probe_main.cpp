@@ -140,9 +140,12 @@ void ref_intersect_raw(
         rh.ray.mask = -1;
         rh.hit.geomID = RTC_INVALID_GEOMETRY_ID;
         rh.hit.instID[0] = RTC_INVALID_GEOMETRY_ID;
-        RTCIntersectContext context;
-        rtcInitIntersectContext(&context);
-        rtcIntersect1(g_rtcScene, &context, &rh);
+        // same context type the reference's filter callback expects (src/scene.cpp:42-49): pass-throughs are intersected
+        CustomRTCIntersectContext context;
+        rtcInitIntersectContext(&context.context);
+        context.rtcManagerPtr = nullptr;
+        context.shouldIntersectPassthroughs = true;
+        rtcIntersect1(g_rtcScene, &context.context, &rh);
         t[i] = rh.ray.tfar;
         geomID[i] = rh.hit.geomID;
         primID[i] = rh.hit.primID;

@@ -1,0 +1,63 @@
+// Flat scene description: what Pathed's parsers produce, captured at the rtc* sink
+// (/root/reference/src/geometry_parser.cpp:5-97, src/quad.cpp:34-150, src/sphere.cpp:20-47) and at the
+// Material / Camera / EnvironmentLight constructors, in registration order.  It is fed to the CUDA
+// library through the C ABI (include/pathed_cuda.h) by feedScene().
+#pragma once
+
+#include "../../include/pathed_cuda.h"
+
+#include <string>
+#include <vector>
+
+namespace pathed {
+
+struct GeometryDesc {
+    bool isSphere = false;
+    // triangle mesh (one Embree geometry): per-vertex position/normal/uv, per-face indices + material
+    std::vector<float> positions, normals, uvs;
+    std::vector<uint32_t> indices, materialOfTri;
+    // sphere
+    float centerRadius[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t sphereMaterial = 0;
+};
+
+struct CameraDesc {
+    float origin[3], target[3], up[3];
+    float verticalFov; // radians
+    int width, height;
+    bool flipHandedness;
+};
+
+struct EnvironmentDesc {
+    bool present = false;
+    std::string filename;
+    std::vector<float> rgba;
+    int width = 0, height = 0;
+    float scale = 1.f;
+    float mapToWorld[16], worldToMap[16];
+};
+
+struct SceneDescription {
+    std::vector<ptc_material_desc> materials;
+    std::vector<GeometryDesc> geometries; // index == Embree geomID
+    CameraDesc camera;
+    EnvironmentDesc environment;
+};
+
+// Table of the C-ABI scene-description entry points; lets the same feeder drive any library that
+// exports them (the product's libpathed_cuda.so; in tests also the CPU checker).
+struct SceneSink {
+    void *ctx;
+    int (*add_material)(void *, const ptc_material_desc *, uint32_t *);
+    int (*add_triangle_mesh)(void *, const float *, const float *, const float *, uint32_t, const uint32_t *,
+                             const uint32_t *, uint32_t, uint32_t *);
+    int (*add_sphere)(void *, const float *, uint32_t, uint32_t *);
+    int (*set_environment)(void *, const float *, int, int, float, const float *, const float *);
+    int (*set_camera)(void *, const float *, const float *, const float *, float, int, int, int);
+    int (*commit)(void *);
+};
+
+// returns the first non-zero status of the sink, 0 on success
+int feedScene(const SceneDescription &scene, const SceneSink &sink);
+
+} // namespace pathed
