@@ -1,0 +1,279 @@
+// Host BVH builder (see bvh.h): binned SAH binary tree -> greedy collapse to 8-wide -> compressed 80-byte nodes.
+#include "bvh.h"
+#include "traverse.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <queue>
+#include <stdexcept>
+#include <thread>
+
+namespace ptc {
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = 3.0e38f; hi[a] = -3.0e38f; } }
+    void grow(const float *p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box &b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float halfArea() const
+    {
+        const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return x < 0.f ? 0.f : x * y + y * z + z * x;
+    }
+};
+
+struct Node2 {
+    Box box;
+    uint32_t left = 0, right = 0; // children when count == 0
+    uint32_t first = 0, count = 0;
+};
+
+struct Builder {
+    const float *pos;
+    const uint32_t *idx;
+    std::vector<Box> primBox;
+    std::vector<float> centroid; // 3 per prim
+    std::vector<uint32_t> order;
+    std::vector<Node2> nodes;
+    std::atomic<uint32_t> nodeCount{0};
+    int maxThreads = 1;
+    std::atomic<int> activeThreads{1};
+
+    static constexpr int BINS = 16;
+    static constexpr uint32_t MAX_LEAF = 3;
+
+    uint32_t alloc() { return nodeCount.fetch_add(1); }
+
+    void build(uint32_t nodeIndex, uint32_t first, uint32_t count, int depth)
+    {
+        Node2 &node = nodes[nodeIndex];
+        node.box.reset();
+        Box cbox; cbox.reset();
+        for (uint32_t i = first; i < first + count; i++) {
+            node.box.grow(primBox[order[i]]);
+            cbox.grow(&centroid[3 * (size_t)order[i]]);
+        }
+        node.first = first; node.count = 0;
+        if (count == 1) { node.count = 1; return; }
+
+        // binned SAH over the three axes
+        float bestCost = 3.0e38f; int bestAxis = -1, bestBin = -1;
+        for (int axis = 0; axis < 3; axis++) {
+            const float lo = cbox.lo[axis], extent = cbox.hi[axis] - cbox.lo[axis];
+            if (!(extent > 0.f)) { continue; }
+            Box binBox[BINS]; uint32_t binCount[BINS];
+            for (int b = 0; b < BINS; b++) { binBox[b].reset(); binCount[b] = 0; }
+            const float scale = (float)BINS / extent;
+            for (uint32_t i = first; i < first + count; i++) {
+                const uint32_t p = order[i];
+                int b = (int)((centroid[3 * (size_t)p + axis] - lo) * scale);
+                b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+                binBox[b].grow(primBox[p]); binCount[b]++;
+            }
+            float rightArea[BINS]; uint32_t rightCount[BINS];
+            Box acc; acc.reset(); uint32_t n = 0;
+            for (int b = BINS - 1; b > 0; b--) { acc.grow(binBox[b]); n += binCount[b]; rightArea[b] = acc.halfArea(); rightCount[b] = n; }
+            acc.reset(); n = 0;
+            for (int b = 0; b < BINS - 1; b++) {
+                acc.grow(binBox[b]); n += binCount[b];
+                if (n == 0 || rightCount[b + 1] == 0) { continue; }
+                const float cost = acc.halfArea() * n + rightArea[b + 1] * rightCount[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+            }
+        }
+        // leaf when it is small enough and splitting does not pay (unit triangle cost, 1.0 per inner step)
+        if (count <= MAX_LEAF) {
+            const float leafCost = (float)count * node.box.halfArea();
+            if (bestAxis < 0 || bestCost + 1.0f * node.box.halfArea() >= leafCost) { node.count = count; return; }
+        }
+        uint32_t mid;
+        if (bestAxis < 0) {
+            mid = first + count / 2; // identical centroids: split by index
+        } else {
+            const float lo = cbox.lo[bestAxis], scale = (float)BINS / (cbox.hi[bestAxis] - cbox.lo[bestAxis]);
+            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
+                int b = (int)((centroid[3 * (size_t)p + bestAxis] - lo) * scale);
+                b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+                return b <= bestBin;
+            });
+            mid = (uint32_t)(it - order.begin());
+            if (mid == first || mid == first + count) { mid = first + count / 2; }
+        }
+        const uint32_t l = alloc(), r = alloc();
+        nodes[nodeIndex].left = l; nodes[nodeIndex].right = r;
+        const uint32_t leftCount = mid - first, rightCount = first + count - mid;
+        if (count > 16384 && activeThreads.load() < maxThreads) {
+            activeThreads.fetch_add(1);
+            std::thread worker([=]() { build(l, first, leftCount, depth + 1); activeThreads.fetch_sub(1); });
+            build(r, mid, rightCount, depth + 1);
+            worker.join();
+        } else {
+            build(l, first, leftCount, depth + 1);
+            build(r, mid, rightCount, depth + 1);
+        }
+    }
+};
+
+uint8_t exponentFor(float extent)
+{
+    // smallest power of two 2^e with 255 * 2^e >= extent
+    if (!(extent > 0.f)) { return 1; }
+    int e;
+    std::frexp(extent / 255.f, &e); // extent/255 = m * 2^e, m in [0.5, 1)  ->  2^e >= extent/255
+    int biased = e + 127;
+    if (biased < 1) { biased = 1; }
+    if (biased > 254) { biased = 254; }
+    return (uint8_t)biased;
+}
+
+} // namespace
+
+void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nPrims, WideBVH &out)
+{
+    out.nodes.clear(); out.triangles.clear(); out.maxDepth = 0;
+    for (int a = 0; a < 3; a++) { out.sceneLo[a] = 0.f; out.sceneHi[a] = 0.f; }
+    if (nPrims == 0) { return; }
+
+    Builder b;
+    b.pos = positions4; b.idx = indices4;
+    b.primBox.resize(nPrims); b.centroid.resize(3 * (size_t)nPrims); b.order.resize(nPrims);
+    for (uint32_t p = 0; p < nPrims; p++) {
+        Box box; box.reset();
+        for (int k = 0; k < 3; k++) { box.grow(positions4 + 4 * (size_t)indices4[4 * (size_t)p + k]); }
+        b.primBox[p] = box;
+        for (int a = 0; a < 3; a++) { b.centroid[3 * (size_t)p + a] = 0.5f * (box.lo[a] + box.hi[a]); }
+        b.order[p] = p;
+    }
+    b.nodes.resize(2 * (size_t)nPrims);
+    b.maxThreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t root = b.alloc();
+    b.build(root, 0, nPrims, 0);
+    for (int a = 0; a < 3; a++) { out.sceneLo[a] = b.nodes[root].box.lo[a]; out.sceneHi[a] = b.nodes[root].box.hi[a]; }
+
+    // ---- collapse to 8-wide, breadth first so that the inner children of a node are contiguous
+    struct Work { uint32_t wide, node2, depth; };
+    std::queue<Work> work;
+    out.nodes.emplace_back();
+    work.push({0u, root, 1u});
+    if (b.nodes[root].count) {
+        // a single-leaf scene still needs an inner root: wrap the leaf as its only child
+    }
+    while (!work.empty()) {
+        const Work w = work.front(); work.pop();
+        out.maxDepth = std::max(out.maxDepth, w.depth);
+        // gather up to 8 children: repeatedly open the inner child with the largest area
+        uint32_t child[8]; int n = 0;
+        const Node2 &self = b.nodes[w.node2];
+        if (self.count) { child[n++] = w.node2; }
+        else { child[n++] = self.left; child[n++] = self.right; }
+        while (n < 8) {
+            int best = -1; float bestArea = -1.f;
+            for (int i = 0; i < n; i++) {
+                const Node2 &c = b.nodes[child[i]];
+                if (c.count == 0 && c.box.halfArea() > bestArea) { bestArea = c.box.halfArea(); best = i; }
+            }
+            if (best < 0) { break; }
+            const Node2 &c = b.nodes[child[best]];
+            child[best] = c.left; child[n++] = c.right;
+        }
+        // slot assignment: child -> slot minimising (centroid - node centroid) . octant direction, greedily,
+        // so that visiting slots in (slot ^ ray octant) order approximates front-to-back
+        float center[3];
+        for (int a = 0; a < 3; a++) { center[a] = 0.5f * (self.box.lo[a] + self.box.hi[a]); }
+        float cost[8][8];
+        for (int c = 0; c < n; c++) {
+            const Box &cb = b.nodes[child[c]].box;
+            for (int s = 0; s < 8; s++) {
+                const float ds[3] = {(s & 4) ? -1.f : 1.f, (s & 2) ? -1.f : 1.f, (s & 1) ? -1.f : 1.f};
+                cost[c][s] = 0.f;
+                for (int a = 0; a < 3; a++) { cost[c][s] += (0.5f * (cb.lo[a] + cb.hi[a]) - center[a]) * ds[a]; }
+            }
+        }
+        int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false};
+        for (int c = 0; c < 8; c++) { slotOf[c] = -1; }
+        for (int round = 0; round < n; round++) {
+            float bestCost = 3.0e38f; int bc = -1, bs = -1;
+            for (int c = 0; c < n; c++) {
+                if (slotOf[c] >= 0) { continue; }
+                for (int s = 0; s < 8; s++) { if (!slotUsed[s] && cost[c][s] < bestCost) { bestCost = cost[c][s]; bc = c; bs = s; } }
+            }
+            slotOf[bc] = bs; slotUsed[bs] = true;
+        }
+        int childInSlot[8];
+        for (int s = 0; s < 8; s++) { childInSlot[s] = -1; }
+        for (int c = 0; c < n; c++) { childInSlot[slotOf[c]] = c; }
+
+        WideNode node;
+        memset(&node, 0, sizeof(node));
+        for (int a = 0; a < 3; a++) {
+            node.origin[a] = self.box.lo[a];
+            node.exponent[a] = exponentFor(self.box.hi[a] - self.box.lo[a]);
+        }
+        node.childBase = (uint32_t)out.nodes.size();
+        node.triBase = (uint32_t)out.triangles.size();
+        for (int s = 0; s < 8; s++) {
+            if (childInSlot[s] < 0) { continue; }
+            const uint32_t c2 = child[childInSlot[s]];
+            const Node2 &c = b.nodes[c2];
+            // quantise outwards and verify against the fp32 decode the kernels use
+            for (int a = 0; a < 3; a++) {
+                const float scale = u2f((uint32_t)node.exponent[a] << 23);
+                int qlo = (int)std::floor((c.box.lo[a] - node.origin[a]) / scale);
+                int qhi = (int)std::ceil((c.box.hi[a] - node.origin[a]) / scale);
+                qlo = std::max(0, std::min(255, qlo)); qhi = std::max(0, std::min(255, qhi));
+                while (qlo > 0 && node.origin[a] + (float)qlo * scale > c.box.lo[a]) { qlo--; }
+                while (qhi < 255 && node.origin[a] + (float)qhi * scale < c.box.hi[a]) { qhi++; }
+                uint8_t *lo = a == 0 ? node.qlox : (a == 1 ? node.qloy : node.qloz);
+                uint8_t *hi = a == 0 ? node.qhix : (a == 1 ? node.qhiy : node.qhiz);
+                lo[s] = (uint8_t)qlo; hi[s] = (uint8_t)qhi;
+            }
+            if (c.count == 0) {
+                node.imask |= (uint8_t)(1u << s);
+                node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                const uint32_t wideIndex = (uint32_t)out.nodes.size();
+                out.nodes.emplace_back();
+                work.push({wideIndex, c2, w.depth + 1});
+            } else {
+                const uint32_t offset = (uint32_t)out.triangles.size() - node.triBase;
+                const uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
+                node.meta[s] = (uint8_t)((unary << 5) | offset);
+                for (uint32_t i = 0; i < c.count; i++) {
+                    const uint32_t p = b.order[c.first + i];
+                    const float *v0 = positions4 + 4 * (size_t)indices4[4 * (size_t)p];
+                    const float *v1 = positions4 + 4 * (size_t)indices4[4 * (size_t)p + 1];
+                    const float *v2 = positions4 + 4 * (size_t)indices4[4 * (size_t)p + 2];
+                    LeafTriangle t;
+                    memset(&t, 0, sizeof(t));
+                    for (int a = 0; a < 3; a++) { t.v0[a] = v0[a]; t.e1[a] = v0[a] - v1[a]; t.e2[a] = v2[a] - v0[a]; }
+                    t.prim = p;
+                    out.triangles.push_back(t);
+                }
+            }
+        }
+        out.nodes[w.wide] = node;
+    }
+    if (out.maxDepth + 2 > PTC_STACK_SIZE) { throw std::runtime_error("BVH deeper than the traversal stack"); }
+}
+
+bool traverseReference(const WideBVH &bvh, const float o[3], const float d[3], float tnear, float tfar, bool anyHit,
+                       float *tOut, uint32_t *primOut, TraversalCounts *counts)
+{
+    BvhView view;
+    view.nodes = (const float4 *)bvh.nodes.data();
+    view.triangles = (const float4 *)bvh.triangles.data();
+    view.spheres = nullptr; view.nSpheres = 0; view.nNodes = (uint32_t)bvh.nodes.size();
+    RayHit hit; TraverseCounters c = {0, 0};
+    const bool found = anyHit ? traverseBVH<true, true>(view, o[0], o[1], o[2], d[0], d[1], d[2], tnear, tfar, hit, &c)
+                              : traverseBVH<false, true>(view, o[0], o[1], o[2], d[0], d[1], d[2], tnear, tfar, hit, &c);
+    if (tOut) { *tOut = hit.t; }
+    if (primOut) { *primOut = hit.prim; }
+    if (counts) { counts->innerVisits += c.inner; counts->triangleTests += c.tris; }
+    return found;
+}
+
+} // namespace ptc

@@ -1,0 +1,1046 @@
+// libpathed_cuda.so — sm_100a wavefront path tracer behind the C ABI of include/pathed_cuda.h.
+//
+// Wavefront stages per wave of P = pixels x spp_per_wave paths:
+//   generate  K1  camera rays (Camera::generateRay, src/camera.cpp:32-55) + path-state initialisation
+//   extend    K2  closest hit over the compressed 8-wide BVH (rtcIntersect1 via Scene::testIntersect)
+//   shadow    K3  any hit for the NEE shadow rays (rtcOccluded1 via Scene::testOcclusion)
+//   shade     K4/K5/K6  finalise the previous vertex's direct lighting (NEE + MIS'd BSDF hit), update the
+//             throughput, sample the BSDF at the new vertex, set up NEE, append to the next extend / shadow
+//             queues with warp-aggregated atomics (ballot + popc compaction)
+//   resolve   K7  sum the wave's per-sample radiance into the fp32 framebuffer in sample order
+// The MIS probe ray (src/path_tracer.cpp:175) and the continuation ray (:44) are the same ray: traced once.
+// All queue sizes live on the device; a wave is a fixed launch sequence with no host synchronisation.
+#include "bvh.h"
+#include "shading.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptc;
+
+// ================================================================================================ device state
+struct PathBuffers {
+    float4 *rayO, *rayD;   // current ray (origin = current vertex)
+    float4 *hit;           // t, u, v, prim bits
+    float4 *modPdf;        // modulation rgb, pdf of the BSDF sample that produced the ray
+    float4 *thrCos;        // BSDF sample throughput rgb, |n_s . wi|
+    float4 *result;        // L() accumulator rgb, w = flags
+    float4 *nee;           // pending light-sampling contribution (valid when the shadow ray is unoccluded)
+    float4 *shadowD;       // shadow ray direction, w = distance to the light sample
+    float4 *out;           // per-sample radiance: camera-hit emission / environment, plus result at termination
+    uint8_t *occluded;
+    uint32_t *extendQueue[2];
+    uint32_t *shadowQueue;
+};
+
+#define FLAG_BOUNCE_MASK 0xFFu
+#define FLAG_DELTA 0x100u
+#define FLAG_DIRECT 0x200u
+#define FLAG_NEE 0x400u
+
+struct WaveParams {
+    uint64_t seed;
+    uint32_t firstSample;  // global index of the first sample of this wave
+    uint32_t sppWave;      // samples per pixel in this wave
+    uint32_t nPixels;
+    int32_t startBounce, lastBounce;
+};
+
+// counters[0 .. MAXB+1]            extend queue sizes per bounce
+// counters[MAXB+2 .. 2*MAXB+3]     shadow queue sizes per bounce
+// counters[2*MAXB+4 ...]           work cursors, one per launch
+#define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
+#define CNT_TOTAL (CNT_STRIDE * 5)
+
+__device__ __forceinline__ uint32_t warpAppend(uint32_t *counter, bool pred)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred); // called by all 32 lanes of the (warp-uniform) work loop
+    if (!pred) { return 0xFFFFFFFFu; }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) { base = atomicAdd(counter, __popc(mask)); }
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// every warp pulls 32 items at a time from a global cursor: balances rays of very different cost (persistent warps)
+__device__ __forceinline__ bool fetchWork(uint32_t *cursor, uint32_t count, uint32_t &item)
+{
+    uint32_t base = 0;
+    if ((threadIdx.x & 31u) == 0) { base = atomicAdd(cursor, 32u); }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) { return false; }
+    item = base + (threadIdx.x & 31u);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 generate
+__global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers pb, WaveParams wp, uint32_t *counters)
+{
+    const uint32_t nPaths = wp.nPixels * wp.sppWave;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += gridDim.x * blockDim.x) {
+        const uint32_t pixel = p % wp.nPixels, s = p / wp.nPixels;
+        Rng rng;
+        rng.initPhilox(wp.seed, pixel, wp.firstSample + s);
+        rng.beginVertex(0);
+        const float jitterX = rng.next() - 0.5f; // box filter, src/camera.cpp:49-55
+        const float jitterY = rng.next() - 0.5f;
+        const int row = (int)(pixel / (uint32_t)scene.width), col = (int)(pixel % (uint32_t)scene.width);
+        V3 o, d;
+        cameraRay(scene, row + jitterY, col + jitterX, o, d);
+        pb.rayO[p] = make_float4(o.x, o.y, o.z, 0.f);
+        pb.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
+        pb.result[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        pb.extendQueue[0][p] = p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0] = nPaths; }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 extend / K3 shadow
+__global__ void __launch_bounds__(128) extendKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor)
+{
+    const uint32_t n = *count;
+    uint32_t item;
+    while (fetchWork(cursor, n, item)) {
+        if (item >= n) { continue; }
+        const uint32_t p = queue[item];
+        const float4 o = pb.rayO[p], d = pb.rayD[p];
+        RayHit hit;
+        traverseBVH<false, false>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR, hit, nullptr);
+        pb.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+    }
+}
+
+__global__ void __launch_bounds__(128) shadowKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor)
+{
+    const uint32_t n = *count;
+    uint32_t item;
+    while (fetchWork(cursor, n, item)) {
+        if (item >= n) { continue; }
+        const uint32_t p = queue[item];
+        const float4 o = pb.rayO[p], d = pb.shadowD[p];
+        RayHit hit;
+        // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
+        pb.occluded[p] = traverseBVH<true, false>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f, hit, nullptr) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4-K6 shade
+// One invocation handles the result of the ray that left vertex k (k = 0: the camera ray).
+__global__ void __launch_bounds__(128) shadeKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const uint32_t *count,
+                                                   uint32_t *cursor, uint32_t *nextQueue, uint32_t *nextCount, uint32_t *shadowCount)
+{
+    const uint32_t n = *count;
+    uint32_t item;
+    while (fetchWork(cursor, n, item)) {
+        const bool valid = item < n;
+        bool pushExtend = false, pushShadow = false;
+        uint32_t p = 0;
+        if (valid) {
+            p = queue[item];
+            const float4 o4 = pb.rayO[p], d4 = pb.rayD[p], h4 = pb.hit[p];
+            float4 res4 = pb.result[p];
+            const uint32_t flags = __float_as_uint(res4.w);
+            const int k = (int)(flags & FLAG_BOUNCE_MASK);
+            const V3 O = mk(o4.x, o4.y, o4.z), D = mk(d4.x, d4.y, d4.z);
+            RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+            const bool isHit = hit.prim != PTC_MISS;
+            Isect bi;
+            if (isHit) { makeIsect(scene, O, D, hit, bi); }
+            V3 result = mk(res4.x, res4.y, res4.z);
+            V3 modulation = mk(1.f, 1.f, 1.f);
+            bool alive = true;
+            if (k == 0) {
+                // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59
+                V3 color = mk(0.f, 0.f, 0.f);
+                if (!isHit) { color = envRadiance(scene, D); alive = false; }
+                else if (checkCounts(wp.startBounce, wp.lastBounce, 0)) {
+                    const DMaterial &m = scene.materials[bi.material];
+                    if (__ldg(&m.emitter) && !(dot(bi.n, bi.wo) < 0.f)) { color = mk(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2])); }
+                }
+                pb.out[p] = make_float4(color.x, color.y, color.z, 0.f);
+            } else {
+                const float4 mp = pb.modPdf[p], tc = pb.thrCos[p];
+                modulation = mk(mp.x, mp.y, mp.z);
+                const V3 thr = mk(tc.x, tc.y, tc.z);
+                if (flags & FLAG_DIRECT) { // direct() of vertex k, src/path_tracer.cpp:79-111
+                    V3 Ld = mk(0.f, 0.f, 0.f);
+                    if ((flags & FLAG_NEE) && !pb.occluded[p]) { const float4 ne = pb.nee[p]; Ld = Ld + mk(ne.x, ne.y, ne.z); }
+                    Ld = Ld + directBsdf(scene, O, tc.w, D, mp.w, thr, (flags & FLAG_DELTA) != 0, isHit, &bi);
+                    result = result + Ld * modulation;
+                }
+                // loop header and body of PathTracer::L, src/path_tracer.cpp:41-58
+                if (checkDone(wp.lastBounce, k + 1) || !isHit) { alive = false; }
+                else {
+                    const float invPDF = 1.f / mp.w;
+                    modulation = modulation * ((thr * tc.w) * invPDF);
+                    if (isBlack(modulation)) { alive = false; }
+                }
+            }
+            if (alive) {
+                const DMaterial &m = scene.materials[bi.material];
+                Rng rng;
+                rng.initPhilox(wp.seed, p % wp.nPixels, wp.firstSample + p / wp.nPixels);
+                rng.beginVertex((uint32_t)(k + 1));
+                BsdfSample bs;
+                bsdfSample(m, bi, rng, bs);
+                const bool wantDirect = checkCounts(wp.startBounce, wp.lastBounce, k + 1) && !__ldg(&m.emitter);
+                if (wantDirect) {
+                    V3 contribution, sd; float maxT;
+                    if (directLightsSetup(scene, m, bi, bs, rng, contribution, sd, maxT)) {
+                        pb.nee[p] = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
+                        pb.shadowD[p] = make_float4(sd.x, sd.y, sd.z, maxT);
+                        pushShadow = true;
+                    }
+                }
+                const bool wantNext = !checkDone(wp.lastBounce, k + 2);
+                if (wantDirect || wantNext) {
+                    pb.rayO[p] = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
+                    pb.rayD[p] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                    pb.modPdf[p] = make_float4(modulation.x, modulation.y, modulation.z, bs.pdf);
+                    pb.thrCos[p] = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
+                    const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u);
+                    pb.result[p] = make_float4(result.x, result.y, result.z, __uint_as_float(nf));
+                    pushExtend = true;
+                } else { alive = false; pushShadow = false; }
+            }
+            if (!alive) { // color += L(...), src/sample_integrator.cpp:53
+                const float4 c = pb.out[p];
+                pb.out[p] = make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f);
+            }
+        }
+        const uint32_t e = warpAppend(nextCount, pushExtend);
+        if (pushExtend) { nextQueue[e] = p; }
+        const uint32_t s = warpAppend(shadowCount, pushShadow);
+        if (pushShadow) { pb.shadowQueue[s] = p; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7 resolve
+__global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WaveParams wp, float *accum)
+{
+    for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < wp.nPixels; pixel += gridDim.x * blockDim.x) {
+        float r = accum[3 * (size_t)pixel], g = accum[3 * (size_t)pixel + 1], b = accum[3 * (size_t)pixel + 2];
+        for (uint32_t s = 0; s < wp.sppWave; s++) { // radianceLookup += color, one sample after the other (src/sample_integrator.cpp:61-63)
+            const float4 c = pb.out[(size_t)s * wp.nPixels + pixel];
+            r += c.x; g += c.y; b += c.z;
+        }
+        accum[3 * (size_t)pixel] = r; accum[3 * (size_t)pixel + 1] = g; accum[3 * (size_t)pixel + 2] = b;
+    }
+}
+
+__global__ void resolveKernel(const float *accum, float *out, uint32_t n, uint32_t spp) // src/integrator.cpp:74-85
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = accum[i] / (int)spp; }
+}
+
+__global__ void tallyKernel(const uint32_t *counters, unsigned long long *totals)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long closest = 0, shadow = 0;
+        for (int b = 0; b < CNT_STRIDE; b++) { closest += counters[b]; shadow += counters[CNT_STRIDE + b]; }
+        totals[0] += closest; totals[1] += shadow;
+    }
+}
+
+// ================================================================================================ probe kernels
+__global__ void intersectKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        RayHit h;
+        ptc_hit out;
+        if (traverseBVH<false, false>(scene.bvh, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], PTC_TNEAR, PTC_TFAR, h, nullptr)) {
+            Isect is; V3 ng;
+            makeIsect(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), h, is, &ng);
+            out.t = h.t; out.u = h.u; out.v = h.v; out.ng[0] = ng.x; out.ng[1] = ng.y; out.ng[2] = ng.z;
+            if (h.prim & PTC_SPHERE_FLAG) { out.geom_id = scene.sphereIds[h.prim & ~PTC_SPHERE_FLAG].x; out.prim_id = 0; }
+            else { const uint2 id = scene.primIds[h.prim]; out.geom_id = id.x; out.prim_id = id.y; }
+        } else {
+            out.t = PTC_TFAR; out.u = 0.f; out.v = 0.f; out.geom_id = PTC_INVALID_ID; out.prim_id = PTC_INVALID_ID; out.ng[0] = out.ng[1] = out.ng[2] = 0.f;
+        }
+        hits[i] = out;
+    }
+}
+
+__device__ __forceinline__ void exportIsect(const Isect &s, float t, ptc_isect &o)
+{
+    o.hit = 1; o.t = t;
+    o.point[0] = s.point.x; o.point[1] = s.point.y; o.point[2] = s.point.z;
+    o.wo[0] = s.wo.x; o.wo[1] = s.wo.y; o.wo[2] = s.wo.z;
+    o.normal[0] = s.n.x; o.normal[1] = s.n.y; o.normal[2] = s.n.z;
+    o.shading_normal[0] = s.ns.x; o.shading_normal[1] = s.ns.y; o.shading_normal[2] = s.ns.z;
+    o.uv[0] = s.u; o.uv[1] = s.v; o.material = s.material;
+}
+__device__ __forceinline__ void importIsect(const ptc_isect &p, Isect &s)
+{
+    s.point = mk(p.point[0], p.point[1], p.point[2]); s.wo = mk(p.wo[0], p.wo[1], p.wo[2]);
+    s.n = mk(p.normal[0], p.normal[1], p.normal[2]); s.ns = mk(p.shading_normal[0], p.shading_normal[1], p.shading_normal[2]);
+    s.u = p.uv[0]; s.v = p.uv[1]; s.material = p.material; s.prim = 0;
+    makeFrame(s.ns, s.wo, s.tx, s.tz);
+}
+
+__global__ void intersectFullKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_isect *out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        RayHit h;
+        ptc_isect o;
+        memset(&o, 0, sizeof(o));
+        if (traverseBVH<false, false>(scene.bvh, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], PTC_TNEAR, PTC_TFAR, h, nullptr)) {
+            Isect is;
+            makeIsect(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), h, is);
+            exportIsect(is, h.t, o);
+        } else { o.t = 3.402823466e+38f; o.material = PTC_INVALID_ID; }
+        out[i] = o;
+    }
+}
+
+__global__ void occludedKernel(DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        RayHit h;
+        occluded[i] = traverseBVH<true, false>(scene.bvh, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], PTC_TNEAR, maxT[i] - 1e-3f, h, nullptr) ? 1 : 0;
+    }
+}
+
+__global__ void cameraRaysKernel(DScene scene, const float *rowCol, uint32_t n, ptc_ray *rays)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 o, d;
+        cameraRay(scene, rowCol[2 * i], rowCol[2 * i + 1], o, d);
+        ptc_ray r; r.origin[0] = o.x; r.origin[1] = o.y; r.origin[2] = o.z; r.direction[0] = d.x; r.direction[1] = d.y; r.direction[2] = d.z;
+        rays[i] = r;
+    }
+}
+
+__global__ void bsdfEvalKernel(DScene scene, uint32_t material, const ptc_isect *isects, const float *wi, uint32_t n, float *f, float *pdf)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Isect s; importIsect(isects[i], s);
+        float p;
+        const V3 v = bsdfEval(scene.materials[material], s, mk(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), p);
+        f[3 * i] = v.x; f[3 * i + 1] = v.y; f[3 * i + 2] = v.z; pdf[i] = p;
+    }
+}
+
+__global__ void bsdfSampleKernel(DScene scene, uint32_t material, const ptc_isect *isects, const float *xi, uint32_t n, float *wi, float *pdf, float *thr)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Isect s; importIsect(isects[i], s);
+        Rng rng; rng.initReplay(xi + 3 * i, 3);
+        BsdfSample b;
+        bsdfSample(scene.materials[material], s, rng, b);
+        wi[3 * i] = b.wi.x; wi[3 * i + 1] = b.wi.y; wi[3 * i + 2] = b.wi.z; pdf[i] = b.pdf;
+        thr[3 * i] = b.thr.x; thr[3 * i + 1] = b.thr.y; thr[3 * i + 2] = b.thr.z;
+    }
+}
+
+__global__ void lightSampleKernel(DScene scene, const float *ref, const float *xi, uint32_t n, ptc_light_sample_t *out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3 p = mk(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]);
+        Rng rng; rng.initReplay(xi + 3 * i, 3);
+        SurfSample ls;
+        const DLight *l = sampleDirectLights(scene, p, rng, ls);
+        ptc_light_sample_t o;
+        o.point[0] = ls.point.x; o.point[1] = ls.point.y; o.point[2] = ls.point.z;
+        o.normal[0] = ls.normal.x; o.normal[1] = ls.normal.y; o.normal[2] = ls.normal.z;
+        o.inv_pdf = ls.invPDF; o.measure = ls.measure; o.solid_angle_pdf = solidAnglePdf(ls, p);
+        const V3 lwo = -normalize(ls.point - p);
+        const V3 e = l->kind == 2 ? envRadiance(scene, -lwo) : mk(l->emit[0], l->emit[1], l->emit[2]);
+        o.emit[0] = e.x; o.emit[1] = e.y; o.emit[2] = e.z;
+        out[i] = o;
+    }
+}
+
+__global__ void lightPdfKernel(DScene scene, const ptc_ray *rays, uint32_t n, float *pdf)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        const V3 O = mk(r.origin[0], r.origin[1], r.origin[2]), D = mk(r.direction[0], r.direction[1], r.direction[2]);
+        RayHit h;
+        if (traverseBVH<false, false>(scene.bvh, O.x, O.y, O.z, D.x, D.y, D.z, PTC_TNEAR, PTC_TFAR, h, nullptr)) {
+            Isect s; makeIsect(scene, O, D, h, s);
+            pdf[i] = scene.materials[s.material].emitter ? lightsPdf(scene, O, s) : -1.f;
+        } else if (scene.hasEnv && !isBlack(envRadiance(scene, D))) {
+            pdf[i] = -2.f - envPdf(scene, D) / (float)scene.nLights;
+        } else { pdf[i] = -1.f; }
+    }
+}
+
+__global__ void envRadianceKernel(DScene scene, const float *dirs, uint32_t n, float *rgb)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3 e = envRadiance(scene, mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        rgb[3 * i] = e.x; rgb[3 * i + 1] = e.y; rgb[3 * i + 2] = e.z;
+    }
+}
+
+// samplePixel body + PathTracer::L as one sequential loop per path (test hook for the replayed random stream);
+// uses the same device functions as the wavefront stages
+__global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        V3 O = mk(r.origin[0], r.origin[1], r.origin[2]), D = mk(r.direction[0], r.direction[1], r.direction[2]);
+        Rng rng; rng.initReplay(xi + (size_t)i * stride, stride);
+        V3 color = mk(0.f, 0.f, 0.f), result = mk(0.f, 0.f, 0.f), modulation = mk(1.f, 1.f, 1.f);
+        RayHit h;
+        Isect isect;
+        if (!traverseBVH<false, false>(scene.bvh, O.x, O.y, O.z, D.x, D.y, D.z, PTC_TNEAR, PTC_TFAR, h, nullptr)) {
+            color = envRadiance(scene, D);
+        } else {
+            makeIsect(scene, O, D, h, isect);
+            if (checkCounts(start, last, 0)) {
+                const DMaterial &m = scene.materials[isect.material];
+                if (m.emitter && !(dot(isect.n, isect.wo) < 0.f)) { color = mk(m.emit[0], m.emit[1], m.emit[2]); }
+            }
+            BsdfSample bs;
+            bsdfSample(scene.materials[isect.material], isect, rng, bs);
+            for (int bounce = 1;;) {
+                const DMaterial &m = scene.materials[isect.material];
+                const bool wantDirect = checkCounts(start, last, bounce) && !m.emitter;
+                V3 Ld = mk(0.f, 0.f, 0.f);
+                if (wantDirect) {
+                    V3 contribution, sd; float maxT;
+                    if (directLightsSetup(scene, m, isect, bs, rng, contribution, sd, maxT)) {
+                        RayHit sh;
+                        if (!traverseBVH<true, false>(scene.bvh, isect.point.x, isect.point.y, isect.point.z, sd.x, sd.y, sd.z, PTC_TNEAR, maxT - 1e-3f, sh, nullptr)) { Ld = Ld + contribution; }
+                    }
+                }
+                const bool wantNext = !checkDone(last, bounce + 1);
+                if (!wantDirect && !wantNext) { break; }
+                Isect bi;
+                const bool isHit = traverseBVH<false, false>(scene.bvh, isect.point.x, isect.point.y, isect.point.z, bs.wi.x, bs.wi.y, bs.wi.z, PTC_TNEAR, PTC_TFAR, h, nullptr);
+                if (isHit) { makeIsect(scene, isect.point, bs.wi, h, bi); }
+                const float cosT = fabsf(dot(isect.ns, bs.wi));
+                if (wantDirect) {
+                    Ld = Ld + directBsdf(scene, isect.point, cosT, bs.wi, bs.pdf, bs.thr, bs.delta, isHit, &bi);
+                    result = result + Ld * modulation;
+                }
+                if (!wantNext) { break; }
+                bounce++;
+                if (!isHit) { break; }
+                const float invPDF = 1.f / bs.pdf;
+                modulation = modulation * ((bs.thr * cosT) * invPDF);
+                if (isBlack(modulation)) { break; }
+                bsdfSample(scene.materials[bi.material], bi, rng, bs);
+                isect = bi;
+            }
+        }
+        rgb[3 * i] = color.x + result.x; rgb[3 * i + 1] = color.y + result.y; rgb[3 * i + 2] = color.z + result.z;
+    }
+}
+
+// ================================================================================================ host context
+struct HostGeometry {
+    bool isSphere = false;
+    uint32_t firstVertex = 0, firstPrim = 0, nPrims = 0;
+    float centerRadius[4] = {0, 0, 0, 0};
+    uint32_t sphereMaterial = 0;
+};
+
+struct ptc_ctx {
+    int device = 0;
+    std::string error;
+    bool committed = false;
+    // staging (host)
+    std::vector<ptc_material_desc> materials;
+    std::vector<float> positions4, normals4, uvs2;
+    std::vector<uint32_t> prims4, primIds2;
+    std::vector<HostGeometry> geometries;
+    bool hasEnv = false, hasCamera = false;
+    std::vector<float> envRgba; int envW = 0, envH = 0; float envScale = 1.f; float envM2W[16], envW2M[16];
+    float camToWorld[12]; float vfov = 0.f; int width = 0, height = 0;
+    WideBVH bvh;
+    uint32_t nLights = 0;
+    // device
+    std::vector<void *> allocations;
+    DScene scene;
+    PathBuffers paths; uint32_t pathCapacity = 0; std::vector<void *> pathAllocations;
+    uint32_t *counters = nullptr;
+    unsigned long long *totals = nullptr;
+    float *accumScratch = nullptr; size_t accumScratchSize = 0;
+    float *pinned = nullptr; size_t pinnedSize = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    int numSMs = 148;
+    int gridTraverse = 0, gridShade = 0, gridSimple = 0;
+    // options / stats
+    int64_t pathsPerWave = 1 << 21;
+    bool stageTiming = false;
+    uint64_t samples = 0, launches = 0;
+    float lastRenderMs = 0.f, traverseMs = 0.f, shadeMs = 0.f;
+};
+
+#define CTX_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->error = _b; return (code); } while (0)
+#define CUDA_TRY(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+
+template <typename T>
+static int upload(ptc_ctx *ctx, const T *src, size_t count, const T **dst, std::vector<void *> &track)
+{
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+    track.push_back(p);
+    if (count) { CUDA_TRY(ctx, cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice)); }
+    *dst = (const T *)p;
+    return PTC_OK;
+}
+
+extern "C" {
+
+int ptc_create(int device, ptc_ctx **out)
+{
+    if (!out) { return PTC_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        fprintf(stderr, "pathed_cuda: no CUDA device available; this library has no CPU fallback\n");
+        return PTC_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { return PTC_ERR_INVALID; }
+    if (cudaSetDevice(device) != cudaSuccess) { return PTC_ERR_CUDA; }
+    ptc_ctx *ctx = new ptc_ctx();
+    ctx->device = device;
+    memset(&ctx->scene, 0, sizeof(ctx->scene));
+    memset(&ctx->paths, 0, sizeof(ctx->paths));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { ctx->numSMs = prop.multiProcessorCount; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->counters, CNT_TOTAL * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->totals, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete ctx;
+        return PTC_ERR_CUDA;
+    }
+    cudaMemset(ctx->totals, 0, 2 * sizeof(unsigned long long));
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, extendKernel, 128, 0);
+    ctx->gridTraverse = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, 128, 0);
+    ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
+    ctx->gridSimple = ctx->numSMs * 8;
+    *out = ctx;
+    return PTC_OK;
+}
+
+void ptc_destroy(ptc_ctx *ctx)
+{
+    if (!ctx) { return; }
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void *p : ctx->allocations) { cudaFree(p); }
+    for (void *p : ctx->pathAllocations) { cudaFree(p); }
+    cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
+    if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
+    if (ctx->evStart) { cudaEventDestroy(ctx->evStart); }
+    if (ctx->evStop) { cudaEventDestroy(ctx->evStop); }
+    delete ctx;
+}
+
+const char *ptc_last_error(ptc_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *id)
+{
+    if (!ctx || !desc) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (desc->type < PTC_LAMBERTIAN || desc->type > PTC_PLASTIC) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented material type %d", desc->type); }
+    if ((desc->type == PTC_MICROFACET || desc->type == PTC_PLASTIC) && desc->distribution != PTC_BECKMANN && desc->distribution != PTC_GGX) {
+        CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented distribution %d", desc->distribution);
+    }
+    ctx->materials.push_back(*desc);
+    if (id) { *id = (uint32_t)ctx->materials.size() - 1; }
+    return PTC_OK;
+}
+
+int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *P, const float *N, const float *UV, uint32_t nv, const uint32_t *I,
+                          const uint32_t *mat, uint32_t nt, uint32_t *geomId)
+{
+    if (!ctx || (nv && !P) || (nt && (!I || !mat))) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    for (uint32_t t = 0; t < nt; t++) {
+        if (mat[t] >= ctx->materials.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "material id %u out of range", mat[t]); }
+        for (int k = 0; k < 3; k++) { if (I[3 * (size_t)t + k] >= nv) { CTX_FAIL(ctx, PTC_ERR_INVALID, "vertex index out of range in triangle %u", t); } }
+    }
+    HostGeometry g;
+    g.firstVertex = (uint32_t)(ctx->positions4.size() / 4);
+    g.firstPrim = (uint32_t)(ctx->prims4.size() / 4);
+    g.nPrims = nt;
+    const uint32_t geom = (uint32_t)ctx->geometries.size();
+    for (uint32_t v = 0; v < nv; v++) {
+        ctx->positions4.insert(ctx->positions4.end(), {P[3 * (size_t)v], P[3 * (size_t)v + 1], P[3 * (size_t)v + 2], 0.f});
+        if (N) { ctx->normals4.insert(ctx->normals4.end(), {N[3 * (size_t)v], N[3 * (size_t)v + 1], N[3 * (size_t)v + 2], 0.f}); }
+        else { ctx->normals4.insert(ctx->normals4.end(), {0.f, 0.f, 0.f, 0.f}); }
+        if (UV) { ctx->uvs2.insert(ctx->uvs2.end(), {UV[2 * (size_t)v], UV[2 * (size_t)v + 1]}); }
+        else { ctx->uvs2.insert(ctx->uvs2.end(), {0.f, 0.f}); }
+    }
+    for (uint32_t t = 0; t < nt; t++) {
+        ctx->prims4.insert(ctx->prims4.end(), {I[3 * (size_t)t] + g.firstVertex, I[3 * (size_t)t + 1] + g.firstVertex, I[3 * (size_t)t + 2] + g.firstVertex, mat[t]});
+        ctx->primIds2.insert(ctx->primIds2.end(), {geom, t});
+    }
+    ctx->geometries.push_back(g);
+    if (geomId) { *geomId = geom; }
+    return PTC_OK;
+}
+
+int ptc_add_sphere(ptc_ctx *ctx, const float cr[4], uint32_t material, uint32_t *geomId)
+{
+    if (!ctx || !cr) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (material >= ctx->materials.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "material id %u out of range", material); }
+    HostGeometry g;
+    g.isSphere = true; g.nPrims = 1; memcpy(g.centerRadius, cr, sizeof(g.centerRadius)); g.sphereMaterial = material;
+    ctx->geometries.push_back(g);
+    if (geomId) { *geomId = (uint32_t)ctx->geometries.size() - 1; }
+    return PTC_OK;
+}
+
+int ptc_set_environment(ptc_ctx *ctx, const float *rgba, int w, int h, float scale, const float m2w[16], const float w2m[16])
+{
+    if (!ctx || !rgba || w <= 0 || h <= 0 || !m2w || !w2m) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    ctx->envRgba.assign(rgba, rgba + (size_t)w * h * 4);
+    ctx->envW = w; ctx->envH = h; ctx->envScale = scale;
+    memcpy(ctx->envM2W, m2w, sizeof(ctx->envM2W)); memcpy(ctx->envW2M, w2m, sizeof(ctx->envW2M));
+    ctx->hasEnv = true;
+    return PTC_OK;
+}
+
+int ptc_set_camera(ptc_ctx *ctx, const float o[3], const float t[3], const float up[3], float vfov, int w, int h, int flip)
+{
+    if (!ctx || !o || !t || !up || w <= 0 || h <= 0) { return PTC_ERR_INVALID; }
+    // lookAt, src/transform.cpp:138-164 (host arithmetic in the reference's order)
+    auto norm = [](const float v[3], float out[3]) { const float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); out[0] = v[0] / n; out[1] = v[1] / n; out[2] = v[2] / n; };
+    auto crossp = [](const float a[3], const float b[3], float out[3]) { out[0] = (a[1] * b[2]) - (a[2] * b[1]); out[1] = (a[2] * b[0]) - (a[0] * b[2]); out[2] = (a[0] * b[1]) - (a[1] * b[0]); };
+    const float diff[3] = {o[0] - t[0], o[1] - t[1], o[2] - t[2]};
+    float dir[3], upn[3], xr[3], xa[3], ya[3];
+    norm(diff, dir);
+    if (dir[0] == up[0] && dir[1] == up[1] && dir[2] == up[2]) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Look direction cannot equal up vector"); }
+    norm(up, upn); crossp(upn, dir, xr); norm(xr, xa); crossp(dir, xa, ya);
+    const float sign = flip ? -1.f : 1.f;
+    const float m[12] = {sign * xa[0], ya[0], dir[0], o[0], sign * xa[1], ya[1], dir[1], o[1], sign * xa[2], ya[2], dir[2], o[2]};
+    memcpy(ctx->camToWorld, m, sizeof(m));
+    ctx->vfov = vfov; ctx->width = w; ctx->height = h; ctx->hasCamera = true;
+    if (ctx->committed) { // the camera may be re-aimed after commit
+        memcpy(ctx->scene.camToWorld, m, sizeof(m));
+        ctx->scene.vfov = vfov; ctx->scene.width = w; ctx->scene.height = h;
+    }
+    return PTC_OK;
+}
+
+// src/distribution.cpp:6-33
+static bool buildCdf(const float *values, int n, float *cdf)
+{
+    float sum = 0.f;
+    for (int i = 0; i < n; i++) { sum += values[i]; }
+    if (sum == 0.f) { for (int i = 0; i < n; i++) { cdf[i] = 0.f; } return true; }
+    for (int i = 0; i < n; i++) { cdf[i] = values[i] / sum; if (i > 0) { cdf[i] += cdf[i - 1]; } }
+    cdf[n - 1] = 1.f;
+    return false;
+}
+
+int ptc_commit(ptc_ctx *ctx)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (!ctx->hasCamera) { CTX_FAIL(ctx, PTC_ERR_STATE, "no camera set"); }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DScene &s = ctx->scene;
+    const uint32_t nPrims = (uint32_t)(ctx->prims4.size() / 4);
+
+    // rtcCommitScene: BVH over all triangle geometries; spheres are kept in a flat list
+    try { buildWideBVH(ctx->positions4.data(), ctx->prims4.data(), nPrims, ctx->bvh); }
+    catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
+
+    std::vector<DMaterial> dm(ctx->materials.size());
+    for (size_t i = 0; i < dm.size(); i++) {
+        const ptc_material_desc &d = ctx->materials[i];
+        DMaterial &m = dm[i];
+        memset(&m, 0, sizeof(m));
+        m.type = d.type; m.distribution = d.distribution; m.albedoKind = d.albedo_kind;
+        m.emitter = !(d.emit[0] == 0.f && d.emit[1] == 0.f && d.emit[2] == 0.f);
+        for (int c = 0; c < 3; c++) { m.diffuse[c] = d.diffuse[c]; m.emit[c] = d.emit[c]; m.on[c] = d.checker_on[c]; m.off[c] = d.checker_off[c]; }
+        const float sigma2 = d.sigma * d.sigma; // OrenNayar::OrenNayar, src/oren_nayar.cpp:11-19
+        m.sigmaA = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+        m.sigmaB = (0.45f * sigma2) / (sigma2 + 0.09f);
+        m.ior = d.ior; m.alpha = d.alpha; m.resU = d.checker_resolution[0]; m.resV = d.checker_resolution[1];
+    }
+
+    // light table: emissive surfaces in registration order, environment light last (src/scene_parser.cpp:173-190)
+    std::vector<DLight> lights;
+    std::vector<float> spheres4; std::vector<uint32_t> sphereIds2;
+    for (size_t g = 0; g < ctx->geometries.size(); g++) {
+        const HostGeometry &ge = ctx->geometries[g];
+        if (ge.isSphere) {
+            spheres4.insert(spheres4.end(), ge.centerRadius, ge.centerRadius + 4);
+            sphereIds2.insert(sphereIds2.end(), {(uint32_t)g, ge.sphereMaterial});
+            if (dm[ge.sphereMaterial].emitter) {
+                DLight l; memset(&l, 0, sizeof(l)); l.kind = 1;
+                memcpy(l.centerRadius, ge.centerRadius, sizeof(l.centerRadius));
+                for (int c = 0; c < 3; c++) { l.emit[c] = dm[ge.sphereMaterial].emit[c]; }
+                lights.push_back(l);
+            }
+            continue;
+        }
+        for (uint32_t p = ge.firstPrim; p < ge.firstPrim + ge.nPrims; p++) {
+            const uint32_t *ix = &ctx->prims4[4 * (size_t)p];
+            if (!dm[ix[3]].emitter) { continue; }
+            DLight l; memset(&l, 0, sizeof(l)); l.kind = 0;
+            for (int c = 0; c < 3; c++) {
+                l.p0[c] = ctx->positions4[4 * (size_t)ix[0] + c]; l.p1[c] = ctx->positions4[4 * (size_t)ix[1] + c]; l.p2[c] = ctx->positions4[4 * (size_t)ix[2] + c];
+                l.emit[c] = dm[ix[3]].emit[c];
+            }
+            lights.push_back(l);
+        }
+    }
+    if (ctx->hasEnv) { DLight l; memset(&l, 0, sizeof(l)); l.kind = 2; lights.push_back(l); }
+    ctx->nLights = (uint32_t)lights.size();
+
+    int rc;
+    auto &A = ctx->allocations;
+    if ((rc = upload(ctx, (const float4 *)ctx->bvh.nodes.data(), ctx->bvh.nodes.size() * 5, &s.bvh.nodes, A))) { return rc; }
+    if ((rc = upload(ctx, (const float4 *)ctx->bvh.triangles.data(), ctx->bvh.triangles.size() * 3, &s.bvh.triangles, A))) { return rc; }
+    if ((rc = upload(ctx, (const float4 *)spheres4.data(), spheres4.size() / 4, &s.bvh.spheres, A))) { return rc; }
+    s.bvh.nSpheres = (uint32_t)(spheres4.size() / 4);
+    s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
+    if ((rc = upload(ctx, (const float4 *)ctx->positions4.data(), ctx->positions4.size() / 4, &s.positions, A))) { return rc; }
+    if ((rc = upload(ctx, (const float4 *)ctx->normals4.data(), ctx->normals4.size() / 4, &s.normals, A))) { return rc; }
+    if ((rc = upload(ctx, (const float2 *)ctx->uvs2.data(), ctx->uvs2.size() / 2, &s.uvs, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint4 *)ctx->prims4.data(), ctx->prims4.size() / 4, &s.prims, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint2 *)ctx->primIds2.data(), ctx->primIds2.size() / 2, &s.primIds, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
+    if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }
+    if ((rc = upload(ctx, lights.data(), lights.size(), &s.lights, A))) { return rc; }
+    s.nLights = ctx->nLights;
+
+    s.hasEnv = ctx->hasEnv ? 1 : 0;
+    if (ctx->hasEnv) {
+        // EnvironmentLight::EnvironmentLight, src/environment_light.cpp:29-53: weight = R+G+B, no sin(theta) (Q9)
+        const int w = ctx->envW, h = ctx->envH;
+        std::vector<float> row(w), theta(h), phiCdf((size_t)w * h), thetaCdf(h);
+        std::vector<uint8_t> phiEmpty(h);
+        for (int t = 0; t < h; t++) {
+            float thetaSum = 0.f;
+            for (int p = 0; p < w; p++) {
+                const float *px = &ctx->envRgba[4 * ((size_t)t * w + p)];
+                float value = 0.f;
+                value += px[0]; value += px[1]; value += px[2];
+                thetaSum += value; row[p] = value;
+            }
+            phiEmpty[t] = buildCdf(row.data(), w, &phiCdf[(size_t)t * w]) ? 1 : 0;
+            theta[t] = thetaSum;
+        }
+        s.envThetaEmpty = buildCdf(theta.data(), h, thetaCdf.data()) ? 1 : 0;
+        if ((rc = upload(ctx, (const float4 *)ctx->envRgba.data(), (size_t)w * h, &s.envRgba, A))) { return rc; }
+        if ((rc = upload(ctx, thetaCdf.data(), thetaCdf.size(), &s.envThetaCdf, A))) { return rc; }
+        if ((rc = upload(ctx, phiCdf.data(), phiCdf.size(), &s.envPhiCdf, A))) { return rc; }
+        if ((rc = upload(ctx, phiEmpty.data(), phiEmpty.size(), &s.envPhiEmpty, A))) { return rc; }
+        s.envW = w; s.envH = h; s.envScale = ctx->envScale;
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 4; c++) { s.envM2W[4 * r + c] = ctx->envM2W[4 * r + c]; s.envW2M[4 * r + c] = ctx->envW2M[4 * r + c]; } }
+    }
+    memcpy(s.camToWorld, ctx->camToWorld, sizeof(s.camToWorld));
+    s.vfov = ctx->vfov; s.width = ctx->width; s.height = ctx->height;
+    ctx->committed = true;
+    return PTC_OK;
+}
+
+#define NEED_COMMIT(ctx) do { if (!(ctx)) { return PTC_ERR_INVALID; } if (!(ctx)->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene not committed"); } } while (0)
+
+static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
+{
+    if (capacity <= ctx->pathCapacity) { return PTC_OK; }
+    for (void *p : ctx->pathAllocations) { cudaFree(p); }
+    ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
+    PathBuffers &pb = ctx->paths;
+    float4 **f4[] = {&pb.rayO, &pb.rayD, &pb.hit, &pb.modPdf, &pb.thrCos, &pb.result, &pb.nee, &pb.shadowD, &pb.out};
+    for (float4 **slot : f4) {
+        CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(float4)));
+        ctx->pathAllocations.push_back(*slot);
+    }
+    CUDA_TRY(ctx, cudaMalloc((void **)&pb.occluded, capacity)); ctx->pathAllocations.push_back(pb.occluded);
+    uint32_t **u32[] = {&pb.extendQueue[0], &pb.extendQueue[1], &pb.shadowQueue};
+    for (uint32_t **slot : u32) {
+        CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(uint32_t)));
+        ctx->pathAllocations.push_back(*slot);
+    }
+    ctx->pathCapacity = capacity;
+    return PTC_OK;
+}
+
+// one wave = fixed launch sequence; all queue sizes stay on the device
+static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream)
+{
+    const DScene &s = ctx->scene;
+    PathBuffers &pb = ctx->paths;
+    uint32_t *cnt = ctx->counters;
+    uint32_t *cursors = cnt + 2 * CNT_STRIDE;
+    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_TOTAL * sizeof(uint32_t), stream));
+    const uint32_t nPaths = wp.nPixels * wp.sppWave;
+    generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    ctx->launches++;
+    // ray k leaves vertex k; rays are needed while direct lighting or continuation wants them
+    const int last = wp.lastBounce;
+    const int maxRay = last; // ray index k <= lastBounce: ray k feeds direct() of vertex k (k <= last) and vertex k+1 <= last
+    for (int k = 0; k <= maxRay; k++) {
+        uint32_t *queue = pb.extendQueue[k & 1], *next = pb.extendQueue[(k + 1) & 1];
+        extendKernel<<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k);
+        if (k > 0) { shadowKernel<<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1); }
+        shadeKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, cnt + k, cursors + 3 * k + 2, next, cnt + k + 1, cnt + CNT_STRIDE + k + 1);
+        ctx->launches += k > 0 ? 3 : 2;
+    }
+    accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice);
+    tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PTC_OK;
+}
+
+static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accumDevice, cudaStream_t stream)
+{
+    if (start < 0 || (last != -1 && start > last)) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bad bounce window [%d, %d]", start, last); }
+    if (last == -1 || last > PTC_MAX_BOUNCES) { last = PTC_MAX_BOUNCES; }
+    const uint32_t nPixels = (uint32_t)ctx->scene.width * (uint32_t)ctx->scene.height;
+    uint32_t sppWave = (uint32_t)std::max<int64_t>(1, ctx->pathsPerWave / (int64_t)nPixels);
+    sppWave = std::min(sppWave, std::max(nSpp, 1u));
+    int rc = ensurePathBuffers(ctx, nPixels * sppWave);
+    if (rc) { return rc; }
+    for (uint32_t done = 0; done < nSpp; done += sppWave) {
+        WaveParams wp;
+        wp.seed = seed; wp.firstSample = firstSample + done; wp.sppWave = std::min(sppWave, nSpp - done); wp.nPixels = nPixels;
+        wp.startBounce = start; wp.lastBounce = last;
+        if ((rc = launchWave(ctx, wp, accumDevice, stream))) { return rc; }
+    }
+    ctx->samples += (uint64_t)nPixels * nSpp;
+    return PTC_OK;
+}
+
+int ptc_render_device(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accumDevice, void *stream)
+{
+    NEED_COMMIT(ctx);
+    if (!accumDevice) { CTX_FAIL(ctx, PTC_ERR_INVALID, "null accumulation buffer"); }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return renderInternal(ctx, seed, firstSample, nSpp, start, last, accumDevice, (cudaStream_t)stream);
+}
+
+int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accum)
+{
+    NEED_COMMIT(ctx);
+    if (!accum) { CTX_FAIL(ctx, PTC_ERR_INVALID, "null accumulation buffer"); }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)3 * ctx->scene.width * ctx->scene.height;
+    if (ctx->accumScratchSize < n) {
+        cudaFree(ctx->accumScratch); ctx->accumScratch = nullptr;
+        if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; }
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->accumScratch, n * sizeof(float)));
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->pinned, n * sizeof(float)));
+        ctx->accumScratchSize = ctx->pinnedSize = n;
+    }
+    // radianceLookup is accumulated, not overwritten (src/sample_integrator.cpp:61-63): upload, add, download
+    memcpy(ctx->pinned, accum, n * sizeof(float));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->accumScratch, ctx->pinned, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->accumScratch, ctx->stream);
+    if (rc) { return rc; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->accumScratch, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->lastRenderMs, ctx->evStart, ctx->evStop);
+    memcpy(accum, ctx->pinned, n * sizeof(float));
+    return PTC_OK;
+}
+
+int ptc_resolve_device(ptc_ctx *ctx, const float *accum, float *out, uint32_t spp, void *stream)
+{
+    NEED_COMMIT(ctx);
+    if (!accum || !out || !spp) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bad resolve arguments"); }
+    const uint32_t n = 3u * (uint32_t)ctx->scene.width * (uint32_t)ctx->scene.height;
+    resolveKernel<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, (cudaStream_t)stream>>>(accum, out, n, spp);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PTC_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------ queries (host buffers)
+template <typename In, typename Out, typename Launch>
+static int roundTrip(ptc_ctx *ctx, const In *in, size_t nIn, Out *out, size_t nOut, Launch launch)
+{
+    In *dIn = nullptr; Out *dOut = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dIn, std::max<size_t>(nIn, 1) * sizeof(In)));
+    if (cudaMalloc((void **)&dOut, std::max<size_t>(nOut, 1) * sizeof(Out)) != cudaSuccess) { cudaFree(dIn); CTX_FAIL(ctx, PTC_ERR_NOMEM, "cudaMalloc failed"); }
+    cudaMemcpyAsync(dIn, in, nIn * sizeof(In), cudaMemcpyHostToDevice, ctx->stream);
+    launch(dIn, dOut);
+    ctx->launches++;
+    cudaMemcpyAsync(out, dOut, nOut * sizeof(Out), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    const cudaError_t e2 = cudaGetLastError();
+    cudaFree(dIn); cudaFree(dOut);
+    if (e != cudaSuccess || e2 != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); }
+    return PTC_OK;
+}
+static inline uint32_t gridFor(ptc_ctx *ctx, uint32_t n) { return std::max(1u, std::min<uint32_t>((n + 127) / 128, (uint32_t)ctx->gridSimple * 4)); }
+
+extern "C" {
+
+int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !hits)) { return PTC_ERR_INVALID; }
+    return roundTrip(ctx, rays, n, hits, n, [&](ptc_ray *d, ptc_hit *o) { intersectKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !out)) { return PTC_ERR_INVALID; }
+    return roundTrip(ctx, rays, n, out, n, [&](ptc_ray *d, ptc_isect *o) { intersectFullKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_occluded(ptc_ctx *ctx, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !maxT || !occluded)) { return PTC_ERR_INVALID; }
+    float *dT = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dT, std::max<size_t>(n, 1) * sizeof(float)));
+    cudaMemcpyAsync(dT, maxT, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, rays, n, occluded, n, [&](ptc_ray *d, uint8_t *o) { occludedKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dT, n, o); });
+    cudaFree(dT);
+    return rc;
+}
+int ptc_intersect_device(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits, void *stream)
+{
+    NEED_COMMIT(ctx);
+    intersectKernel<<<gridFor(ctx, n), 128, 0, (cudaStream_t)stream>>>(ctx->scene, rays, n, hits);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PTC_OK;
+}
+int ptc_occluded_device(ptc_ctx *ctx, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, void *stream)
+{
+    NEED_COMMIT(ctx);
+    occludedKernel<<<gridFor(ctx, n), 128, 0, (cudaStream_t)stream>>>(ctx->scene, rays, maxT, n, occluded);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PTC_OK;
+}
+int ptc_camera_rays(ptc_ctx *ctx, const float *rowCol, uint32_t n, ptc_ray *rays)
+{
+    NEED_COMMIT(ctx);
+    return roundTrip(ctx, rowCol, (size_t)2 * n, rays, n, [&](float *d, ptc_ray *o) { cameraRaysKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_bsdf_eval(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *wi, uint32_t n, float *f, float *pdf)
+{
+    NEED_COMMIT(ctx);
+    if (material >= ctx->materials.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "material id out of range"); }
+    float *dWi = nullptr, *dPdf = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dWi, std::max<size_t>(n, 1) * 3 * sizeof(float)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dPdf, std::max<size_t>(n, 1) * sizeof(float)));
+    cudaMemcpyAsync(dWi, wi, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, isects, n, f, (size_t)3 * n, [&](ptc_isect *d, float *o) { bsdfEvalKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, material, d, dWi, n, o, dPdf); });
+    if (!rc) { cudaMemcpy(pdf, dPdf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost); }
+    cudaFree(dWi); cudaFree(dPdf);
+    return rc;
+}
+int ptc_bsdf_sample(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *xi, uint32_t n, float *wi, float *pdf, float *thr)
+{
+    NEED_COMMIT(ctx);
+    if (material >= ctx->materials.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "material id out of range"); }
+    float *dXi = nullptr, *dPdf = nullptr, *dThr = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dXi, std::max<size_t>(n, 1) * 3 * sizeof(float)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dPdf, std::max<size_t>(n, 1) * sizeof(float)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dThr, std::max<size_t>(n, 1) * 3 * sizeof(float)));
+    cudaMemcpyAsync(dXi, xi, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, isects, n, wi, (size_t)3 * n, [&](ptc_isect *d, float *o) { bsdfSampleKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, material, d, dXi, n, o, dPdf, dThr); });
+    if (!rc) { cudaMemcpy(pdf, dPdf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost); cudaMemcpy(thr, dThr, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost); }
+    cudaFree(dXi); cudaFree(dPdf); cudaFree(dThr);
+    return rc;
+}
+int ptc_light_sample(ptc_ctx *ctx, const float *ref, const float *xi, uint32_t n, ptc_light_sample_t *out)
+{
+    NEED_COMMIT(ctx);
+    if (!ctx->nLights) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene has no lights"); }
+    float *dXi = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dXi, std::max<size_t>(n, 1) * 3 * sizeof(float)));
+    cudaMemcpyAsync(dXi, xi, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, ref, (size_t)3 * n, out, n, [&](float *d, ptc_light_sample_t *o) { lightSampleKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dXi, n, o); });
+    cudaFree(dXi);
+    return rc;
+}
+int ptc_light_pdf(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, float *pdf)
+{
+    NEED_COMMIT(ctx);
+    return roundTrip(ctx, rays, n, pdf, n, [&](ptc_ray *d, float *o) { lightPdfKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_environment_radiance(ptc_ctx *ctx, const float *dirs, uint32_t n, float *rgb)
+{
+    NEED_COMMIT(ctx);
+    return roundTrip(ctx, dirs, (size_t)3 * n, rgb, (size_t)3 * n, [&](float *d, float *o) { envRadianceKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
+{
+    NEED_COMMIT(ctx);
+    if (last == -1 || last > PTC_MAX_BOUNCES) { last = PTC_MAX_BOUNCES; }
+    float *dXi = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&dXi, std::max<size_t>((size_t)n * stride, 1) * sizeof(float)));
+    cudaMemcpyAsync(dXi, xi, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, rays, n, rgb, (size_t)3 * n, [&](ptc_ray *d, float *o) { radianceReplayKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dXi, stride, n, start, last, o); });
+    cudaFree(dXi);
+    return rc;
+}
+
+int ptc_num_lights(ptc_ctx *ctx, uint32_t *out) { NEED_COMMIT(ctx); *out = ctx->nLights; return PTC_OK; }
+
+int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
+{
+    if (!ctx || !out) { return PTC_ERR_INVALID; }
+    memset(out, 0, sizeof(*out));
+    unsigned long long totals[2] = {0, 0};
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(totals, ctx->totals, sizeof(totals), cudaMemcpyDeviceToHost);
+    out->closest_rays = totals[0]; out->shadow_rays = totals[1]; out->samples = ctx->samples; out->kernel_launches = ctx->launches;
+    out->bvh_nodes = ctx->bvh.nodes.size(); out->bvh_triangles = ctx->bvh.triangles.size();
+    out->bvh_bytes = ctx->bvh.nodes.size() * sizeof(WideNode) + ctx->bvh.triangles.size() * sizeof(LeafTriangle);
+    out->last_render_ms = ctx->lastRenderMs; out->traverse_ms = ctx->traverseMs; out->shade_ms = ctx->shadeMs;
+    return PTC_OK;
+}
+
+int ptc_reset_stats(ptc_ctx *ctx)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaMemset(ctx->totals, 0, 2 * sizeof(unsigned long long));
+    ctx->samples = 0; ctx->launches = 0; ctx->traverseMs = ctx->shadeMs = 0.f;
+    return PTC_OK;
+}
+
+int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) { return PTC_ERR_INVALID; }
+    if (!strcmp(name, "paths_per_wave")) { if (value < 1024) { CTX_FAIL(ctx, PTC_ERR_INVALID, "paths_per_wave must be >= 1024"); } ctx->pathsPerWave = value; return PTC_OK; }
+    if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
+    CTX_FAIL(ctx, PTC_ERR_INVALID, "unknown option %s", name);
+}
+
+int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner, uint64_t *tris)
+{
+    NEED_COMMIT(ctx);
+    TraversalCounts c;
+    for (uint32_t i = 0; i < n; i++) { traverseReference(ctx->bvh, rays[i].origin, rays[i].direction, PTC_TNEAR, PTC_TFAR, false, nullptr, nullptr, &c); }
+    if (inner) { *inner = c.innerVisits; }
+    if (tris) { *tris = c.triangleTests; }
+    return PTC_OK;
+}
+
+} // extern "C"

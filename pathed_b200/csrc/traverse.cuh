@@ -1,0 +1,229 @@
+// Single-ray traversal of the compressed 8-wide BVH: closest hit (rtcIntersect1) and any hit (rtcOccluded1).
+// Shared by the sm_100a kernels and by the host-side counting traversal (identical arithmetic, so the host
+// counts of inner-node visits / triangle tests are exactly what the kernels execute).
+//
+// Triangle test = Embree's Moeller-Trumbore in its exact operation order, including the fused multiply-adds
+// of its AVX2 build (ext/embree/kernels/geometry/triangle_intersector_moeller.h:75-113, common/math/vec3.h:216,221):
+// inclusive edge tests, |den|*tnear < T <= |den|*tfar, no back-face culling.
+// Sphere test = ext/embree/kernels/geometry/sphere_intersector.h:67-106.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PTC_HD __host__ __device__ __forceinline__
+#else
+#define PTC_HD inline
+#endif
+
+namespace ptc {
+
+PTC_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+PTC_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+PTC_HD uint32_t highestBit(uint32_t x) // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)x);
+#else
+    return 31u - (uint32_t)__builtin_clz(x);
+#endif
+}
+PTC_HD uint32_t popCount(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+PTC_HD float4 loadNodeWord(const float4 *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+struct BvhView {
+    const float4 *nodes;     // 5 float4 per node
+    const float4 *triangles; // 3 float4 per triangle
+    const float4 *spheres;   // center.xyz, radius
+    uint32_t nSpheres;
+    uint32_t nNodes;
+};
+
+#define PTC_SPHERE_FLAG 0x80000000u
+#define PTC_MISS 0xFFFFFFFFu
+
+struct RayHit {
+    float t, u, v;
+    uint32_t prim; // global triangle primitive, or PTC_SPHERE_FLAG | sphere slot, or PTC_MISS
+};
+
+// Embree's AVX2 Vec3 helpers: dot = madd chain, cross = msub
+PTC_HD float edot(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(ax, bx, fmaf(ay, by, az * bz)); }
+
+PTC_HD bool triangleTest(const float4 a, const float4 b, const float4 c, float ox, float oy, float oz, float dx, float dy,
+                         float dz, float tnear, float tfar, float &t, float &u, float &v)
+{
+    // a = (v0, prim), b = (e1 = v0 - v1), c = (e2 = v2 - v0); Ng = e2 x e1
+    const float ngx = fmaf(c.y, b.z, -(c.z * b.y)), ngy = fmaf(c.z, b.x, -(c.x * b.z)), ngz = fmaf(c.x, b.y, -(c.y * b.x));
+    const float cx = a.x - ox, cy = a.y - oy, cz = a.z - oz;
+    const float rx = fmaf(cy, dz, -(cz * dy)), ry = fmaf(cz, dx, -(cx * dz)), rz = fmaf(cx, dy, -(cy * dx));
+    const float den = edot(ngx, ngy, ngz, dx, dy, dz);
+    const float absDen = fabsf(den);
+    const uint32_t sgn = f2u(den) & 0x80000000u;
+    const float U = u2f(f2u(edot(rx, ry, rz, c.x, c.y, c.z)) ^ sgn);
+    const float V = u2f(f2u(edot(rx, ry, rz, b.x, b.y, b.z)) ^ sgn);
+    if (!(den != 0.f && U >= 0.f && V >= 0.f && U + V <= absDen)) { return false; }
+    const float T = u2f(f2u(edot(ngx, ngy, ngz, cx, cy, cz)) ^ sgn);
+    if (!(absDen * tnear < T && T <= absDen * tfar)) { return false; }
+    t = T / absDen; u = U / absDen; v = V / absDen;
+    return true;
+}
+
+PTC_HD bool sphereTest(const float4 s, float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar,
+                       float &t, float &ngx, float &ngy, float &ngz)
+{
+    const float rd2 = 1.f / edot(dx, dy, dz, dx, dy, dz);
+    const float c0x = s.x - ox, c0y = s.y - oy, c0z = s.z - oz;
+    const float projC0 = edot(c0x, c0y, c0z, dx, dy, dz) * rd2;
+    const float px = c0x - dx * projC0, py = c0y - dy * projC0, pz = c0z - dz * projC0;
+    const float l2 = edot(px, py, pz, px, py, pz);
+    const float r2 = s.w * s.w;
+    if (!(l2 <= r2)) { return false; }
+    float td = sqrtf((r2 - l2) * rd2);
+    const float tIn = projC0 - td, tOut = projC0 + td;
+    const bool validIn = (tIn > tnear) && (tIn < tfar);
+    const bool validOut = !validIn && (tOut > tnear) && (tOut < tfar);
+    if (!validIn && !validOut) { return false; }
+    if (validIn) { td = -1.0f * td; }
+    t = validIn ? tIn : tOut;
+    ngx = dx * td - px; ngy = dy * td - py; ngz = dz * td - pz;
+    return true;
+}
+
+struct TraverseCounters { uint32_t inner, tris; };
+
+#define PTC_STACK_SIZE 40
+
+// ANY: return at the first accepted hit.  On return hit.t holds the closest t (or the input tfar on a miss).
+template <bool ANY, bool COUNT>
+PTC_HD bool traverseBVH(const BvhView &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tnear,
+                        float tfar, RayHit &hit, TraverseCounters *counters)
+{
+    hit.t = tfar; hit.u = 0.f; hit.v = 0.f; hit.prim = PTC_MISS;
+    bool found = false;
+
+    if (bvh.nNodes) {
+        // reciprocal direction; zero components are nudged so that 0 * inf never appears in the slab test
+        const float eps = 1e-30f;
+        const float idx = 1.f / (fabsf(dx) > eps ? dx : (f2u(dx) & 0x80000000u ? -eps : eps));
+        const float idy = 1.f / (fabsf(dy) > eps ? dy : (f2u(dy) & 0x80000000u ? -eps : eps));
+        const float idz = 1.f / (fabsf(dz) > eps ? dz : (f2u(dz) & 0x80000000u ? -eps : eps));
+        const uint32_t octInv = 7u - ((dx < 0.f ? 4u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 1u : 0u));
+        const uint32_t octInv4 = octInv * 0x01010101u;
+
+        uint2 stack[PTC_STACK_SIZE];
+        int sp = 0;
+        uint2 ngroup = make_uint2(0u, 0x80000000u); // root = slot (7 ^ octInv) of a virtual parent with no siblings
+        for (;;) {
+            uint2 tgroup;
+            if (ngroup.y & 0xFF000000u) {
+                const uint32_t hitsImask = ngroup.y;
+                const uint32_t childBit = highestBit(hitsImask);
+                ngroup.y &= ~(1u << childBit);
+                if ((ngroup.y & 0xFF000000u) && sp < PTC_STACK_SIZE) { stack[sp++] = ngroup; }
+                const uint32_t slot = (childBit - 24u) ^ octInv;
+                const uint32_t relative = popCount(hitsImask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+                const float4 *node = bvh.nodes + (size_t)(ngroup.x + relative) * 5;
+                const float4 n0 = loadNodeWord(node + 0), n1 = loadNodeWord(node + 1), n2 = loadNodeWord(node + 2),
+                             n3 = loadNodeWord(node + 3), n4 = loadNodeWord(node + 4);
+                if (COUNT) { counters->inner++; }
+                const uint32_t e = f2u(n0.w);
+                const float ax = u2f((e & 0xFFu) << 23) * idx, ay = u2f(((e >> 8) & 0xFFu) << 23) * idy,
+                            az = u2f(((e >> 16) & 0xFFu) << 23) * idz;
+                const float bx = (n0.x - ox) * idx, by = (n0.y - oy) * idy, bz = (n0.z - oz) * idz;
+                ngroup.x = f2u(n1.x);
+                tgroup.x = f2u(n1.y);
+                uint32_t hitmask = 0;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+                    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                    const uint32_t innerMask4 = ((isInner4 >> 4) & 0x01010101u) * 0xFFu;
+                    const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1F1F1F1Fu;
+                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                    const uint32_t qlox = f2u(half ? n2.y : n2.x), qloy = f2u(half ? n2.w : n2.z), qloz = f2u(half ? n3.y : n3.x);
+                    const uint32_t qhix = f2u(half ? n3.w : n3.z), qhiy = f2u(half ? n4.y : n4.x), qhiz = f2u(half ? n4.w : n4.z);
+                    const uint32_t xmin = dx < 0.f ? qhix : qlox, xmax = dx < 0.f ? qlox : qhix;
+                    const uint32_t ymin = dy < 0.f ? qhiy : qloy, ymax = dy < 0.f ? qloy : qhiy;
+                    const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int sh = 8 * j;
+                        const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), ax, bx), t1x = fmaf((float)((xmax >> sh) & 0xFFu), ax, bx);
+                        const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), ay, by), t1y = fmaf((float)((ymax >> sh) & 0xFFu), ay, by);
+                        const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), az, bz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), az, bz);
+                        const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear));
+                        const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, hit.t)) * 1.0000004f;
+                        if (tmin <= tmax) { hitmask |= ((childBits4 >> sh) & 0xFFu) << ((bitIndex4 >> sh) & 0xFFu); }
+                    }
+                }
+                ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
+                tgroup.y = hitmask & 0x00FFFFFFu;
+            } else {
+                tgroup = ngroup;
+                ngroup = make_uint2(0u, 0u);
+            }
+            while (tgroup.y) {
+                const uint32_t bit = highestBit(tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                const float4 *tri = bvh.triangles + (size_t)(tgroup.x + bit) * 3;
+                const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
+                if (COUNT) { counters->tris++; }
+                float t, u, v;
+                if (triangleTest(a, b, c, ox, oy, oz, dx, dy, dz, tnear, hit.t, t, u, v)) {
+                    const uint32_t prim = f2u(a.w);
+                    // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
+                    if (!(found && t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; }
+                    found = true;
+                    if (ANY) { return true; }
+                }
+            }
+            if (!(ngroup.y & 0xFF000000u)) {
+                if (sp == 0) { break; }
+                ngroup = stack[--sp];
+            }
+        }
+    }
+    // spheres: a handful per scene (mis-pbrt: 5), tested linearly after the mesh BVH; strict depth test
+    for (uint32_t s = 0; s < bvh.nSpheres; s++) {
+        float t, nx, ny, nz;
+        if (sphereTest(loadNodeWord(bvh.spheres + s), ox, oy, oz, dx, dy, dz, tnear, hit.t, t, nx, ny, nz)) {
+            hit.t = t; hit.u = 0.f; hit.v = 0.f; hit.prim = PTC_SPHERE_FLAG | s;
+            found = true;
+            if (ANY) { return true; }
+        }
+    }
+    return found;
+}
+
+} // namespace ptc
