@@ -1,0 +1,304 @@
+#!/usr/bin/env python3
+"""Benchmark of the path-tracing hot path (BASELINE.json: Msamples/s and Mrays/s vs the host-CPU Embree path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dragon|cornell|...]
+
+Workload (config.workload): scenes/dragon.json, 1024 x 1024, PathTracer, startBounce 0, lastBounce 10 — the
+configuration the north-star target is quoted on (">= 100x the reference CPU Msamples/s on dragon.json on 1 B200").
+One step = one pass of the hot path over one batch = SPP_PER_STEP samples per pixel over the whole image
+(16 spp -> 16.8 M samples; 16 steps = the config's 256 spp).  Synthetic data: the dragon mesh and the environment
+map are seeded procedural stand-ins (tools/make_assets.py) because the reference's assets/ are not in its repo.
+
+Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + synchronize on both sides):
+  value     ptc_render_device: framebuffer resident in HBM, no host traffic in the timed region
+  e2e       ptc_render: the reference-facing call with a HOST radianceLookup buffer (H2D + D2H of the fp32
+            framebuffer inside the timed region), i.e. what Integrator::run's sampleImage loop would call
+  roofline  the extend (closest-hit traversal) kernel: algorithmic bytes per launch from counted node visits and
+            triangle tests / mean launch duration measured live with CUDA events on the launch stream
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
+L2: every wave streams its path state (2 M paths x 148 B = 310 MB, plus queues) through each stage, more than the
+126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~50 MB) is meant to be L2-resident.
+
+Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
+indices of every pixel, Philox-keyed by (pixel, sample, bounce)); per step one NCCL reduce of the fp32 framebuffer to
+rank 0.  Per-GPU work is fixed as N grows ("weak").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "dragon": dict(scene="scenes/dragon.json", width=1024, height=1024, last_bounce=10),
+    "cornell": dict(scene="scenes/cornell.json", width=512, height=512, last_bounce=10),
+    "cornell-glass": dict(scene="scenes/cornell-glass.json", width=512, height=512, last_bounce=10),
+    "mis-pbrt": dict(scene="scenes/mis-pbrt.json", width=768, height=512, last_bounce=10),
+    "teapot": dict(scene="scenes/teapot.json", width=1920, height=1080, last_bounce=10),
+}
+SPP_PER_STEP = 16
+REF_SPP_PER_STEP = 1  # the CPU reference does ~0.5 Msamples/s: one spp of 1024^2 is ~2 s
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
+
+
+def run_reference(workload, steps, warmup, spp_per_step=REF_SPP_PER_STEP):
+    """Times the UNMODIFIED reference renderer (Embree + PathTracer, OpenMP over the host cores)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "pathed_ref_headless")
+    if not os.path.exists(binary):
+        return None
+    w = WORKLOADS[workload]
+    with tempfile.TemporaryDirectory() as tmp:
+        def job(name, spp):
+            path = os.path.join(tmp, name + ".json")
+            json.dump({"spp": spp, "integrator": "PathTracer", "scene": w["scene"], "startBounce": 0, "lastBounce": w["last_bounce"],
+                       "output_directory": os.path.join(tmp, name), "showUI": False, "force": True,
+                       "width": w["width"], "height": w["height"], "output_name": name}, open(path, "w"))
+            return path
+        cmd = [binary, "--root", ROOT, job("timed", steps * spp_per_step)]
+        if warmup > 0:
+            cmd += ["--warmup", job("warmup", warmup * spp_per_step)]
+        out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("REF_RESULT")][-1]
+    r = json.loads(line[len("REF_RESULT "):])
+    r["spp_per_step"] = spp_per_step
+    return r
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload]
+    r = run_reference(args.workload, args.steps, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pathed_ref_headless is not built"}))
+        return 0
+    value = r["msamples_per_s"]
+    sample = "%d spp of %dx%d (%d steps x %d spp), %d OpenMP threads" % (r["spp"], w["width"], w["height"], args.steps, r["spp_per_step"], r["threads"])
+    print(json.dumps({
+        "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["render_wall_s"] * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], w["width"], w["height"], w["last_bounce"]),
+                   "spp_per_step": r["spp_per_step"]},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": r["threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dragon", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    if rank == 0:
+        __graft_entry__.build()
+    if distributed:
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+
+    from pathed_b200 import load_scene
+    w = WORKLOADS[args.workload]
+    width, height, last = w["width"], w["height"], w["last_bounce"]
+    spp = args.spp_per_step
+    t0 = time.time()
+    ctx = load_scene(w["scene"], width, height, device=local_rank)
+    build_s = time.time() - t0
+    n_pix = width * height
+    accum = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    seed = 0x5EED
+
+    def step_device(i):
+        # global sample indices of this step: [i*world*spp, (i+1)*world*spp); this rank takes its contiguous block
+        first = (i * world + rank) * spp
+        ctx.render_device(seed, first, spp, 0, last, accum.data_ptr(), stream)
+        if distributed:
+            dist.reduce(accum, dst=0)
+
+    def timed(fn, steps):
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device="cuda")
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: device-resident framebuffer
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step_device, args.steps)
+    st = ctx.stats()
+    launches = int(st.kernel_launches)
+    rays = int(st.closest_rays + st.shadow_rays)
+    samples_total = float(n_pix) * spp * args.steps * world
+    value = samples_total / (ms * 1e-3) * 1e-6
+
+    # ---- e2e: host radianceLookup through ptc_render (H2D + D2H of the framebuffer inside the timed region)
+    host_accum = np.zeros((height, width, 3), np.float32)
+
+    def step_host(i):
+        ctx.render(seed, (i * world + rank) * spp, spp, 0, last, accum=host_accum)
+
+    for i in range(3):
+        step_host(i)
+    if distributed:
+        dist.barrier()
+    t_start = time.perf_counter()
+    e2e_device_ms = 0.0
+    for i in range(args.steps):
+        step_host(i)
+        e2e_device_ms += ctx.stats().last_render_ms
+    e2e_wall_ms = (time.perf_counter() - t_start) * 1e3
+    e2e_ms = torch.tensor([max(e2e_wall_ms, e2e_device_ms)], device="cuda")
+    if distributed:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = samples_total / (float(e2e_ms.item()) * 1e-3) * 1e-6
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel (extend), rank 0 only: stage-timed pass, then counted pass (same seed)
+    roofline, stages = None, None
+    if rank == 0:
+        peak, peak_note = measured_peak()
+        ctx.set_option("stage_timing", 1)
+        ctx.reset_stats()
+        for i in range(args.steps):
+            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+        tst = ctx.stats()
+        ctx.set_option("stage_timing", 0)
+        ctx.set_option("count_traversal", 1)
+        ctx.reset_stats()
+        count_steps = min(args.steps, 2)
+        for i in range(count_steps):
+            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+        cst = ctx.stats()
+        ctx.set_option("count_traversal", 0)
+        # algorithmic bytes per extend ray: 32 B ray + 16 B hit record + 80 B per inner node + 48 B per triangle test
+        per_ray = 32 + 16 + (80.0 * cst.extend_inner_visits + 48.0 * cst.extend_triangle_tests) / max(cst.closest_rays, 1)
+        extend_rays_per_launch = tst.closest_rays / max(tst.extend_launches, 1)
+        bytes_per_launch = per_ray * extend_rays_per_launch
+        ms_per_launch = tst.extend_ms / max(tst.extend_launches, 1)
+        achieved = bytes_per_launch / (ms_per_launch * 1e-3) * 1e-9
+        total_stage = tst.extend_ms + tst.shadow_ms + tst.shade_ms + tst.other_ms
+        roofline = {"bound": "hbm", "kernel": "extendKernel (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+                    "bytes_per_ray": per_ray, "inner_visits_per_ray": cst.extend_inner_visits / max(cst.closest_rays, 1),
+                    "triangle_tests_per_ray": cst.extend_triangle_tests / max(cst.closest_rays, 1),
+                    "rays_per_launch": extend_rays_per_launch, "ms_per_launch": ms_per_launch,
+                    "note": "algorithmic bytes: the BVH (%.1f MB) is L2-resident, so this exceeds DRAM traffic" % (tst.bvh_bytes / 1e6)}
+        stages = {"extend_ms": tst.extend_ms, "shadow_ms": tst.shadow_ms, "shade_ms": tst.shade_ms, "other_ms": tst.other_ms,
+                  "extend_share": tst.extend_ms / max(total_stage, 1e-9), "extend_grays_per_s": tst.closest_rays / max(tst.extend_ms, 1e-9) * 1e-6,
+                  "shadow_grays_per_s": tst.shadow_rays / max(tst.shadow_ms, 1e-9) * 1e-6}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_reference(args.workload, steps=8, warmup=1)
+        if r is not None:
+            cpu = {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": r["threads"], "kind": "reference",
+                   "sample": "%d spp of %dx%d after 1 warm-up spp, unmodified reference + Embree 3.6.0, %d OpenMP threads, %.1f s"
+                             % (r["spp"], width, height, r["threads"], r["render_wall_s"])}
+
+    if rank == 0:
+        fb_bytes = n_pix * 3 * 4
+        line = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], width, height, last), "spp_per_step": spp,
+                       "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, 1 << 21) * 148 / 1e6, max(1, n_pix * spp >> 21)),
+                       "scene_build_s": build_s},
+            "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes},
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -112,9 +112,14 @@ typedef struct ptc_stats {
     uint64_t bvh_nodes;
     uint64_t bvh_triangles;
     uint64_t bvh_bytes;
-    float last_render_ms; /* device time of the last ptc_render* call (CUDA events) */
-    float traverse_ms;    /* of which: extend + shadow kernels (only when stage timing is enabled) */
-    float shade_ms;
+    /* traversal work counters, filled while option "count_traversal" is on (same code path as the scalar
+     * reference traversal of ptc_count_traversal; SURVEY.md 8(d): algorithmic bytes per ray) */
+    uint64_t extend_inner_visits, extend_triangle_tests;
+    uint64_t shadow_inner_visits, shadow_triangle_tests;
+    /* per-stage device time (CUDA events on the launching stream), filled while option "stage_timing" is on */
+    uint64_t extend_launches, shadow_launches, shade_launches;
+    float extend_ms, shadow_ms, shade_ms, other_ms;
+    float last_render_ms; /* device time of the last ptc_render call (CUDA events, copies included) */
 } ptc_stats;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -199,7 +204,7 @@ int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint
 int ptc_num_lights(ptc_ctx *ctx, uint32_t *out); /* Scene::lights().size() */
 int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out);
 int ptc_reset_stats(ptc_ctx *ctx);
-int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "paths_per_wave" */
+int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave" */
 /* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
  * visits and triangle tests per ray (algorithmic bytes per ray) */
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);

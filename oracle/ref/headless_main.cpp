@@ -4,7 +4,10 @@
 // Adds: --root DIR (the reference chdir("..")s into its repo root, main.cpp:60),
 // wall-clock timing around Integrator::run, optional fp32 dump of the final image.
 //
-//   pathed_ref_headless --root DIR job.json [--raw out.f32]
+//   pathed_ref_headless --root DIR job.json [--raw out.f32] [--warmup warmup_job.json]
+//
+// --warmup runs Integrator::run once with another job file (same scene and resolution, fewer spp) before the
+// timed run, for bench.py's warm-up steps.
 //
 // The raw dump is Image::m_raw as the reference stores it: 3*W*H floats, RGB,
 // scanline 0 = TOP of the image (Image::set flips, src/image.cpp:21-26).
@@ -42,10 +45,11 @@ RTCScene g_rtcScene;
 
 int main(int argc, char *argv[])
 {
-    std::string root = ".", jobPath = "job.json", rawPath;
+    std::string root = ".", jobPath = "job.json", rawPath, warmupPath;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--root") && i + 1 < argc) { root = argv[++i]; }
         else if (!strcmp(argv[i], "--raw") && i + 1 < argc) { rawPath = argv[++i]; }
+        else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) { warmupPath = argv[++i]; }
         else { jobPath = argv[i]; }
     }
 
@@ -74,11 +78,22 @@ int main(int argc, char *argv[])
     std::shared_ptr<Integrator> integrator = g_job->integrator();
 
     bool quit = false;
+    if (!warmupPath.empty()) {
+        std::ifstream warmupFile(warmupPath);
+        if (!warmupFile) { fprintf(stderr, "cannot open warm-up job %s\n", warmupPath.c_str()); return 1; }
+        Job *timedJob = g_job;
+        g_job = new Job(warmupFile);
+        g_job->init();
+        Image scratch(width, height);
+        g_job->integrator()->run(scratch, scene, [](RenderStatus) {}, &quit);
+        g_job = timedJob;
+    }
+    const auto tr = std::chrono::steady_clock::now();
     integrator->run(image, scene, [](RenderStatus) {}, &quit);
     const auto t2 = std::chrono::steady_clock::now();
 
     const double buildS = std::chrono::duration<double>(t1 - t0).count();
-    const double renderS = std::chrono::duration<double>(t2 - t1).count();
+    const double renderS = std::chrono::duration<double>(t2 - tr).count();
     const double samples = double(width) * height * g_job->spp();
 
     if (!rawPath.empty()) {

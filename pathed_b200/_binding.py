@@ -27,10 +27,14 @@ class MaterialDesc(ctypes.Structure):
 
 
 class Stats(ctypes.Structure):
-    _fields_ = [("closest_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64), ("samples", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint64), ("bvh_nodes", ctypes.c_uint64), ("bvh_triangles", ctypes.c_uint64),
-                ("bvh_bytes", ctypes.c_uint64), ("last_render_ms", ctypes.c_float), ("traverse_ms", ctypes.c_float),
-                ("shade_ms", ctypes.c_float)]
+    _fields_ = [(n, ctypes.c_uint64) for n in ("closest_rays", "shadow_rays", "samples", "kernel_launches", "bvh_nodes",
+                                               "bvh_triangles", "bvh_bytes", "extend_inner_visits", "extend_triangle_tests",
+                                               "shadow_inner_visits", "shadow_triangle_tests", "extend_launches",
+                                               "shadow_launches", "shade_launches")] + \
+               [(n, ctypes.c_float) for n in ("extend_ms", "shadow_ms", "shade_ms", "other_ms", "last_render_ms")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("direction", np.float32, 3)])

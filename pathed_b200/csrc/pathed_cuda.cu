@@ -103,32 +103,48 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
 }
 
 // ------------------------------------------------------------------------------------------------ K2 extend / K3 shadow
-__global__ void __launch_bounds__(128) extendKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor)
+__device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigned long long *work)
+{
+    uint32_t inner = c.inner, tris = c.tris;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { inner += __shfl_xor_sync(0xFFFFFFFFu, inner, o); tris += __shfl_xor_sync(0xFFFFFFFFu, tris, o); }
+    if ((threadIdx.x & 31u) == 0) { atomicAdd(work, (unsigned long long)inner); atomicAdd(work + 1, (unsigned long long)tris); }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) extendKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
+                                                    unsigned long long *work)
 {
     const uint32_t n = *count;
     uint32_t item;
+    TraverseCounters tc = {0, 0};
     while (fetchWork(cursor, n, item)) {
         if (item >= n) { continue; }
         const uint32_t p = queue[item];
         const float4 o = pb.rayO[p], d = pb.rayD[p];
         RayHit hit;
-        traverseBVH<false, false>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR, hit, nullptr);
+        traverseBVH<false, COUNT>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR, hit, &tc);
         pb.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
     }
+    if (COUNT) { flushCounters(tc, work); }
 }
 
-__global__ void __launch_bounds__(128) shadowKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) shadowKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
+                                                    unsigned long long *work)
 {
     const uint32_t n = *count;
     uint32_t item;
+    TraverseCounters tc = {0, 0};
     while (fetchWork(cursor, n, item)) {
         if (item >= n) { continue; }
         const uint32_t p = queue[item];
         const float4 o = pb.rayO[p], d = pb.shadowD[p];
         RayHit hit;
         // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
-        pb.occluded[p] = traverseBVH<true, false>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f, hit, nullptr) ? 1 : 0;
+        pb.occluded[p] = traverseBVH<true, COUNT>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f, hit, &tc) ? 1 : 0;
     }
+    if (COUNT) { flushCounters(tc, work); }
 }
 
 // ------------------------------------------------------------------------------------------------ K4-K6 shade
@@ -476,9 +492,47 @@ struct ptc_ctx {
     int gridTraverse = 0, gridShade = 0, gridSimple = 0;
     // options / stats
     int64_t pathsPerWave = 1 << 21;
-    bool stageTiming = false;
+    bool stageTiming = false, countTraversal = false;
     uint64_t samples = 0, launches = 0;
-    float lastRenderMs = 0.f, traverseMs = 0.f, shadeMs = 0.f;
+    float lastRenderMs = 0.f;
+    // stage timing: CUDA events on the launching stream around every launch, summed per kernel class
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> pending;
+    std::vector<cudaEvent_t> eventPool;
+    double stageMs[4] = {0, 0, 0, 0};
+    uint64_t stageLaunches[4] = {0, 0, 0, 0};
+};
+
+enum { STAGE_EXTEND = 0, STAGE_SHADOW = 1, STAGE_SHADE = 2, STAGE_OTHER = 3 };
+
+static cudaEvent_t takeEvent(ptc_ctx *ctx)
+{
+    if (!ctx->eventPool.empty()) { cudaEvent_t e = ctx->eventPool.back(); ctx->eventPool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+static void collectTimings(ptc_ctx *ctx)
+{
+    for (const ptc_ctx::Timed &t : ctx->pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(t.b);
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        ctx->stageMs[t.kind] += ms; ctx->stageLaunches[t.kind]++;
+        ctx->eventPool.push_back(t.a); ctx->eventPool.push_back(t.b);
+    }
+    ctx->pending.clear();
+}
+struct StageTimer { // brackets one launch when stage timing is on
+    ptc_ctx *ctx; cudaStream_t stream; cudaEvent_t a = nullptr; int kind;
+    StageTimer(ptc_ctx *c, cudaStream_t s, int k) : ctx(c), stream(s), kind(k)
+    {
+        if (ctx->stageTiming) { a = takeEvent(ctx); cudaEventRecord(a, stream); }
+    }
+    ~StageTimer()
+    {
+        if (a) { cudaEvent_t b = takeEvent(ctx); cudaEventRecord(b, stream); ctx->pending.push_back({a, b, kind}); }
+    }
 };
 
 #define CTX_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->error = _b; return (code); } while (0)
@@ -518,13 +572,13 @@ int ptc_create(int device, ptc_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess ||
         cudaMalloc((void **)&ctx->counters, CNT_TOTAL * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->totals, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc((void **)&ctx->totals, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return PTC_ERR_CUDA;
     }
-    cudaMemset(ctx->totals, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(ctx->totals, 0, 6 * sizeof(unsigned long long));
     int perSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, extendKernel, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, extendKernel<false>, 128, 0);
     ctx->gridTraverse = ctx->numSMs * std::max(perSM, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, 128, 0);
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
@@ -545,6 +599,8 @@ void ptc_destroy(ptc_ctx *ctx)
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
     if (ctx->evStart) { cudaEventDestroy(ctx->evStart); }
     if (ctx->evStop) { cudaEventDestroy(ctx->evStop); }
+    collectTimings(ctx);
+    for (cudaEvent_t e : ctx->eventPool) { cudaEventDestroy(e); }
     delete ctx;
 }
 
@@ -786,21 +842,39 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     uint32_t *cursors = cnt + 2 * CNT_STRIDE;
     CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_TOTAL * sizeof(uint32_t), stream));
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
-    generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    unsigned long long *work = ctx->totals + 2;
+    {
+        StageTimer t(ctx, stream, STAGE_OTHER);
+        generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    }
     ctx->launches++;
-    // ray k leaves vertex k; rays are needed while direct lighting or continuation wants them
-    const int last = wp.lastBounce;
-    const int maxRay = last; // ray index k <= lastBounce: ray k feeds direct() of vertex k (k <= last) and vertex k+1 <= last
-    for (int k = 0; k <= maxRay; k++) {
+    // ray k leaves vertex k (k = 0: camera ray).  Ray k feeds direct() of vertex k and creates vertex k + 1, so rays
+    // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
+    for (int k = 0; k <= wp.lastBounce; k++) {
         uint32_t *queue = pb.extendQueue[k & 1], *next = pb.extendQueue[(k + 1) & 1];
-        extendKernel<<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k);
-        if (k > 0) { shadowKernel<<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1); }
-        shadeKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, cnt + k, cursors + 3 * k + 2, next, cnt + k + 1, cnt + CNT_STRIDE + k + 1);
+        {
+            StageTimer t(ctx, stream, STAGE_EXTEND);
+            if (ctx->countTraversal) { extendKernel<true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
+            else { extendKernel<false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
+        }
+        if (k > 0) {
+            StageTimer t(ctx, stream, STAGE_SHADOW);
+            if (ctx->countTraversal) { shadowKernel<true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
+            else { shadowKernel<false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
+        }
+        {
+            StageTimer t(ctx, stream, STAGE_SHADE);
+            shadeKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, cnt + k, cursors + 3 * k + 2, next, cnt + k + 1, cnt + CNT_STRIDE + k + 1);
+        }
         ctx->launches += k > 0 ? 3 : 2;
     }
-    accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice);
-    tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+    {
+        StageTimer t(ctx, stream, STAGE_OTHER);
+        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice);
+        tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+    }
     ctx->launches += 2;
+    if (ctx->pending.size() > 4096) { collectTimings(ctx); }
     CUDA_TRY(ctx, cudaGetLastError());
     return PTC_OK;
 }
@@ -1004,14 +1078,21 @@ int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
 {
     if (!ctx || !out) { return PTC_ERR_INVALID; }
     memset(out, 0, sizeof(*out));
-    unsigned long long totals[2] = {0, 0};
+    unsigned long long totals[6] = {0, 0, 0, 0, 0, 0};
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    collectTimings(ctx);
     cudaMemcpy(totals, ctx->totals, sizeof(totals), cudaMemcpyDeviceToHost);
     out->closest_rays = totals[0]; out->shadow_rays = totals[1]; out->samples = ctx->samples; out->kernel_launches = ctx->launches;
+    out->extend_inner_visits = totals[2]; out->extend_triangle_tests = totals[3];
+    out->shadow_inner_visits = totals[4]; out->shadow_triangle_tests = totals[5];
     out->bvh_nodes = ctx->bvh.nodes.size(); out->bvh_triangles = ctx->bvh.triangles.size();
     out->bvh_bytes = ctx->bvh.nodes.size() * sizeof(WideNode) + ctx->bvh.triangles.size() * sizeof(LeafTriangle);
-    out->last_render_ms = ctx->lastRenderMs; out->traverse_ms = ctx->traverseMs; out->shade_ms = ctx->shadeMs;
+    out->extend_launches = ctx->stageLaunches[STAGE_EXTEND]; out->shadow_launches = ctx->stageLaunches[STAGE_SHADOW];
+    out->shade_launches = ctx->stageLaunches[STAGE_SHADE];
+    out->extend_ms = (float)ctx->stageMs[STAGE_EXTEND]; out->shadow_ms = (float)ctx->stageMs[STAGE_SHADOW];
+    out->shade_ms = (float)ctx->stageMs[STAGE_SHADE]; out->other_ms = (float)ctx->stageMs[STAGE_OTHER];
+    out->last_render_ms = ctx->lastRenderMs;
     return PTC_OK;
 }
 
@@ -1020,8 +1101,10 @@ int ptc_reset_stats(ptc_ctx *ctx)
     if (!ctx) { return PTC_ERR_INVALID; }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaMemset(ctx->totals, 0, 2 * sizeof(unsigned long long));
-    ctx->samples = 0; ctx->launches = 0; ctx->traverseMs = ctx->shadeMs = 0.f;
+    collectTimings(ctx);
+    cudaMemset(ctx->totals, 0, 6 * sizeof(unsigned long long));
+    ctx->samples = 0; ctx->launches = 0;
+    for (int i = 0; i < 4; i++) { ctx->stageMs[i] = 0; ctx->stageLaunches[i] = 0; }
     return PTC_OK;
 }
 
@@ -1030,6 +1113,7 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) { return PTC_ERR_INVALID; }
     if (!strcmp(name, "paths_per_wave")) { if (value < 1024) { CTX_FAIL(ctx, PTC_ERR_INVALID, "paths_per_wave must be >= 1024"); } ctx->pathsPerWave = value; return PTC_OK; }
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
+    if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
     CTX_FAIL(ctx, PTC_ERR_INVALID, "unknown option %s", name);
 }
 
