@@ -57,6 +57,16 @@ struct WaveParams {
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
 #define CNT_TOTAL (CNT_STRIDE * 5)
 
+// Path slot q of a wave -> pixel.  Slots are laid out in 8x4 pixel tiles so that the 32 camera rays of a warp (and the
+// secondary rays they spawn) stay spatially coherent; falls back to row-major when the image is not tileable.
+__device__ __forceinline__ uint32_t slotToPixel(uint32_t q, uint32_t width, uint32_t height)
+{
+    if ((width & 7u) || (height & 3u)) { return q; }
+    const uint32_t tile = q >> 5, within = q & 31u, tilesX = width >> 3;
+    const uint32_t col = (tile % tilesX) * 8u + (within & 7u), row = (tile / tilesX) * 4u + (within >> 3);
+    return row * width + col;
+}
+
 __device__ __forceinline__ uint32_t warpAppend(uint32_t *counter, bool pred)
 {
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred); // called by all 32 lanes of the (warp-uniform) work loop
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += gridDim.x * blockDim.x) {
-        const uint32_t pixel = p % wp.nPixels, s = p / wp.nPixels;
+        const uint32_t pixel = slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), s = p / wp.nPixels;
         Rng rng;
         rng.initPhilox(wp.seed, pixel, wp.firstSample + s);
         rng.beginVertex(0);
@@ -111,38 +121,61 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
     if ((threadIdx.x & 31u) == 0) { atomicAdd(work, (unsigned long long)inner); atomicAdd(work + 1, (unsigned long long)tris); }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) extendKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
-                                                    unsigned long long *work)
-{
-    const uint32_t n = *count;
-    uint32_t item;
-    TraverseCounters tc = {0, 0};
-    while (fetchWork(cursor, n, item)) {
-        if (item >= n) { continue; }
-        const uint32_t p = queue[item];
-        const float4 o = pb.rayO[p], d = pb.rayD[p];
-        RayHit hit;
-        traverseBVH<false, COUNT>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR, hit, &tc);
-        pb.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
-    }
-    if (COUNT) { flushCounters(tc, work); }
-}
+// Persistent warps with lane refill: every lane owns one ray; when a ray finishes its lane goes idle, and once at most
+// PTC_REFILL_BELOW lanes are still busy the warp pulls new rays for all idle lanes from the queue cursor with a single
+// atomic.  Keeps SIMT lanes busy although rays take very different numbers of steps (sky rays: 2-3, mesh rays: 20+).
+#ifndef PTC_REFILL_BELOW
+#define PTC_REFILL_BELOW 24
+#endif
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) shadowKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
-                                                    unsigned long long *work)
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
+                                                      unsigned long long *work)
 {
     const uint32_t n = *count;
-    uint32_t item;
+    const uint32_t lane = threadIdx.x & 31u;
     TraverseCounters tc = {0, 0};
-    while (fetchWork(cursor, n, item)) {
-        if (item >= n) { continue; }
-        const uint32_t p = queue[item];
-        const float4 o = pb.rayO[p], d = pb.shadowD[p];
-        RayHit hit;
-        // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
-        pb.occluded[p] = traverseBVH<true, COUNT>(scene.bvh, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f, hit, &tc) ? 1 : 0;
+    TraversalState st;
+    bool busy = false, more = n > 0;
+    uint32_t p = 0;
+    const bool hasNodes = scene.bvh.nNodes != 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (idle && more) {
+            const uint32_t k = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) { base = atomicAdd(cursor, k); }
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!busy) {
+                const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
+                if (item < n) {
+                    p = queue[item];
+                    const float4 o = pb.rayO[p];
+                    if (ANY) { // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
+                        const float4 d = pb.shadowD[p];
+                        traversalInit(st, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f);
+                    } else {   // Scene::testIntersect, src/scene.cpp:91-120
+                        const float4 d = pb.rayD[p];
+                        traversalInit(st, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR);
+                    }
+                    busy = true;
+                }
+            }
+            more = base + k < n;
+        }
+        if (!__any_sync(0xFFFFFFFFu, busy)) { break; }
+        for (;;) {
+            if (busy) {
+                if (!hasNodes || traversalStep<ANY, COUNT>(scene.bvh, st, &tc)) {
+                    const bool found = traversalSpheres<ANY>(scene.bvh, st);
+                    if (ANY) { pb.occluded[p] = found ? 1 : 0; }
+                    else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
+                    busy = false;
+                }
+            }
+            const uint32_t active = __ballot_sync(0xFFFFFFFFu, busy);
+            if (active == 0u || (more && __popc(active) <= PTC_REFILL_BELOW)) { break; }
+        }
     }
     if (COUNT) { flushCounters(tc, work); }
 }
@@ -202,7 +235,7 @@ __global__ void __launch_bounds__(128) shadeKernel(DScene scene, PathBuffers pb,
             if (alive) {
                 const DMaterial &m = scene.materials[bi.material];
                 Rng rng;
-                rng.initPhilox(wp.seed, p % wp.nPixels, wp.firstSample + p / wp.nPixels);
+                rng.initPhilox(wp.seed, slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + p / wp.nPixels);
                 rng.beginVertex((uint32_t)(k + 1));
                 BsdfSample bs;
                 bsdfSample(m, bi, rng, bs);
@@ -239,15 +272,16 @@ __global__ void __launch_bounds__(128) shadeKernel(DScene scene, PathBuffers pb,
 }
 
 // ------------------------------------------------------------------------------------------------ K7 resolve
-__global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WaveParams wp, float *accum)
+__global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WaveParams wp, float *accum, uint32_t width, uint32_t height)
 {
-    for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < wp.nPixels; pixel += gridDim.x * blockDim.x) {
-        float r = accum[3 * (size_t)pixel], g = accum[3 * (size_t)pixel + 1], b = accum[3 * (size_t)pixel + 2];
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < wp.nPixels; q += gridDim.x * blockDim.x) {
+        const size_t pixel = slotToPixel(q, width, height);
+        float r = accum[3 * pixel], g = accum[3 * pixel + 1], b = accum[3 * pixel + 2];
         for (uint32_t s = 0; s < wp.sppWave; s++) { // radianceLookup += color, one sample after the other (src/sample_integrator.cpp:61-63)
-            const float4 c = pb.out[(size_t)s * wp.nPixels + pixel];
+            const float4 c = pb.out[(size_t)s * wp.nPixels + q];
             r += c.x; g += c.y; b += c.z;
         }
-        accum[3 * (size_t)pixel] = r; accum[3 * (size_t)pixel + 1] = g; accum[3 * (size_t)pixel + 2] = b;
+        accum[3 * pixel] = r; accum[3 * pixel + 1] = g; accum[3 * pixel + 2] = b;
     }
 }
 
@@ -578,7 +612,7 @@ int ptc_create(int device, ptc_ctx **out)
     }
     cudaMemset(ctx->totals, 0, 6 * sizeof(unsigned long long));
     int perSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, extendKernel<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (traverseKernel<false, false>), 128, 0);
     ctx->gridTraverse = ctx->numSMs * std::max(perSM, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, 128, 0);
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
@@ -854,13 +888,13 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         uint32_t *queue = pb.extendQueue[k & 1], *next = pb.extendQueue[(k + 1) & 1];
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
-            if (ctx->countTraversal) { extendKernel<true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
-            else { extendKernel<false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
+            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
+            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
         }
         if (k > 0) {
             StageTimer t(ctx, stream, STAGE_SHADOW);
-            if (ctx->countTraversal) { shadowKernel<true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
-            else { shadowKernel<false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
+            if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
+            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
@@ -870,7 +904,7 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     }
     {
         StageTimer t(ctx, stream, STAGE_OTHER);
-        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice);
+        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height);
         tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
     }
     ctx->launches += 2;

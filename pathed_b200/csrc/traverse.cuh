@@ -124,105 +124,134 @@ struct TraverseCounters { uint32_t inner, tris; };
 
 #define PTC_STACK_SIZE 40
 
+// Per-ray traversal state: lets a kernel interleave single steps of many rays (persistent warps that refill idle lanes)
+// while the per-ray visiting order stays exactly the one of the plain loop below.
+struct TraversalState {
+    float ox, oy, oz, dx, dy, dz, idx, idy, idz, tnear;
+    uint32_t octInv;
+    uint2 ngroup;
+    int sp;
+    bool found;
+    RayHit hit;
+    uint2 stack[PTC_STACK_SIZE];
+};
+
+PTC_HD void traversalInit(TraversalState &st, float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar)
+{
+    st.ox = ox; st.oy = oy; st.oz = oz; st.dx = dx; st.dy = dy; st.dz = dz; st.tnear = tnear;
+    // reciprocal direction; zero components are nudged so that 0 * inf never appears in the slab test
+    const float eps = 1e-30f;
+    st.idx = 1.f / (fabsf(dx) > eps ? dx : (f2u(dx) & 0x80000000u ? -eps : eps));
+    st.idy = 1.f / (fabsf(dy) > eps ? dy : (f2u(dy) & 0x80000000u ? -eps : eps));
+    st.idz = 1.f / (fabsf(dz) > eps ? dz : (f2u(dz) & 0x80000000u ? -eps : eps));
+    st.octInv = 7u - ((dx < 0.f ? 4u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 1u : 0u));
+    st.ngroup = make_uint2(0u, 0x80000000u); // root = slot (7 ^ octInv) of a virtual parent with no siblings
+    st.sp = 0;
+    st.found = false;
+    st.hit.t = tfar; st.hit.u = 0.f; st.hit.v = 0.f; st.hit.prim = PTC_MISS;
+}
+
+// One step = visit one inner node (8 quantised child boxes), test the triangles of its leaf children that were hit,
+// pop the next node group.  Returns true when the BVH part of the traversal is finished (ANY: or a hit was found).
+template <bool ANY, bool COUNT>
+PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
+{
+    uint2 ngroup = st.ngroup;
+    uint2 tgroup;
+    {
+        const uint32_t octInv4 = st.octInv * 0x01010101u;
+        const uint32_t hitsImask = ngroup.y;
+        const uint32_t childBit = highestBit(hitsImask);
+        ngroup.y &= ~(1u << childBit);
+        if ((ngroup.y & 0xFF000000u) && st.sp < PTC_STACK_SIZE) { st.stack[st.sp++] = ngroup; }
+        const uint32_t slot = (childBit - 24u) ^ st.octInv;
+        const uint32_t relative = popCount(hitsImask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const float4 *node = bvh.nodes + (size_t)(ngroup.x + relative) * 5;
+        const float4 n0 = loadNodeWord(node + 0), n1 = loadNodeWord(node + 1), n2 = loadNodeWord(node + 2),
+                     n3 = loadNodeWord(node + 3), n4 = loadNodeWord(node + 4);
+        if (COUNT) { counters->inner++; }
+        const uint32_t e = f2u(n0.w);
+        const float ax = u2f((e & 0xFFu) << 23) * st.idx, ay = u2f(((e >> 8) & 0xFFu) << 23) * st.idy,
+                    az = u2f(((e >> 16) & 0xFFu) << 23) * st.idz;
+        const float bx = (n0.x - st.ox) * st.idx, by = (n0.y - st.oy) * st.idy, bz = (n0.z - st.oz) * st.idz;
+        ngroup.x = f2u(n1.x);
+        tgroup.x = f2u(n1.y);
+        uint32_t hitmask = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+            const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t innerMask4 = ((isInner4 >> 4) & 0x01010101u) * 0xFFu;
+            const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1F1F1F1Fu;
+            const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = f2u(half ? n2.y : n2.x), qloy = f2u(half ? n2.w : n2.z), qloz = f2u(half ? n3.y : n3.x);
+            const uint32_t qhix = f2u(half ? n3.w : n3.z), qhiy = f2u(half ? n4.y : n4.x), qhiz = f2u(half ? n4.w : n4.z);
+            const uint32_t xmin = st.dx < 0.f ? qhix : qlox, xmax = st.dx < 0.f ? qlox : qhix;
+            const uint32_t ymin = st.dy < 0.f ? qhiy : qloy, ymax = st.dy < 0.f ? qloy : qhiy;
+            const uint32_t zmin = st.dz < 0.f ? qhiz : qloz, zmax = st.dz < 0.f ? qloz : qhiz;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sh = 8 * j;
+                const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), ax, bx), t1x = fmaf((float)((xmax >> sh) & 0xFFu), ax, bx);
+                const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), ay, by), t1y = fmaf((float)((ymax >> sh) & 0xFFu), ay, by);
+                const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), az, bz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), az, bz);
+                const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tnear));
+                const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, st.hit.t)) * 1.0000004f;
+                if (tmin <= tmax) { hitmask |= ((childBits4 >> sh) & 0xFFu) << ((bitIndex4 >> sh) & 0xFFu); }
+            }
+        }
+        ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
+        tgroup.y = hitmask & 0x00FFFFFFu;
+    }
+    while (tgroup.y) {
+        const uint32_t bit = highestBit(tgroup.y);
+        tgroup.y &= ~(1u << bit);
+        const float4 *tri = bvh.triangles + (size_t)(tgroup.x + bit) * 3;
+        const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
+        if (COUNT) { counters->tris++; }
+        float t, u, v;
+        if (triangleTest(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, u, v)) {
+            const uint32_t prim = f2u(a.w);
+            // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
+            if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.prim = prim; }
+            st.found = true;
+            if (ANY) { return true; }
+        }
+    }
+    if (!(ngroup.y & 0xFF000000u)) {
+        if (st.sp == 0) { return true; }
+        ngroup = st.stack[--st.sp];
+    }
+    st.ngroup = ngroup;
+    return false;
+}
+
+// spheres: a handful per scene (mis-pbrt: 5), tested linearly after the mesh BVH; strict depth test
+template <bool ANY>
+PTC_HD bool traversalSpheres(const BvhView &bvh, TraversalState &st)
+{
+    if (ANY && st.found) { return true; }
+    for (uint32_t s = 0; s < bvh.nSpheres; s++) {
+        float t, nx, ny, nz;
+        if (sphereTest(loadNodeWord(bvh.spheres + s), st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, nx, ny, nz)) {
+            st.hit.t = t; st.hit.u = 0.f; st.hit.v = 0.f; st.hit.prim = PTC_SPHERE_FLAG | s;
+            st.found = true;
+            if (ANY) { return true; }
+        }
+    }
+    return st.found;
+}
+
 // ANY: return at the first accepted hit.  On return hit.t holds the closest t (or the input tfar on a miss).
 template <bool ANY, bool COUNT>
 PTC_HD bool traverseBVH(const BvhView &bvh, float ox, float oy, float oz, float dx, float dy, float dz, float tnear,
                         float tfar, RayHit &hit, TraverseCounters *counters)
 {
-    hit.t = tfar; hit.u = 0.f; hit.v = 0.f; hit.prim = PTC_MISS;
-    bool found = false;
-
-    if (bvh.nNodes) {
-        // reciprocal direction; zero components are nudged so that 0 * inf never appears in the slab test
-        const float eps = 1e-30f;
-        const float idx = 1.f / (fabsf(dx) > eps ? dx : (f2u(dx) & 0x80000000u ? -eps : eps));
-        const float idy = 1.f / (fabsf(dy) > eps ? dy : (f2u(dy) & 0x80000000u ? -eps : eps));
-        const float idz = 1.f / (fabsf(dz) > eps ? dz : (f2u(dz) & 0x80000000u ? -eps : eps));
-        const uint32_t octInv = 7u - ((dx < 0.f ? 4u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 1u : 0u));
-        const uint32_t octInv4 = octInv * 0x01010101u;
-
-        uint2 stack[PTC_STACK_SIZE];
-        int sp = 0;
-        uint2 ngroup = make_uint2(0u, 0x80000000u); // root = slot (7 ^ octInv) of a virtual parent with no siblings
-        for (;;) {
-            uint2 tgroup;
-            if (ngroup.y & 0xFF000000u) {
-                const uint32_t hitsImask = ngroup.y;
-                const uint32_t childBit = highestBit(hitsImask);
-                ngroup.y &= ~(1u << childBit);
-                if ((ngroup.y & 0xFF000000u) && sp < PTC_STACK_SIZE) { stack[sp++] = ngroup; }
-                const uint32_t slot = (childBit - 24u) ^ octInv;
-                const uint32_t relative = popCount(hitsImask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-                const float4 *node = bvh.nodes + (size_t)(ngroup.x + relative) * 5;
-                const float4 n0 = loadNodeWord(node + 0), n1 = loadNodeWord(node + 1), n2 = loadNodeWord(node + 2),
-                             n3 = loadNodeWord(node + 3), n4 = loadNodeWord(node + 4);
-                if (COUNT) { counters->inner++; }
-                const uint32_t e = f2u(n0.w);
-                const float ax = u2f((e & 0xFFu) << 23) * idx, ay = u2f(((e >> 8) & 0xFFu) << 23) * idy,
-                            az = u2f(((e >> 16) & 0xFFu) << 23) * idz;
-                const float bx = (n0.x - ox) * idx, by = (n0.y - oy) * idy, bz = (n0.z - oz) * idz;
-                ngroup.x = f2u(n1.x);
-                tgroup.x = f2u(n1.y);
-                uint32_t hitmask = 0;
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const uint32_t meta4 = f2u(half ? n1.w : n1.z);
-                    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                    const uint32_t innerMask4 = ((isInner4 >> 4) & 0x01010101u) * 0xFFu;
-                    const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1F1F1F1Fu;
-                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                    const uint32_t qlox = f2u(half ? n2.y : n2.x), qloy = f2u(half ? n2.w : n2.z), qloz = f2u(half ? n3.y : n3.x);
-                    const uint32_t qhix = f2u(half ? n3.w : n3.z), qhiy = f2u(half ? n4.y : n4.x), qhiz = f2u(half ? n4.w : n4.z);
-                    const uint32_t xmin = dx < 0.f ? qhix : qlox, xmax = dx < 0.f ? qlox : qhix;
-                    const uint32_t ymin = dy < 0.f ? qhiy : qloy, ymax = dy < 0.f ? qloy : qhiy;
-                    const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int sh = 8 * j;
-                        const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), ax, bx), t1x = fmaf((float)((xmax >> sh) & 0xFFu), ax, bx);
-                        const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), ay, by), t1y = fmaf((float)((ymax >> sh) & 0xFFu), ay, by);
-                        const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), az, bz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), az, bz);
-                        const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear));
-                        const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, hit.t)) * 1.0000004f;
-                        if (tmin <= tmax) { hitmask |= ((childBits4 >> sh) & 0xFFu) << ((bitIndex4 >> sh) & 0xFFu); }
-                    }
-                }
-                ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
-                tgroup.y = hitmask & 0x00FFFFFFu;
-            } else {
-                tgroup = ngroup;
-                ngroup = make_uint2(0u, 0u);
-            }
-            while (tgroup.y) {
-                const uint32_t bit = highestBit(tgroup.y);
-                tgroup.y &= ~(1u << bit);
-                const float4 *tri = bvh.triangles + (size_t)(tgroup.x + bit) * 3;
-                const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
-                if (COUNT) { counters->tris++; }
-                float t, u, v;
-                if (triangleTest(a, b, c, ox, oy, oz, dx, dy, dz, tnear, hit.t, t, u, v)) {
-                    const uint32_t prim = f2u(a.w);
-                    // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
-                    if (!(found && t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; }
-                    found = true;
-                    if (ANY) { return true; }
-                }
-            }
-            if (!(ngroup.y & 0xFF000000u)) {
-                if (sp == 0) { break; }
-                ngroup = stack[--sp];
-            }
-        }
-    }
-    // spheres: a handful per scene (mis-pbrt: 5), tested linearly after the mesh BVH; strict depth test
-    for (uint32_t s = 0; s < bvh.nSpheres; s++) {
-        float t, nx, ny, nz;
-        if (sphereTest(loadNodeWord(bvh.spheres + s), ox, oy, oz, dx, dy, dz, tnear, hit.t, t, nx, ny, nz)) {
-            hit.t = t; hit.u = 0.f; hit.v = 0.f; hit.prim = PTC_SPHERE_FLAG | s;
-            found = true;
-            if (ANY) { return true; }
-        }
-    }
+    TraversalState st;
+    traversalInit(st, ox, oy, oz, dx, dy, dz, tnear, tfar);
+    if (bvh.nNodes) { while (!traversalStep<ANY, COUNT>(bvh, st, counters)) {} }
+    const bool found = traversalSpheres<ANY>(bvh, st);
+    hit = st.hit;
     return found;
 }
 
