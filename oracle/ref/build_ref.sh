@@ -28,6 +28,7 @@ if [ ! -d "$B/embree" ]; then
   cp "$HERE/embree_config.h" "$B/embree/kernels/config.h"
   echo '#define RTC_HASH "pathed-b200-oracle"' > "$B/embree/kernels/hash.h"
 fi
+cp "$HERE/rtcore_config.h" "$B/embree/include/embree3/rtcore_config.h"
 rm -rf "$B/pathed"; mkdir -p "$B/pathed"
 cp -rs "$REF/include" "$B/pathed/include"
 cp -rs "$REF/src" "$B/pathed/src"
