@@ -176,12 +176,13 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     seed = 0x5EED
 
+    from pathed_b200.distributed import reduce_framebuffer, sample_block
+
     def step_device(i):
         # global sample indices of this step: [i*world*spp, (i+1)*world*spp); this rank takes its contiguous block
-        first = (i * world + rank) * spp
-        ctx.render_device(seed, first, spp, 0, last, accum.data_ptr(), stream)
-        if distributed:
-            dist.reduce(accum, dst=0)
+        first, count = sample_block(i, rank, world, spp)
+        ctx.render_device(seed, first, count, 0, last, accum.data_ptr(), stream)
+        reduce_framebuffer(accum, dst=0)
 
     def timed(fn, steps):
         if distributed:
@@ -218,7 +219,7 @@ def main():
     host_accum = np.zeros((height, width, 3), np.float32)
 
     def step_host(i):
-        ctx.render(seed, (i * world + rank) * spp, spp, 0, last, accum=host_accum)
+        ctx.render(seed, sample_block(i, rank, world, spp)[0], spp, 0, last, accum=host_accum)
 
     for i in range(3):
         step_host(i)

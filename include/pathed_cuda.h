@@ -170,6 +170,20 @@ int ptc_resolve_device(ptc_ctx *ctx, const float *accum_rgb_device, float *out_r
                        void *cuda_stream);
 #define PTC_MAX_BOUNCES 64
 
+/* ---- context-owned device framebuffer: Integrator::run's radianceLookup kept in HBM ----------- */
+/* `std::vector<float> radianceLookup(3*W*H)` zero-filled (src/integrator.cpp:37-40) */
+int ptc_framebuffer_clear(ptc_ctx *ctx);
+/* ptc_render into the context's framebuffer; asynchronous on the context's stream, no host traffic */
+int ptc_framebuffer_render(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
+                           int last_bounce);
+/* K7 + the multi-GPU reduce in ONE kernel on `root`'s device: out = (root's framebuffer + every peer context's
+ * framebuffer, read through NVLink peer mappings) / divisor, i.e. `radianceLookup[i] / (i + 1)` of
+ * src/integrator.cpp:74-85 over the spp split of SURVEY 8(e).  Waits for all contexts' pending renders,
+ * copies the result to out_rgb_host (3*W*H floats) and returns when it is there.  divisor = 1 gives the raw sums.
+ * peers may be NULL when n_peers = 0; at most PTC_MAX_PEERS peers. */
+int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t n_peers, uint32_t divisor, float *out_rgb_host);
+#define PTC_MAX_PEERS 15
+
 /* ---- ray queries (keep Scene::testIntersect / testOcclusion alive for CPU integrators; parity) */
 int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);        /* rtcIntersect1 */
 int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out);  /* Scene::testIntersect */

@@ -5,4 +5,4 @@ The product is the CUDA library `libpathed_cuda.so` (C ABI: include/pathed_cuda.
 thin ctypes bindings for scripts (tests, bench.py); there is no Python or CPU compute path.
 """
 from ._binding import (Api, MaterialDesc, PathedError, SceneFile, Stats, create_context, cuda_lib, host_lib,  # noqa: F401
-                       load_scene, rays_array, RAY_DTYPE, HIT_DTYPE, ISECT_DTYPE, LIGHT_SAMPLE_DTYPE)
+                       load_scene, rays_array, job_describe, bounce_controller, image_save, read_exr, scene_query, RAY_DTYPE, HIT_DTYPE, ISECT_DTYPE, LIGHT_SAMPLE_DTYPE)

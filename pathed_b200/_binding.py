@@ -169,6 +169,20 @@ class Api:
     def resolve_device(self, accum_ptr, out_ptr, spp, stream=0):
         self._call("resolve_device", ctypes.c_void_p(accum_ptr), ctypes.c_void_p(out_ptr), ctypes.c_uint32(spp), ctypes.c_void_p(stream))
 
+    # ---- context-owned device framebuffer (Integrator::run's radianceLookup kept in HBM)
+    def framebuffer_clear(self):
+        self._call("framebuffer_clear")
+
+    def framebuffer_render(self, seed, first_sample, n_spp, start_bounce, last_bounce):
+        self._call("framebuffer_render", ctypes.c_uint64(seed), ctypes.c_uint32(first_sample), ctypes.c_uint32(n_spp),
+                   ctypes.c_int(start_bounce), ctypes.c_int(last_bounce))
+
+    def framebuffer_gather(self, peers=(), divisor=1):
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        arr = (ctypes.c_void_p * max(len(peers), 1))(*[p.ctx.value for p in peers])
+        self._call("framebuffer_gather", arr, ctypes.c_uint32(len(peers)), ctypes.c_uint32(divisor), _ptr(out))
+        return out
+
     # ---- queries
     def intersect(self, rays):
         hits = np.zeros(len(rays), HIT_DTYPE)
@@ -322,6 +336,58 @@ class SceneFile:
             self.close()
         except Exception:
             pass
+
+
+def job_describe(job_path):
+    """Every accessor of the C++ Job (pathed_b200/host/job.cpp) for a job file, as a dict."""
+    import json
+    out, err = ctypes.create_string_buffer(4096), ctypes.create_string_buffer(512)
+    rc = host_lib().pth_job_describe(job_path.encode(), out, ctypes.c_int(4096), err, ctypes.c_int(512))
+    if rc != 0:
+        raise PathedError("Job(%s): %s" % (job_path, err.value.decode()))
+    return json.loads(out.value.decode())
+
+
+def bounce_controller(start, last, bounce):
+    """(checkCounts, checkDone, copyAfterBounce window) of the C++ BounceController."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    bits = host_lib().pth_bounce_controller(ctypes.c_int(start), ctypes.c_int(last), ctypes.c_int(bounce), ctypes.byref(a), ctypes.byref(b))
+    return bool(bits & 1), bool(bits & 2), (a.value, b.value)
+
+
+def image_save(output_directory, stem, rgb, spp, bmp_name=""):
+    """Image::set per pixel (row 0 = bottom), setSpp, saveCheckpoint(stem), write(bmp); returns the 8-bit preview."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    h, w, _ = rgb.shape
+    preview = np.zeros((h, w, 3), np.uint8)
+    rc = host_lib().pth_image_save(output_directory.encode(), stem.encode(), bmp_name.encode(), ctypes.c_int(w), ctypes.c_int(h),
+                                   ctypes.c_int(spp), _ptr(rgb), _ptr(preview))
+    if rc != 0:
+        raise PathedError("Image::save failed")
+    return preview
+
+
+def read_exr(path):
+    """RGBA fp32, top scanline first (pathed_b200/host/exr_io.cpp)."""
+    lib = host_lib()
+    w, h = ctypes.c_int(), ctypes.c_int()
+    if lib.pth_exr_read_rgba(path.encode(), None, ctypes.c_int(0), ctypes.byref(w), ctypes.byref(h)) != 0:
+        raise PathedError("cannot read " + path)
+    out = np.zeros((h.value, w.value, 4), np.float32)
+    lib.pth_exr_read_rgba(path.encode(), _ptr(out), ctypes.c_int(w.value * h.value), ctypes.byref(w), ctypes.byref(h))
+    return out
+
+
+def scene_query(scene_file, origin, direction, max_t):
+    """Scene::testIntersect + Scene::testOcclusion of the C++ host layer for one ray (needs a GPU)."""
+    o = (ctypes.c_float * 3)(*origin); d = (ctypes.c_float * 3)(*direction)
+    out = (ctypes.c_float * 14)(); occ = ctypes.c_int(); err = ctypes.create_string_buffer(512)
+    rc = host_lib().pth_scene_query(scene_file.handle, o, d, ctypes.c_float(max_t), out, ctypes.byref(occ), err, ctypes.c_int(512))
+    if rc != 0:
+        raise PathedError(err.value.decode())
+    v = list(out)
+    return {"hit": v[0] != 0, "t": v[1], "point": v[2:5], "normal": v[5:8], "shading_normal": v[8:11], "uv": v[11:13],
+            "material": int(v[13]), "occluded": occ.value != 0}
 
 
 _cuda_lib = None

@@ -45,8 +45,10 @@ def build_host(force=False):
     target = os.path.join(PKG, "libpathed_host.so")
     deps = _sources(HOST, (".cpp", ".hpp"))
     lib_sources = [s for s in _sources(HOST, (".cpp",)) if not s.endswith("main.cpp")]
-    if force or _stale(target, deps):
-        subprocess.check_call([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", target] + lib_sources + ["-lz", "-ldl"])
+    cuda = build_cuda()
+    if force or _stale(target, deps + [cuda]):
+        subprocess.check_call([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", target] + lib_sources +
+                              ["-L" + PKG, "-lpathed_cuda", "-Wl,-rpath,$ORIGIN", "-lz", "-ldl", "-lpthread"])
     return target
 
 

@@ -290,6 +290,27 @@ __global__ void resolveKernel(const float *accum, float *out, uint32_t n, uint32
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = accum[i] / (int)spp; }
 }
 
+// K7 resolve fused with the spp-split reduce: every framebuffer but the first lives on another GPU and is read through
+// its NVLink peer mapping (or a staged local copy when peer access is unavailable); summed in a fixed order
+struct FramebufferSet { const float *fb[PTC_MAX_PEERS + 1]; int count; };
+__global__ void __launch_bounds__(256) gatherResolveKernel(FramebufferSet set, float *out, uint32_t n, uint32_t divisor)
+{
+    const uint32_t n4 = n >> 2;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 sum = reinterpret_cast<const float4 *>(set.fb[0])[i];
+        for (int g = 1; g < set.count; g++) {
+            const float4 v = reinterpret_cast<const float4 *>(set.fb[g])[i];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        reinterpret_cast<float4 *>(out)[i] = make_float4(sum.x / (int)divisor, sum.y / (int)divisor, sum.z / (int)divisor, sum.w / (int)divisor);
+    }
+    for (uint32_t i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float sum = set.fb[0][i];
+        for (int g = 1; g < set.count; g++) { sum += set.fb[g][i]; }
+        out[i] = sum / (int)divisor;
+    }
+}
+
 __global__ void tallyKernel(const uint32_t *counters, unsigned long long *totals)
 {
     if (threadIdx.x == 0) {
@@ -519,6 +540,8 @@ struct ptc_ctx {
     uint32_t *counters = nullptr;
     unsigned long long *totals = nullptr;
     float *accumScratch = nullptr; size_t accumScratchSize = 0;
+    float *framebuffer = nullptr, *gatherOut = nullptr, *gatherStage = nullptr; size_t framebufferSize = 0, gatherStageSize = 0;
+    cudaEvent_t framebufferReady = nullptr;
     float *pinned = nullptr; size_t pinnedSize = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -629,6 +652,8 @@ void ptc_destroy(ptc_ctx *ctx)
     for (void *p : ctx->allocations) { cudaFree(p); }
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
+    cudaFree(ctx->framebuffer); cudaFree(ctx->gatherOut); cudaFree(ctx->gatherStage);
+    if (ctx->framebufferReady) { cudaEventDestroy(ctx->framebufferReady); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
     if (ctx->evStart) { cudaEventDestroy(ctx->evStart); }
@@ -964,6 +989,90 @@ int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp,
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->lastRenderMs, ctx->evStart, ctx->evStop);
     memcpy(accum, ctx->pinned, n * sizeof(float));
+    return PTC_OK;
+}
+
+static int ensureFramebuffer(ptc_ctx *ctx)
+{
+    const size_t n = (size_t)3 * ctx->scene.width * ctx->scene.height;
+    if (ctx->framebufferSize == n) { return PTC_OK; }
+    cudaFree(ctx->framebuffer); cudaFree(ctx->gatherOut); ctx->framebuffer = ctx->gatherOut = nullptr; ctx->framebufferSize = 0;
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->framebuffer, n * sizeof(float)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->gatherOut, n * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->framebuffer, 0, n * sizeof(float), ctx->stream));
+    if (!ctx->framebufferReady) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->framebufferReady, cudaEventDisableTiming)); }
+    ctx->framebufferSize = n;
+    return PTC_OK;
+}
+
+int ptc_framebuffer_clear(ptc_ctx *ctx)
+{
+    NEED_COMMIT(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = ensureFramebuffer(ctx);
+    if (rc) { return rc; }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->framebuffer, 0, ctx->framebufferSize * sizeof(float), ctx->stream));
+    return PTC_OK;
+}
+
+int ptc_framebuffer_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last)
+{
+    NEED_COMMIT(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = ensureFramebuffer(ctx);
+    if (rc) { return rc; }
+    return renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->framebuffer, ctx->stream);
+}
+
+int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers, uint32_t divisor, float *out)
+{
+    NEED_COMMIT(root);
+    if (!out || !divisor || (nPeers && !peers) || nPeers > PTC_MAX_PEERS) { CTX_FAIL(root, PTC_ERR_INVALID, "bad gather arguments"); }
+    CUDA_TRY(root, cudaSetDevice(root->device));
+    int rc = ensureFramebuffer(root);
+    if (rc) { return rc; }
+    const size_t n = root->framebufferSize;
+    FramebufferSet set;
+    set.fb[0] = root->framebuffer; set.count = 1;
+    size_t staged = 0;
+    for (uint32_t g = 0; g < nPeers; g++) {
+        ptc_ctx *peer = peers[g];
+        if (!peer || !peer->committed || peer->framebufferSize != n) { CTX_FAIL(root, PTC_ERR_STATE, "peer %u has no framebuffer of the same size", g); }
+        // order the gather after the peer's pending renders
+        CUDA_TRY(root, cudaSetDevice(peer->device));
+        CUDA_TRY(root, cudaEventRecord(peer->framebufferReady, peer->stream));
+        CUDA_TRY(root, cudaSetDevice(root->device));
+        CUDA_TRY(root, cudaStreamWaitEvent(root->stream, peer->framebufferReady, 0));
+        int canAccess = 0;
+        if (peer->device != root->device) { cudaDeviceCanAccessPeer(&canAccess, root->device, peer->device); }
+        if (peer->device == root->device) { set.fb[set.count++] = peer->framebuffer; continue; }
+        if (canAccess) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); set.fb[set.count++] = peer->framebuffer; continue; }
+            cudaGetLastError();
+        }
+        // no peer mapping: stage the peer's framebuffer into local memory first
+        if (root->gatherStageSize < (size_t)nPeers * n) {
+            CUDA_TRY(root, cudaStreamSynchronize(root->stream));
+            cudaFree(root->gatherStage); root->gatherStage = nullptr; root->gatherStageSize = 0;
+            CUDA_TRY(root, cudaMalloc((void **)&root->gatherStage, (size_t)nPeers * n * sizeof(float)));
+            root->gatherStageSize = (size_t)nPeers * n;
+        }
+        float *slot = root->gatherStage + staged * n; staged++;
+        CUDA_TRY(root, cudaMemcpyPeerAsync(slot, root->device, peer->framebuffer, peer->device, n * sizeof(float), root->stream));
+        set.fb[set.count++] = slot;
+    }
+    if (root->pinnedSize < n) {
+        if (root->pinned) { cudaFreeHost(root->pinned); root->pinned = nullptr; }
+        CUDA_TRY(root, cudaMallocHost((void **)&root->pinned, n * sizeof(float)));
+        root->pinnedSize = n;
+    }
+    gatherResolveKernel<<<std::min<uint32_t>((uint32_t)((n / 4 + 255) / 256) + 1, (uint32_t)root->gridSimple * 4), 256, 0, root->stream>>>(set, root->gatherOut, (uint32_t)n, divisor);
+    root->launches++;
+    CUDA_TRY(root, cudaGetLastError());
+    CUDA_TRY(root, cudaMemcpyAsync(root->pinned, root->gatherOut, n * sizeof(float), cudaMemcpyDeviceToHost, root->stream));
+    CUDA_TRY(root, cudaStreamSynchronize(root->stream));
+    memcpy(out, root->pinned, n * sizeof(float));
     return PTC_OK;
 }
 

@@ -1,0 +1,77 @@
+// Image: fp32 raw buffer (stored top scanline first), 8-bit gamma preview, EXR output.
+// Behaviour follows /root/reference/src/image.cpp:13-160 (Q14: row 0 is the bottom scanline; EXR = 3 x HALF, B,G,R, uncompressed;
+// auto.exr + auto-%05dspp.exr checkpoints).
+#include "pathed.hpp"
+
+#include "exr_io.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+
+namespace pathed {
+
+Image::Image(int width, int height)
+    : m_height(height), m_width(width), m_spp(0), m_data((size_t)3 * height * width), m_raw((size_t)3 * height * width)
+{}
+
+void Image::set(int row, int col, float r, float g, float b)
+{
+    const size_t flipped = 3 * ((size_t)(m_height - row - 1) * m_width + col);
+    m_raw[flipped + 0] = r; m_raw[flipped + 1] = g; m_raw[flipped + 2] = b;
+    const size_t index = 3 * ((size_t)row * m_width + col);
+    // powf(x, 1/2.2) with a double exponent narrowed by the call, then truncation to a byte
+    m_data[index + 0] = (unsigned char)(fminf(powf(r, 1 / 2.2), 1.f) * 255);
+    m_data[index + 1] = (unsigned char)(fminf(powf(g, 1 / 2.2), 1.f) * 255);
+    m_data[index + 2] = (unsigned char)(fminf(powf(b, 1 / 2.2), 1.f) * 255);
+}
+
+void Image::save(const std::string &filestem) { save(filestem, false); }
+void Image::saveCheckpoint(const std::string &filestem) { save(filestem, true); }
+
+void Image::save(const std::string &filestem, bool checkpoint)
+{
+    const size_t n = (size_t)m_width * m_height;
+    std::vector<float> planes[3];
+    for (int c = 0; c < 3; c++) { planes[c].resize(n); }
+    for (size_t i = 0; i < n; i++) { for (int c = 0; c < 3; c++) { planes[c][i] = m_raw[3 * i + c]; } }
+    const std::string directory = g_job ? g_job->outputDirectory() : std::string();
+    const std::string outputExr = directory + filestem + ".exr";
+    char suffix[32];
+    snprintf(suffix, sizeof(suffix), "-%05dspp.exr", m_spp);
+    const std::string outputSppExr = directory + filestem + suffix;
+    try {
+        saveEXR(outputExr, m_width, m_height, {"B", "G", "R"}, {planes[2].data(), planes[1].data(), planes[0].data()}, true);
+        printf("Saved exr file. [ %s ] \n", outputExr.c_str());
+        if (checkpoint) {
+            saveEXR(outputSppExr, m_width, m_height, {"B", "G", "R"}, {planes[2].data(), planes[1].data(), planes[0].data()}, true);
+            printf("Saved exr file. [ %s ] \n", outputSppExr.c_str());
+        }
+    } catch (const std::exception &e) {
+        fprintf(stderr, "Save EXR err: %s\n", e.what());
+    }
+}
+
+void Image::write(const std::string &filename)
+{
+    // stbi_write_bmp(path, w, h, 3, data): 24-bit BMP, bottom-up rows of B,G,R padded to 4 bytes
+    const std::string path = (g_job ? g_job->outputDirectory() : std::string()) + filename;
+    const int pad = (4 - (m_width * 3) % 4) % 4;
+    const uint32_t dataSize = (uint32_t)((m_width * 3 + pad) * m_height), fileSize = 54 + dataSize;
+    std::ofstream out(path, std::ios::binary);
+    auto u16 = [&](uint16_t v) { out.write((const char *)&v, 2); };
+    auto u32 = [&](uint32_t v) { out.write((const char *)&v, 4); };
+    out.write("BM", 2); u32(fileSize); u16(0); u16(0); u32(54);
+    u32(40); u32((uint32_t)m_width); u32((uint32_t)m_height); u16(1); u16(24); u32(0); u32(0); u32(0); u32(0); u32(0); u32(0);
+    const char zero[3] = {0, 0, 0};
+    for (int row = m_height - 1; row >= 0; row--) {
+        for (int col = 0; col < m_width; col++) {
+            const unsigned char *px = &m_data[3 * ((size_t)row * m_width + col)];
+            const char bgr[3] = {(char)px[2], (char)px[1], (char)px[0]};
+            out.write(bgr, 3);
+        }
+        out.write(zero, pad);
+    }
+}
+
+} // namespace pathed

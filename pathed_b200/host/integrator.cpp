@@ -1,0 +1,232 @@
+// Scene (ray queries over the GPU BVH), Integrator::run and CudaPathTracer: the rendering side of the host API.
+// The reference's loop is /root/reference/src/integrator.cpp:19-106 -> src/sample_integrator.cpp:80-113 -> src/path_tracer.cpp:19-216;
+// here one call into the C ABI covers a whole batch of samples per pixel and the framebuffer stays in HBM between checkpoints.
+#include "pathed.hpp"
+
+#include "scene_parser.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <iomanip>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+
+namespace pathed {
+
+namespace {
+
+void check(ptc_ctx *ctx, int status, const char *what)
+{
+    if (status != PTC_OK) { throw std::runtime_error(std::string(what) + ": " + ptc_last_error(ctx)); }
+}
+
+// adapters from the C ABI to the parser's sink table
+int sinkMaterial(void *c, const ptc_material_desc *d, uint32_t *id) { return ptc_add_material((ptc_ctx *)c, d, id); }
+int sinkMesh(void *c, const float *p, const float *n, const float *uv, uint32_t nv, const uint32_t *i, const uint32_t *m, uint32_t nt, uint32_t *g)
+{
+    return ptc_add_triangle_mesh((ptc_ctx *)c, p, n, uv, nv, i, m, nt, g);
+}
+int sinkSphere(void *c, const float *cr, uint32_t m, uint32_t *g) { return ptc_add_sphere((ptc_ctx *)c, cr, m, g); }
+int sinkEnvironment(void *c, const float *rgba, int w, int h, float s, const float *m2w, const float *w2m)
+{
+    return ptc_set_environment((ptc_ctx *)c, rgba, w, h, s, m2w, w2m);
+}
+int sinkCamera(void *c, const float *o, const float *t, const float *u, float f, int w, int h, int flip)
+{
+    return ptc_set_camera((ptc_ctx *)c, o, t, u, f, w, h, flip);
+}
+int sinkCommit(void *c) { return ptc_commit((ptc_ctx *)c); }
+
+double now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ Scene
+Scene::Scene(const SceneDescription &description, int gpus) : m_width(description.camera.width), m_height(description.camera.height)
+{
+    for (int device = 0; device < std::max(1, gpus); device++) {
+        ptc_ctx *ctx = nullptr;
+        if (ptc_create(device, &ctx) != PTC_OK || !ctx) {
+            for (ptc_ctx *c : m_contexts) { ptc_destroy(c); }
+            throw std::runtime_error("Failed to create device " + std::to_string(device) + " (no CUDA device? there is no CPU path)");
+        }
+        m_contexts.push_back(ctx);
+        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit};
+        const int status = feedScene(description, sink);
+        if (status != PTC_OK) {
+            const std::string message = ptc_last_error(ctx);
+            for (ptc_ctx *c : m_contexts) { ptc_destroy(c); }
+            throw std::runtime_error("scene upload failed: " + message);
+        }
+    }
+}
+
+Scene::~Scene()
+{
+    for (ptc_ctx *ctx : m_contexts) { ptc_destroy(ctx); }
+}
+
+Intersection Scene::testIntersect(const Ray &ray) const
+{
+    std::lock_guard<std::mutex> guard(m_queryLock);
+    ptc_ray r;
+    for (int a = 0; a < 3; a++) { r.origin[a] = ray.origin[a]; r.direction[a] = ray.direction[a]; }
+    ptc_isect is;
+    check(m_contexts[0], ptc_intersect_full(m_contexts[0], &r, 1, &is), "testIntersect");
+    Intersection out;
+    out.hit = is.hit != 0;
+    out.t = is.t; // miss: std::numeric_limits<float>::max(), like IntersectionHelper::miss (include/intersection.h:60-72)
+    for (int a = 0; a < 3; a++) {
+        out.point[a] = is.point[a]; out.woWorld[a] = is.wo[a]; out.normal[a] = is.normal[a]; out.shadingNormal[a] = is.shading_normal[a];
+    }
+    out.uv[0] = is.uv[0]; out.uv[1] = is.uv[1];
+    out.material = is.material;
+    return out;
+}
+
+bool Scene::testOcclusion(const Ray &ray, float maxT) const
+{
+    std::lock_guard<std::mutex> guard(m_queryLock);
+    ptc_ray r;
+    for (int a = 0; a < 3; a++) { r.origin[a] = ray.origin[a]; r.direction[a] = ray.direction[a]; }
+    uint8_t occluded = 0;
+    check(m_contexts[0], ptc_occluded(m_contexts[0], &r, &maxT, 1, &occluded), "testOcclusion");
+    return occluded != 0;
+}
+
+uint32_t Scene::lightCount() const
+{
+    uint32_t n = 0;
+    check(m_contexts[0], ptc_num_lights(m_contexts[0], &n), "lightCount");
+    return n;
+}
+
+std::unique_ptr<Scene> parseSceneForJob(const Job &job, const std::string &rootDirectory)
+{
+    const SceneDescription description = parseScene(job.scene(), rootDirectory, job.width(), job.height());
+    return std::unique_ptr<Scene>(new Scene(description, job.gpus()));
+}
+
+// ------------------------------------------------------------------------------------------------ Integrator
+// The reference's loop, kept for integrators that only provide sampleImage: one spp per wave through a HOST radianceLookup.
+void Integrator::run(Image &image, Scene &scene, std::function<void(RenderStatus)> callback, bool *quit)
+{
+    const int width = g_job->width(), height = g_job->height(), primarySamples = g_job->spp();
+    printf("Beginning pre-process...\n");
+    const double preBegin = now();
+    preprocess(scene);
+    printf("Pre-process complete (%0.1fs elapsed)\n", now() - preBegin);
+
+    std::vector<float> radianceLookup((size_t)3 * width * height, 0.f);
+    for (int i = 0; i < primarySamples; i++) {
+        const double begin = now();
+        sampleImage(radianceLookup, scene);
+        const double end = now();
+        postwave(scene, i + 1);
+        RenderStatus status;
+        status.setSample(i + 1);
+        callback(status);
+        {
+            std::lock_guard<std::mutex> guard(image.getLock());
+            image.setSpp(i + 1);
+            for (int row = 0; row < height; row++) {
+                for (int col = 0; col < width; col++) {
+                    const size_t index = 3 * ((size_t)row * width + col);
+                    image.set(row, col, radianceLookup[index] / (i + 1), radianceLookup[index + 1] / (i + 1), radianceLookup[index + 2] / (i + 1));
+                }
+            }
+            const int maxJ = (int)log2f((float)primarySamples);
+            for (int j = 0; j <= maxJ; j++) { if (1 << j == i + 1) { image.saveCheckpoint("auto"); } }
+        }
+        std::ostringstream line;
+        line << "sample: " << i + 1 << "/" << primarySamples << std::fixed << std::setprecision(1) << " (" << (end - begin) << "s elapsed)";
+        Logger::line(line.str());
+        if (*quit) { return; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CudaPathTracer
+CudaPathTracer::CudaPathTracer(BounceController bounceController, uint64_t seed, int waveSpp)
+    : m_bounceController(bounceController), m_seed(seed), m_waveSpp(std::max(1, waveSpp))
+{}
+
+void CudaPathTracer::sampleImage(std::vector<float> &radianceLookup, Scene &scene)
+{
+    ptc_ctx *ctx = scene.context(0);
+    check(ctx, ptc_render(ctx, m_seed, m_nextSample, 1, m_bounceController.startBounce(), m_bounceController.lastBounce(), radianceLookup.data()),
+          "sampleImage");
+    m_nextSample++;
+    m_samples += (uint64_t)scene.width() * scene.height();
+}
+
+// Waves end at every power of two (the reference checkpoints there, src/integrator.cpp:87-92) and after at most
+// wave_spp samples; inside a wave the samples are split over the GPUs in contiguous blocks of global sample indices,
+// each GPU accumulating into its own device framebuffer.  At a wave boundary ONE kernel on GPU 0 sums all framebuffers
+// through peer (NVLink) loads and divides by the sample count (K7 resolve), and the result is copied to the host once.
+void CudaPathTracer::run(Image &image, Scene &scene, std::function<void(RenderStatus)> callback, bool *quit)
+{
+    const int width = g_job->width(), height = g_job->height(), primarySamples = g_job->spp();
+    if (width != scene.width() || height != scene.height()) { throw std::runtime_error("job resolution differs from the scene's camera"); }
+    printf("Beginning pre-process...\n");
+    const double preBegin = now();
+    preprocess(scene);
+    printf("Pre-process complete (%0.1fs elapsed)\n", now() - preBegin);
+
+    const int gpus = scene.gpus();
+    const int start = m_bounceController.startBounce(), last = m_bounceController.lastBounce();
+    for (int g = 0; g < gpus; g++) { check(scene.context(g), ptc_framebuffer_clear(scene.context(g)), "framebuffer clear"); }
+    std::vector<ptc_ctx *> peers;
+    for (int g = 1; g < gpus; g++) { peers.push_back(scene.context(g)); }
+    std::vector<float> resolved((size_t)3 * width * height);
+
+    int done = 0;
+    while (done < primarySamples) {
+        const double begin = now();
+        int nextPowerOfTwo = 1;
+        while (nextPowerOfTwo <= done) { nextPowerOfTwo <<= 1; }
+        const int target = std::min(std::min(nextPowerOfTwo, done + m_waveSpp * gpus), primarySamples);
+        const int waveSamples = target - done;
+        // contiguous blocks: GPU g takes samples [done + g*per, ...); any split gives the same sums up to fp32 order
+        const int per = (waveSamples + gpus - 1) / gpus;
+        for (int g = 0; g < gpus; g++) {
+            const int first = done + g * per, count = std::min(per, target - first);
+            if (count <= 0) { continue; }
+            check(scene.context(g), ptc_framebuffer_render(scene.context(g), m_seed, (uint32_t)first, (uint32_t)count, start, last), "render");
+        }
+        done = target;
+        check(scene.context(0), ptc_framebuffer_gather(scene.context(0), peers.data(), (uint32_t)peers.size(), (uint32_t)done, resolved.data()),
+              "framebuffer gather");
+        const double end = now();
+        m_renderSeconds += end - begin;
+        m_samples += (uint64_t)waveSamples * width * height;
+        m_nextSample = (uint32_t)done;
+        postwave(scene, done);
+
+        RenderStatus status;
+        status.setSample(done);
+        callback(status);
+        {
+            std::lock_guard<std::mutex> guard(image.getLock());
+            image.setSpp(done);
+            for (int row = 0; row < height; row++) {
+                for (int col = 0; col < width; col++) {
+                    const size_t index = 3 * ((size_t)row * width + col);
+                    image.set(row, col, resolved[index], resolved[index + 1], resolved[index + 2]);
+                }
+            }
+            if ((done & (done - 1)) == 0) { image.saveCheckpoint("auto"); }
+        }
+        std::ostringstream line;
+        line << "sample: " << done << "/" << primarySamples << std::fixed << std::setprecision(1) << " (" << (end - begin) << "s elapsed)";
+        Logger::line(line.str());
+        if (*quit) { return; }
+    }
+}
+
+} // namespace pathed

@@ -1,0 +1,102 @@
+"""GPU tests (pytest -m gpu) of the C++ host API and the context-owned framebuffer: the `pathed` command-line renderer run on a
+job.json like the reference's binary, Scene::testIntersect / testOcclusion, and the peer-memory reduce + resolve."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pathed_b200 import SceneFile, load_scene, read_exr, scene_query
+from pathed_b200._binding import PKG_DIR, REPO_ROOT, rays_array
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_job(tmp_path, **over):
+    job = {"spp": 8, "integrator": "PathTracer", "scene": "scenes/cornell.json", "startBounce": 0, "lastBounce": 10,
+           "output_directory": str(tmp_path / "out"), "output_name": "final", "showUI": False, "force": True, "width": 48, "height": 40}
+    job.update(over)
+    os.makedirs(str(tmp_path), exist_ok=True)
+    path = str(tmp_path / "job.json")
+    json.dump(job, open(path, "w"))
+    r = subprocess.run([os.path.join(PKG_DIR, "pathed"), path, "--root", REPO_ROOT], capture_output=True, text=True)
+    return job, r
+
+
+def test_cli_renders_a_job_like_the_reference_binary(tmp_path):
+    job, r = _run_job(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = str(tmp_path / "out")
+    # src/integrator.cpp:87-92 checkpoints at every power of two; app/main.cpp:115 saves <output_name>.exr at the end
+    for name in ["report.json", "auto.exr", "final.exr"] + ["auto-%05dspp.exr" % s for s in (1, 2, 4, 8)]:
+        assert os.path.exists(os.path.join(out, name)), name
+    assert json.load(open(os.path.join(out, "report.json")))["scene"] == job["scene"]
+    assert "sample: 8/8" in r.stdout and "PATHED_RESULT" in r.stdout
+    ctx = load_scene(job["scene"], job["width"], job["height"])
+    for spp in (1, 8):
+        want = (ctx.render(0x5EED, 0, spp, 0, 10) / np.float32(spp))[::-1].astype(np.float16).astype(np.float32)
+        got = read_exr(os.path.join(out, "auto-%05dspp.exr" % spp))[..., :3]
+        assert np.array_equal(got, want), spp  # same Philox streams, same accumulation order: bit-exact after HALF
+    assert np.array_equal(read_exr(os.path.join(out, "final.exr")), read_exr(os.path.join(out, "auto.exr")))
+
+
+def test_cli_wave_size_and_seed_keys(tmp_path):
+    _, a = _run_job(tmp_path, spp=6, wave_spp=1, seed=7)
+    assert a.returncode == 0, a.stdout
+    assert [l for l in a.stdout.splitlines() if "sample: " in l][-1].split("sample: ")[1].startswith("6/6")
+    assert a.stdout.count("sample: ") == 6  # one wave per spp, like the reference
+    got = read_exr(str(tmp_path / "out" / "final.exr"))[..., :3]
+    ctx = load_scene("scenes/cornell.json", 48, 40)
+    want = (ctx.render(7, 0, 6, 0, 10) / np.float32(6))[::-1].astype(np.float16).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_cli_rejects_what_the_reference_rejects(tmp_path):
+    _, r = _run_job(tmp_path, integrator="VolumePathTracer")
+    assert r.returncode == 1 and "Unimplemented" in r.stdout
+    _, r = _run_job(tmp_path, scene="scenes/does-not-exist.json")
+    assert r.returncode == 1
+
+
+def test_scene_queries_through_the_host_api():
+    sf = SceneFile("scenes/cornell.json", 32, 32)
+    ctx = sf.feed(__import__("pathed_b200").create_context(0))
+    cam = ctx.camera_rays(np.array([[16.0, 16.0], [3.0, 29.0]], np.float32))
+    full = ctx.intersect_full(cam)
+    for i in range(2):
+        q = scene_query(sf, cam["origin"][i], cam["direction"][i], 0.5 * float(full["t"][i]))
+        assert q["hit"] and q["t"] == full["t"][i] and q["material"] == int(full["material"][i])
+        assert np.array_equal(np.float32(q["point"]), full["point"][i]) and np.array_equal(np.float32(q["normal"]), full["normal"][i])
+        assert not q["occluded"]  # the segment ends half way to the first surface
+        assert scene_query(sf, cam["origin"][i], cam["direction"][i], 2.0 * float(full["t"][i]))["occluded"]
+    miss = scene_query(sf, (0, 1, 10), (0, 0, 1), 5.0)
+    assert not miss["hit"] and not miss["occluded"]
+
+
+def test_framebuffer_gather_sums_contexts_and_resolves():
+    """two contexts (same device here; peer devices on a multi-GPU box) each render half of the samples into their own HBM
+    framebuffer; one kernel sums them and divides by the sample count"""
+    a = load_scene("scenes/cornell-glass.json", 40, 40)
+    b = load_scene("scenes/cornell-glass.json", 40, 40)
+    a.framebuffer_clear(); b.framebuffer_clear()
+    a.framebuffer_render(5, 0, 4, 0, 10)
+    b.framebuffer_render(5, 4, 4, 0, 10)
+    got = a.framebuffer_gather([b], divisor=8)
+    want = load_scene("scenes/cornell-glass.json", 40, 40).render(5, 0, 8, 0, 10) / np.float32(8)
+    assert np.allclose(got, want, rtol=2e-6, atol=1e-7)
+    sums = a.framebuffer_gather([], divisor=1)
+    assert np.array_equal(sums, load_scene("scenes/cornell-glass.json", 40, 40).render(5, 0, 4, 0, 10))
+    a.framebuffer_clear()
+    assert not a.framebuffer_gather([], divisor=1).any()
+
+
+def test_multi_gpu_job_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _, one = _run_job(tmp_path / "a", spp=8)
+    _, two = _run_job(tmp_path / "b", spp=8, gpus=2)
+    assert one.returncode == 0 and two.returncode == 0, two.stdout
+    x = read_exr(str(tmp_path / "a" / "out" / "final.exr")); y = read_exr(str(tmp_path / "b" / "out" / "final.exr"))
+    assert np.allclose(x, y, rtol=2e-3, atol=1e-4)  # HALF output of sums that differ in the last fp32 bit
