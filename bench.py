@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--workload", default="dragon", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--paths-per-wave", type=int, default=0, help="override the library's wave size (paths resident per wave)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -171,6 +172,9 @@ def main():
     t0 = time.time()
     ctx = load_scene(w["scene"], width, height, device=local_rank)
     build_s = time.time() - t0
+    if args.paths_per_wave:
+        ctx.set_option("paths_per_wave", args.paths_per_wave)
+    ppw = args.paths_per_wave or (1 << 21)
     n_pix = width * height
     accum = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
@@ -268,7 +272,8 @@ def main():
                     "triangle_tests_per_ray": cst.extend_triangle_tests / max(cst.closest_rays, 1),
                     "rays_per_launch": extend_rays_per_launch, "ms_per_launch": ms_per_launch,
                     "note": "algorithmic bytes: the BVH (%.1f MB) is L2-resident, so this exceeds DRAM traffic" % (tst.bvh_bytes / 1e6)}
-        stages = {"extend_ms": tst.extend_ms, "shadow_ms": tst.shadow_ms, "shade_ms": tst.shade_ms, "other_ms": tst.other_ms,
+        ext_counts, sh_counts = ctx.wave_counts(last + 2)
+        stages = {"last_wave_extend_rays": ext_counts, "last_wave_shadow_rays": sh_counts, "extend_ms": tst.extend_ms, "shadow_ms": tst.shadow_ms, "shade_ms": tst.shade_ms, "other_ms": tst.other_ms,
                   "extend_share": tst.extend_ms / max(total_stage, 1e-9), "extend_grays_per_s": tst.closest_rays / max(tst.extend_ms, 1e-9) * 1e-6,
                   "shadow_grays_per_s": tst.shadow_rays / max(tst.shadow_ms, 1e-9) * 1e-6}
 
@@ -288,7 +293,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], width, height, last), "spp_per_step": spp,
                        "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, 1 << 21) * 148 / 1e6, max(1, n_pix * spp >> 21)),
+                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 148 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
                        "scene_build_s": build_s},
             "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes},

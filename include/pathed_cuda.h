@@ -218,6 +218,9 @@ int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint
 int ptc_num_lights(ptc_ctx *ctx, uint32_t *out); /* Scene::lights().size() */
 int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out);
 int ptc_reset_stats(ptc_ctx *ctx);
+/* queue sizes of the most recent wave: extend_counts[k] = rays that left vertex k (k = 0: camera rays), shadow_counts[k] =
+ * NEE shadow rays cast at vertex k; up to `capacity` (<= PTC_MAX_BOUNCES + 2) entries each */
+int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend_counts, uint32_t *shadow_counts, uint32_t capacity);
 int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave" */
 /* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
  * visits and triangle tests per ray (algorithmic bytes per ray) */

@@ -262,6 +262,11 @@ class Api:
         self._call("get_stats", ctypes.byref(out))
         return out
 
+    def wave_counts(self, n=12):
+        e = (ctypes.c_uint32 * n)(); s = (ctypes.c_uint32 * n)()
+        self._call("get_wave_counts", e, s, ctypes.c_uint32(n))
+        return list(e), list(s)
+
     def reset_stats(self):
         self._call("reset_stats")
 

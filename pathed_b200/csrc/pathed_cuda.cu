@@ -1239,6 +1239,17 @@ int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
     return PTC_OK;
 }
 
+int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend, uint32_t *shadow, uint32_t capacity)
+{
+    if (!ctx || !extend || !shadow) { return PTC_ERR_INVALID; }
+    uint32_t host[2 * CNT_STRIDE];
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(host, ctx->counters, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "cudaMemcpy failed"); }
+    for (uint32_t k = 0; k < capacity && k < CNT_STRIDE; k++) { extend[k] = host[k]; shadow[k] = host[CNT_STRIDE + k]; }
+    return PTC_OK;
+}
+
 int ptc_reset_stats(ptc_ctx *ctx)
 {
     if (!ctx) { return PTC_ERR_INVALID; }
