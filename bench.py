@@ -174,7 +174,7 @@ def main():
     build_s = time.time() - t0
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
-    ppw = args.paths_per_wave or (1 << 21)
+    ppw = args.paths_per_wave or (1 << 24)
     n_pix = width * height
     accum = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream

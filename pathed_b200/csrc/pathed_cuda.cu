@@ -4,9 +4,11 @@
 //   generate  K1  camera rays (Camera::generateRay, src/camera.cpp:32-55) + path-state initialisation
 //   extend    K2  closest hit over the compressed 8-wide BVH (rtcIntersect1 via Scene::testIntersect)
 //   shadow    K3  any hit for the NEE shadow rays (rtcOccluded1 via Scene::testOcclusion)
-//   shade     K4/K5/K6  finalise the previous vertex's direct lighting (NEE + MIS'd BSDF hit), update the
-//             throughput, sample the BSDF at the new vertex, set up NEE, append to the next extend / shadow
-//             queues with warp-aggregated atomics (ballot + popc compaction)
+//   logic     K5/K6  finalise the previous vertex's direct lighting (NEE + MIS'd BSDF hit / environment miss), update the
+//             throughput, terminate; survivors are binned by the material class of the surface they hit
+//   material  K4  one kernel per material class present in the scene (compile-time specialised BSDF code, coherent
+//             warps): build the Intersection, sample the BSDF, set up NEE, append to the next extend / shadow queues
+//             (all queue appends are warp-aggregated: ballot + popc + one atomic per warp)
 //   resolve   K7  sum the wave's per-sample radiance into the fp32 framebuffer in sample order
 // The MIS probe ray (src/path_tracer.cpp:175) and the continuation ray (:44) are the same ray: traced once.
 // All queue sizes live on the device; a wave is a fixed launch sequence with no host synchronisation.
@@ -24,6 +26,7 @@
 using namespace ptc;
 
 // ================================================================================================ device state
+#define PTC_MATERIAL_CLASSES 6 /* PTC_LAMBERTIAN .. PTC_PLASTIC */
 struct PathBuffers {
     float4 *rayO, *rayD;   // current ray (origin = current vertex)
     float4 *hit;           // t, u, v, prim bits
@@ -36,6 +39,7 @@ struct PathBuffers {
     uint8_t *occluded;
     uint32_t *extendQueue[2];
     uint32_t *shadowQueue;
+    uint32_t *classQueue[PTC_MATERIAL_CLASSES]; // survivors of the logic stage, binned by material class (null: class absent from the scene)
 };
 
 #define FLAG_BOUNCE_MASK 0xFFu
@@ -51,11 +55,15 @@ struct WaveParams {
     int32_t startBounce, lastBounce;
 };
 
-// counters[0 .. MAXB+1]            extend queue sizes per bounce
-// counters[MAXB+2 .. 2*MAXB+3]     shadow queue sizes per bounce
-// counters[2*MAXB+4 ...]           work cursors, one per launch
+// Device-side bookkeeping of one wave: queue sizes and work cursors per bounce (no host synchronisation inside a wave)
+struct BounceCounters {
+    uint32_t extendCount, shadowCount;           // rays leaving vertex k / NEE shadow rays cast at vertex k
+    uint32_t classCount[PTC_MATERIAL_CLASSES];   // survivors of logic(k) per material class
+    uint32_t extendCursor, shadowCursor, logicCursor, classCursor[PTC_MATERIAL_CLASSES];
+    uint32_t pad[15];
+};
+static_assert(sizeof(BounceCounters) == 128, "one cache line per bounce");
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
-#define CNT_TOTAL (CNT_STRIDE * 5)
 
 // Path slot q of a wave -> pixel.  Slots are laid out in 8x4 pixel tiles so that the 32 camera rays of a warp (and the
 // secondary rays they spawn) stay spatially coherent; falls back to row-major when the image is not tileable.
@@ -91,7 +99,7 @@ __device__ __forceinline__ bool fetchWork(uint32_t *cursor, uint32_t count, uint
 }
 
 // ------------------------------------------------------------------------------------------------ K1 generate
-__global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers pb, WaveParams wp, uint32_t *counters)
+__global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *counters)
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += gridDim.x * blockDim.x) {
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
         pb.result[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
         pb.extendQueue[0][p] = p;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0] = nPaths; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0].extendCount = nPaths; }
 }
 
 // ------------------------------------------------------------------------------------------------ K2 extend / K3 shadow
@@ -180,48 +188,60 @@ __global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers 
     if (COUNT) { flushCounters(tc, work); }
 }
 
-// ------------------------------------------------------------------------------------------------ K4-K6 shade
-// One invocation handles the result of the ray that left vertex k (k = 0: the camera ray).
-__global__ void __launch_bounds__(128) shadeKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const uint32_t *count,
-                                                   uint32_t *cursor, uint32_t *nextQueue, uint32_t *nextCount, uint32_t *shadowCount)
+// ------------------------------------------------------------------------------------------------ K5-K6 logic
+// Handles the result of the ray that left vertex k (k = 0: the camera ray): everything in PathTracer::L between two
+// BSDF samples.  Cheap per path (the Intersection is only built for emitter hits); survivors go to the class queues.
+__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
 {
-    const uint32_t n = *count;
+    const uint32_t n = bc->extendCount;
     uint32_t item;
-    while (fetchWork(cursor, n, item)) {
-        const bool valid = item < n;
-        bool pushExtend = false, pushShadow = false;
+    while (fetchWork(&bc->logicCursor, n, item)) {
+        int cls = -1;
         uint32_t p = 0;
-        if (valid) {
+        if (item < n) {
             p = queue[item];
-            const float4 o4 = pb.rayO[p], d4 = pb.rayD[p], h4 = pb.hit[p];
+            const float4 d4 = pb.rayD[p], h4 = pb.hit[p];
             float4 res4 = pb.result[p];
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
-            const V3 O = mk(o4.x, o4.y, o4.z), D = mk(d4.x, d4.y, d4.z);
-            RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
-            const bool isHit = hit.prim != PTC_MISS;
-            Isect bi;
-            if (isHit) { makeIsect(scene, O, D, hit, bi); }
+            const V3 D = mk(d4.x, d4.y, d4.z);
+            const uint32_t prim = __float_as_uint(h4.w);
+            const bool isHit = prim != PTC_MISS;
+            uint32_t material = 0;
+            bool emitter = false;
+            if (isHit) {
+                material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w);
+                emitter = __ldg(&scene.materials[material].emitter) != 0;
+            }
             V3 result = mk(res4.x, res4.y, res4.z);
-            V3 modulation = mk(1.f, 1.f, 1.f);
             bool alive = true;
             if (k == 0) {
                 // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59
                 V3 color = mk(0.f, 0.f, 0.f);
                 if (!isHit) { color = envRadiance(scene, D); alive = false; }
-                else if (checkCounts(wp.startBounce, wp.lastBounce, 0)) {
-                    const DMaterial &m = scene.materials[bi.material];
-                    if (__ldg(&m.emitter) && !(dot(bi.n, bi.wo) < 0.f)) { color = mk(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2])); }
+                else if (emitter && checkCounts(wp.startBounce, wp.lastBounce, 0)) {
+                    const float4 o4 = pb.rayO[p];
+                    RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = prim;
+                    Isect bi;
+                    makeIsect(scene, mk(o4.x, o4.y, o4.z), D, hit, bi);
+                    const DMaterial &m = scene.materials[material];
+                    if (!(dot(bi.n, bi.wo) < 0.f)) { color = mk(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2])); }
                 }
                 pb.out[p] = make_float4(color.x, color.y, color.z, 0.f);
             } else {
                 const float4 mp = pb.modPdf[p], tc = pb.thrCos[p];
-                modulation = mk(mp.x, mp.y, mp.z);
+                V3 modulation = mk(mp.x, mp.y, mp.z);
                 const V3 thr = mk(tc.x, tc.y, tc.z);
                 if (flags & FLAG_DIRECT) { // direct() of vertex k, src/path_tracer.cpp:79-111
                     V3 Ld = mk(0.f, 0.f, 0.f);
                     if ((flags & FLAG_NEE) && !pb.occluded[p]) { const float4 ne = pb.nee[p]; Ld = Ld + mk(ne.x, ne.y, ne.z); }
-                    Ld = Ld + directBsdf(scene, O, tc.w, D, mp.w, thr, (flags & FLAG_DELTA) != 0, isHit, &bi);
+                    if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
+                        const float4 o4 = pb.rayO[p];
+                        const V3 O = mk(o4.x, o4.y, o4.z);
+                        Isect bi;
+                        if (isHit) { RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = prim; makeIsect(scene, O, D, hit, bi); }
+                        Ld = Ld + directBsdf(scene, O, tc.w, D, mp.w, thr, (flags & FLAG_DELTA) != 0, isHit, &bi);
+                    }
                     result = result + Ld * modulation;
                 }
                 // loop header and body of PathTracer::L, src/path_tracer.cpp:41-58
@@ -230,44 +250,79 @@ __global__ void __launch_bounds__(128) shadeKernel(DScene scene, PathBuffers pb,
                     const float invPDF = 1.f / mp.w;
                     modulation = modulation * ((thr * tc.w) * invPDF);
                     if (isBlack(modulation)) { alive = false; }
+                    else { pb.modPdf[p] = make_float4(modulation.x, modulation.y, modulation.z, mp.w); }
                 }
+                if (alive && (flags & FLAG_DIRECT)) { pb.result[p] = make_float4(result.x, result.y, result.z, res4.w); }
             }
-            if (alive) {
-                const DMaterial &m = scene.materials[bi.material];
-                Rng rng;
-                rng.initPhilox(wp.seed, slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + p / wp.nPixels);
-                rng.beginVertex((uint32_t)(k + 1));
-                BsdfSample bs;
-                bsdfSample(m, bi, rng, bs);
-                const bool wantDirect = checkCounts(wp.startBounce, wp.lastBounce, k + 1) && !__ldg(&m.emitter);
-                if (wantDirect) {
-                    V3 contribution, sd; float maxT;
-                    if (directLightsSetup(scene, m, bi, bs, rng, contribution, sd, maxT)) {
-                        pb.nee[p] = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
-                        pb.shadowD[p] = make_float4(sd.x, sd.y, sd.z, maxT);
-                        pushShadow = true;
-                    }
-                }
-                const bool wantNext = !checkDone(wp.lastBounce, k + 2);
-                if (wantDirect || wantNext) {
-                    pb.rayO[p] = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
-                    pb.rayD[p] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
-                    pb.modPdf[p] = make_float4(modulation.x, modulation.y, modulation.z, bs.pdf);
-                    pb.thrCos[p] = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
-                    const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u);
-                    pb.result[p] = make_float4(result.x, result.y, result.z, __uint_as_float(nf));
-                    pushExtend = true;
-                } else { alive = false; pushShadow = false; }
-            }
-            if (!alive) { // color += L(...), src/sample_integrator.cpp:53
+            if (alive) { cls = __ldg(&scene.materials[material].type); }
+            else { // color += L(...), src/sample_integrator.cpp:53
                 const float4 c = pb.out[p];
                 pb.out[p] = make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f);
             }
         }
-        const uint32_t e = warpAppend(nextCount, pushExtend);
+#pragma unroll
+        for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
+            if (!(classMask & (1u << t))) { continue; }
+            const uint32_t slot = warpAppend(&bc->classCount[t], cls == t);
+            if (cls == t) { pb.classQueue[t][slot] = p; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 material
+// Vertex k + 1 of every surviving path whose hit surface has material class TYPE: Intersection, BSDF sample, NEE set-up.
+template <int TYPE>
+__global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t *nextQueue, BounceCounters *next)
+{
+    const uint32_t n = bc->classCount[TYPE];
+    const uint32_t *queue = pb.classQueue[TYPE];
+    uint32_t item;
+    while (fetchWork(&bc->classCursor[TYPE], n, item)) {
+        bool pushExtend = false, pushShadow = false;
+        uint32_t p = 0;
+        if (item < n) {
+            p = queue[item];
+            const float4 o4 = pb.rayO[p], d4 = pb.rayD[p], h4 = pb.hit[p], res4 = pb.result[p];
+            const uint32_t flags = __float_as_uint(res4.w);
+            const int k = (int)(flags & FLAG_BOUNCE_MASK);
+            RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+            Isect bi;
+            makeIsect(scene, mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z), hit, bi);
+            const DMaterial &m = scene.materials[bi.material];
+            Rng rng;
+            rng.initPhilox(wp.seed, slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + p / wp.nPixels);
+            rng.beginVertex((uint32_t)(k + 1));
+            BsdfSample bs;
+            bsdfSample<TYPE>(m, bi, rng, bs);
+            const bool wantDirect = checkCounts(wp.startBounce, wp.lastBounce, k + 1) && !__ldg(&m.emitter);
+            if (wantDirect) {
+                V3 contribution, sd; float maxT;
+                if (directLightsSetup<TYPE>(scene, m, bi, bs, rng, contribution, sd, maxT)) {
+                    pb.nee[p] = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
+                    pb.shadowD[p] = make_float4(sd.x, sd.y, sd.z, maxT);
+                    pushShadow = true;
+                }
+            }
+            const bool wantNext = !checkDone(wp.lastBounce, k + 2);
+            if (wantDirect || wantNext) {
+                pb.rayO[p] = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
+                pb.rayD[p] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                const float4 mp = pb.modPdf[p]; // k = 0: not written yet, the modulation starts at 1
+                pb.modPdf[p] = k == 0 ? make_float4(1.f, 1.f, 1.f, bs.pdf) : make_float4(mp.x, mp.y, mp.z, bs.pdf);
+                pb.thrCos[p] = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
+                const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u);
+                pb.result[p] = make_float4(res4.x, res4.y, res4.z, __uint_as_float(nf));
+                pushExtend = true;
+            } else { // the path ends here: color += L(...)
+                pushShadow = false;
+                const float4 c = pb.out[p];
+                pb.out[p] = make_float4(c.x + res4.x, c.y + res4.y, c.z + res4.z, 0.f);
+            }
+        }
+        const uint32_t e = warpAppend(&next->extendCount, pushExtend);
         if (pushExtend) { nextQueue[e] = p; }
-        const uint32_t s = warpAppend(shadowCount, pushShadow);
-        if (pushShadow) { pb.shadowQueue[s] = p; }
+        const uint32_t sh = warpAppend(&next->shadowCount, pushShadow);
+        if (pushShadow) { pb.shadowQueue[sh] = p; }
     }
 }
 
@@ -311,11 +366,11 @@ __global__ void __launch_bounds__(256) gatherResolveKernel(FramebufferSet set, f
     }
 }
 
-__global__ void tallyKernel(const uint32_t *counters, unsigned long long *totals)
+__global__ void tallyKernel(const BounceCounters *counters, unsigned long long *totals)
 {
     if (threadIdx.x == 0) {
         unsigned long long closest = 0, shadow = 0;
-        for (int b = 0; b < CNT_STRIDE; b++) { closest += counters[b]; shadow += counters[CNT_STRIDE + b]; }
+        for (int b = 0; b < CNT_STRIDE; b++) { closest += counters[b].extendCount; shadow += counters[b].shadowCount; }
         totals[0] += closest; totals[1] += shadow;
     }
 }
@@ -537,7 +592,8 @@ struct ptc_ctx {
     std::vector<void *> allocations;
     DScene scene;
     PathBuffers paths; uint32_t pathCapacity = 0; std::vector<void *> pathAllocations;
-    uint32_t *counters = nullptr;
+    BounceCounters *counters = nullptr;
+    uint32_t classMask = 0; // material classes present in the scene
     unsigned long long *totals = nullptr;
     float *accumScratch = nullptr; size_t accumScratchSize = 0;
     float *framebuffer = nullptr, *gatherOut = nullptr, *gatherStage = nullptr; size_t framebufferSize = 0, gatherStageSize = 0;
@@ -546,9 +602,9 @@ struct ptc_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int numSMs = 148;
-    int gridTraverse = 0, gridShade = 0, gridSimple = 0;
+    int gridTraverse = 0, gridShade = 0, gridLogic = 0, gridSimple = 0;
     // options / stats
-    int64_t pathsPerWave = 1 << 21;
+    int64_t pathsPerWave = 1 << 24; // 16.8 M paths x 157 B = 2.6 GB of path state per wave: long queues keep 148 SMs busy through the late bounces
     bool stageTiming = false, countTraversal = false;
     uint64_t samples = 0, launches = 0;
     float lastRenderMs = 0.f;
@@ -628,7 +684,7 @@ int ptc_create(int device, ptc_ctx **out)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { ctx->numSMs = prop.multiProcessorCount; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->counters, CNT_TOTAL * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->counters, CNT_STRIDE * sizeof(BounceCounters)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->totals, 6 * sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx;
         return PTC_ERR_CUDA;
@@ -637,7 +693,9 @@ int ptc_create(int device, ptc_ctx **out)
     int perSM = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (traverseKernel<false, false>), 128, 0);
     ctx->gridTraverse = ctx->numSMs * std::max(perSM, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, logicKernel, 256, 0);
+    ctx->gridLogic = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, materialKernel<PTC_PLASTIC>, 128, 0);
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
     *out = ctx;
@@ -778,9 +836,11 @@ int ptc_commit(ptc_ctx *ctx)
     catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
 
     std::vector<DMaterial> dm(ctx->materials.size());
+    ctx->classMask = 0;
     for (size_t i = 0; i < dm.size(); i++) {
         const ptc_material_desc &d = ctx->materials[i];
         DMaterial &m = dm[i];
+        ctx->classMask |= 1u << d.type;
         memset(&m, 0, sizeof(m));
         m.type = d.type; m.distribution = d.distribution; m.albedoKind = d.albedo_kind;
         m.emitter = !(d.emit[0] == 0.f && d.emit[1] == 0.f && d.emit[2] == 0.f);
@@ -888,6 +948,12 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
         CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(uint32_t)));
         ctx->pathAllocations.push_back(*slot);
     }
+    for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
+        pb.classQueue[t] = nullptr;
+        if (!(ctx->classMask & (1u << t))) { continue; }
+        CUDA_TRY(ctx, cudaMalloc((void **)&pb.classQueue[t], (size_t)capacity * sizeof(uint32_t)));
+        ctx->pathAllocations.push_back(pb.classQueue[t]);
+    }
     ctx->pathCapacity = capacity;
     return PTC_OK;
 }
@@ -897,9 +963,8 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
 {
     const DScene &s = ctx->scene;
     PathBuffers &pb = ctx->paths;
-    uint32_t *cnt = ctx->counters;
-    uint32_t *cursors = cnt + 2 * CNT_STRIDE;
-    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_TOTAL * sizeof(uint32_t), stream));
+    BounceCounters *cnt = ctx->counters;
+    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(BounceCounters), stream));
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     unsigned long long *work = ctx->totals + 2;
     {
@@ -911,19 +976,27 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
     for (int k = 0; k <= wp.lastBounce; k++) {
         uint32_t *queue = pb.extendQueue[k & 1], *next = pb.extendQueue[(k + 1) & 1];
+        BounceCounters *bc = cnt + k;
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
-            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
-            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, cnt + k, cursors + 3 * k, work); }
+            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, &bc->extendCount, &bc->extendCursor, work); }
+            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, &bc->extendCount, &bc->extendCursor, work); }
         }
         if (k > 0) {
             StageTimer t(ctx, stream, STAGE_SHADOW);
-            if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
-            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, cnt + CNT_STRIDE + k, cursors + 3 * k + 1, work + 2); }
+            if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
-            shadeKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, cnt + k, cursors + 3 * k + 2, next, cnt + k + 1, cnt + CNT_STRIDE + k + 1);
+            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, queue, bc, ctx->classMask);
+            const int g = ctx->gridShade;
+            if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
         }
         ctx->launches += k > 0 ? 3 : 2;
     }
@@ -1242,11 +1315,11 @@ int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
 int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend, uint32_t *shadow, uint32_t capacity)
 {
     if (!ctx || !extend || !shadow) { return PTC_ERR_INVALID; }
-    uint32_t host[2 * CNT_STRIDE];
+    std::vector<BounceCounters> host(CNT_STRIDE);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    if (cudaMemcpy(host, ctx->counters, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "cudaMemcpy failed"); }
-    for (uint32_t k = 0; k < capacity && k < CNT_STRIDE; k++) { extend[k] = host[k]; shadow[k] = host[CNT_STRIDE + k]; }
+    if (cudaMemcpy(host.data(), ctx->counters, CNT_STRIDE * sizeof(BounceCounters), cudaMemcpyDeviceToHost) != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "cudaMemcpy failed"); }
+    for (uint32_t k = 0; k < capacity && k < CNT_STRIDE; k++) { extend[k] = host[k].extendCount; shadow[k] = host[k].shadowCount; }
     return PTC_OK;
 }
 

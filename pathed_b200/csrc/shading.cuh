@@ -351,10 +351,12 @@ __device__ __forceinline__ V3 microfacetF(const DMaterial &m, const Isect &i, V3
     return mk(val, val, val);
 }
 
-// Material::f(isect, wi, &pdf)
-__device__ V3 bsdfEval(const DMaterial &m, const Isect &i, V3 wiW, float &pdf)
+// Material::f(isect, wi, &pdf).  TYPE >= 0 fixes the material class at compile time (material-sorted shading queues);
+// TYPE < 0 dispatches on m.type.
+template <int TYPE = -1>
+__device__ __forceinline__ V3 bsdfEval(const DMaterial &m, const Isect &i, V3 wiW, float &pdf)
 {
-    switch (m.type) {
+    switch (TYPE >= 0 ? TYPE : m.type) {
     case PTC_LAMBERTIAN: return lambertF(m, i, wiW, pdf);
     case PTC_OREN_NAYAR: { // src/oren_nayar.cpp:21-69; back-side cases report pdf = 1 (Q12)
         pdf = 1.f;
@@ -399,14 +401,15 @@ __device__ __forceinline__ void microfacetSample(const DMaterial &m, const Isect
 }
 
 // Material::sample(isect, random)
-__device__ void bsdfSample(const DMaterial &m, const Isect &i, Rng &r, BsdfSample &s)
+template <int TYPE = -1>
+__device__ __forceinline__ void bsdfSample(const DMaterial &m, const Isect &i, Rng &r, BsdfSample &s)
 {
-    switch (m.type) {
+    switch (TYPE >= 0 ? TYPE : m.type) {
     case PTC_LAMBERTIAN: lambertSample(m, i, r, s); return;
     case PTC_OREN_NAYAR: { // src/oren_nayar.cpp:71-85
         float unused;
         const V3 l = cosineSample(r);
-        s.wi = toWorld(i, l); s.pdf = l.y * PTC_INV_PI; s.thr = bsdfEval(m, i, s.wi, unused); s.delta = false;
+        s.wi = toWorld(i, l); s.pdf = l.y * PTC_INV_PI; s.thr = bsdfEval<PTC_OREN_NAYAR>(m, i, s.wi, unused); s.delta = false;
         return;
     }
     case PTC_MIRROR: { // src/mirror.cpp:21-37
@@ -626,8 +629,9 @@ __device__ __forceinline__ void cameraRay(const DScene &s, float row, float col,
 // ------------------------------------------------------------------------------------------------ direct lighting
 // PathTracer::directSampleLights up to the shadow test (src/path_tracer.cpp:113-165): returns the contribution that
 // applies when the shadow ray is unoccluded, plus the shadow ray; false = no shadow ray needed (contribution 0)
-__device__ bool directLightsSetup(const DScene &s, const DMaterial &m, const Isect &i, const BsdfSample &bs, Rng &r,
-                                  V3 &contribution, V3 &shadowDir, float &shadowMaxT)
+template <int TYPE = -1>
+__device__ __forceinline__ bool directLightsSetup(const DScene &s, const DMaterial &m, const Isect &i, const BsdfSample &bs, Rng &r,
+                                                  V3 &contribution, V3 &shadowDir, float &shadowMaxT)
 {
     if (bs.delta) { return false; }
     SurfSample ls;
@@ -637,7 +641,7 @@ __device__ bool directLightsSetup(const DScene &s, const DMaterial &m, const Ise
     if (dot(ls.normal, wi) >= 0.f) { return false; } // back of the light
     const float pdf = solidAnglePdf(ls, i.point);
     float brdfPDF;
-    const V3 f = bsdfEval(m, i, wi, brdfPDF);
+    const V3 f = bsdfEval<TYPE>(m, i, wi, brdfPDF);
     const float w = (1 * pdf) / (1 * pdf + 1 * brdfPDF); // MIS::balanceWeight, include/mis.h:4-7
     const V3 lwo = -normalize(ld);
     const V3 Le = __ldg(&light->kind) == 2 ? envRadiance(s, -lwo) : mk(__ldg(&light->emit[0]), __ldg(&light->emit[1]), __ldg(&light->emit[2]));

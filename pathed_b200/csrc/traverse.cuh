@@ -52,6 +52,46 @@ PTC_HD uint32_t popCount(uint32_t x)
     return (uint32_t)__builtin_popcount(x);
 #endif
 }
+PTC_HD uint32_t lowestBit(uint32_t x) // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+// byte j of x as the float 32768 + byte (one PRMT on the device, no int -> float conversion)
+PTC_HD float byteToMagic(uint32_t x, int j)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7504u | ((uint32_t)j << 4)));
+#else
+    return u2f(0x47000000u | (((x >> (8 * j)) & 0xFFu) << 8));
+#endif
+}
+// a * b + c rounded towards -inf / +inf
+PTC_HD float fmaDown(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rd(a, b, c);
+#else
+    const double exact = (double)a * (double)b + (double)c;
+    float r = (float)exact;
+    if ((double)r > exact) { r = nextafterf(r, -INFINITY); }
+    return r;
+#endif
+}
+PTC_HD float fmaUp(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_ru(a, b, c);
+#else
+    const double exact = (double)a * (double)b + (double)c;
+    float r = (float)exact;
+    if ((double)r < exact) { r = nextafterf(r, INFINITY); }
+    return r;
+#endif
+}
 PTC_HD float4 loadNodeWord(const float4 *p)
 {
 #if defined(__CUDA_ARCH__)
@@ -159,7 +199,6 @@ PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounte
     uint2 ngroup = st.ngroup;
     uint2 tgroup;
     {
-        const uint32_t octInv4 = st.octInv * 0x01010101u;
         const uint32_t hitsImask = ngroup.y;
         const uint32_t childBit = highestBit(hitsImask);
         ngroup.y &= ~(1u << childBit);
@@ -171,19 +210,19 @@ PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounte
                      n3 = loadNodeWord(node + 3), n4 = loadNodeWord(node + 4);
         if (COUNT) { counters->inner++; }
         const uint32_t e = f2u(n0.w);
+        // plane distance t = (origin + q * 2^e - o) / d = q * a + b.  q is turned into a float without a conversion
+        // instruction: the byte is dropped into mantissa bits 8..15 of 2^15, which reads 32768 + q exactly, and the 32768 * a
+        // is taken out of b once per node (rounded down for entry planes, up for exit planes, so boxes stay conservative).
         const float ax = u2f((e & 0xFFu) << 23) * st.idx, ay = u2f(((e >> 8) & 0xFFu) << 23) * st.idy,
                     az = u2f(((e >> 16) & 0xFFu) << 23) * st.idz;
         const float bx = (n0.x - st.ox) * st.idx, by = (n0.y - st.oy) * st.idy, bz = (n0.z - st.oz) * st.idz;
+        const float bx0 = fmaDown(-32768.f, ax, bx), by0 = fmaDown(-32768.f, ay, by), bz0 = fmaDown(-32768.f, az, bz);
+        const float bx1 = fmaUp(-32768.f, ax, bx), by1 = fmaUp(-32768.f, ay, by), bz1 = fmaUp(-32768.f, az, bz);
         ngroup.x = f2u(n1.x);
         tgroup.x = f2u(n1.y);
-        uint32_t hitmask = 0;
+        uint32_t hits8 = 0;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const uint32_t meta4 = f2u(half ? n1.w : n1.z);
-            const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t innerMask4 = ((isInner4 >> 4) & 0x01010101u) * 0xFFu;
-            const uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1F1F1F1Fu;
-            const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
             const uint32_t qlox = f2u(half ? n2.y : n2.x), qloy = f2u(half ? n2.w : n2.z), qloz = f2u(half ? n3.y : n3.x);
             const uint32_t qhix = f2u(half ? n3.w : n3.z), qhiy = f2u(half ? n4.y : n4.x), qhiz = f2u(half ? n4.w : n4.z);
             const uint32_t xmin = st.dx < 0.f ? qhix : qlox, xmax = st.dx < 0.f ? qlox : qhix;
@@ -191,14 +230,24 @@ PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounte
             const uint32_t zmin = st.dz < 0.f ? qhiz : qloz, zmax = st.dz < 0.f ? qloz : qhiz;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int sh = 8 * j;
-                const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), ax, bx), t1x = fmaf((float)((xmax >> sh) & 0xFFu), ax, bx);
-                const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), ay, by), t1y = fmaf((float)((ymax >> sh) & 0xFFu), ay, by);
-                const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), az, bz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), az, bz);
+                const float t0x = fmaf(byteToMagic(xmin, j), ax, bx0), t1x = fmaf(byteToMagic(xmax, j), ax, bx1);
+                const float t0y = fmaf(byteToMagic(ymin, j), ay, by0), t1y = fmaf(byteToMagic(ymax, j), ay, by1);
+                const float t0z = fmaf(byteToMagic(zmin, j), az, bz0), t1z = fmaf(byteToMagic(zmax, j), az, bz1);
                 const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tnear));
                 const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, st.hit.t)) * 1.0000004f;
-                if (tmin <= tmax) { hitmask |= ((childBits4 >> sh) & 0xFFu) << ((bitIndex4 >> sh) & 0xFFu); }
+                if (tmin <= tmax) { hits8 |= 1u << (4 * half + j); }
             }
+        }
+        // octant-ordered traversal mask, assembled for the children that were hit only
+        uint32_t hitmask = 0;
+        const uint32_t metaLo = f2u(n1.z), metaHi = f2u(n1.w);
+        while (hits8) {
+            const uint32_t i = lowestBit(hits8);
+            hits8 &= hits8 - 1u;
+            const uint32_t meta = ((i & 4u ? metaHi : metaLo) >> (8u * (i & 3u))) & 0xFFu;
+            const uint32_t isInner = (meta & (meta << 1)) & 0x10u; // inner: 0b001xxxxx with xxxxx >= 24
+            const uint32_t bitIndex = (meta ^ (isInner ? st.octInv : 0u)) & 0x1Fu;
+            hitmask |= (meta >> 5) << bitIndex;
         }
         ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
         tgroup.y = hitmask & 0x00FFFFFFu;
