@@ -14,10 +14,11 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
   e2e       ptc_render: the reference-facing call with a HOST radianceLookup buffer (H2D + D2H of the fp32
             framebuffer inside the timed region), i.e. what Integrator::run's sampleImage loop would call
   roofline  the extend (closest-hit traversal) kernel: algorithmic bytes per launch from counted node visits and
-            triangle tests / mean launch duration measured live with CUDA events on the launch stream
+            triangle tests (SURVEY 8(d)) / mean launch duration measured live with CUDA events on the launch stream;
+            `traffic` = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
-L2: every wave streams its path state (2 M paths x 148 B = 310 MB, plus queues) through each stage, more than the
-126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~50 MB) is meant to be L2-resident.
+L2: every wave streams its path state (16.8 M paths x 157 B = 2.6 GB, plus queues) through each stage, far more than the
+126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~55 MB) is meant to be L2-resident.
 
 Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
 indices of every pixel, Philox-keyed by (pixel, sample, bounce)); per step one NCCL reduce of the fp32 framebuffer to
@@ -220,10 +221,23 @@ def main():
     value = samples_total / (ms * 1e-3) * 1e-6
 
     # ---- e2e: host radianceLookup through ptc_render (H2D + D2H of the framebuffer inside the timed region)
+    # N > 1: every rank makes the same host-buffer call, then the per-rank host framebuffers are summed on rank 0:
+    # pinned host -> device, NCCL reduce, device -> pinned host (all inside the timed region)
     host_accum = np.zeros((height, width, 3), np.float32)
+    pinned = torch.zeros(height * width * 3, dtype=torch.float32).pin_memory() if distributed else None
+    staged = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda") if distributed else None
 
     def step_host(i):
+        if distributed:
+            host_accum.fill(0.0)
         ctx.render(seed, sample_block(i, rank, world, spp)[0], spp, 0, last, accum=host_accum)
+        if distributed:
+            pinned.copy_(torch.from_numpy(host_accum.reshape(-1)))
+            staged.copy_(pinned, non_blocking=True)
+            reduce_framebuffer(staged, dst=0)
+            if rank == 0:
+                pinned.copy_(staged)
+            torch.cuda.synchronize()
 
     for i in range(3):
         step_host(i)
@@ -265,9 +279,16 @@ def main():
         bytes_per_launch = per_ray * extend_rays_per_launch
         ms_per_launch = tst.extend_ms / max(tst.extend_launches, 1)
         achieved = bytes_per_launch / (ms_per_launch * 1e-3) * 1e-9
+        traffic, traffic_source = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.workload == "dragon":
+            t = json.load(open(tpath))
+            # measured per ray under ncu on this workload; scaled to the rays one launch processes here
+            traffic = t["extend_dram_bytes_per_ray"] * extend_rays_per_launch
+            traffic_source = t["source"]
         total_stage = tst.extend_ms + tst.shadow_ms + tst.shade_ms + tst.other_ms
-        roofline = {"bound": "hbm", "kernel": "extendKernel (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+        roofline = {"bound": "hbm", "kernel": "traverseKernel<false> (extend: closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_note,
                     "bytes_per_ray": per_ray, "inner_visits_per_ray": cst.extend_inner_visits / max(cst.closest_rays, 1),
                     "triangle_tests_per_ray": cst.extend_triangle_tests / max(cst.closest_rays, 1),
                     "rays_per_launch": extend_rays_per_launch, "ms_per_launch": ms_per_launch,

@@ -226,6 +226,14 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_tim
  * visits and triangle tests per ray (algorithmic bytes per ray) */
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);
 
+/* host-only self-check of the BVH builder and of the traversal code it shares with the kernels (needs no GPU and no
+ * context): builds the compressed wide BVH of a triangle soup, traces `rays` (closest hit, tnear 1e-3, tfar 1e5) with the
+ * scalar traversal and by brute force over all triangles with the same triangle test.
+ * stats: [0] inner nodes, [1] leaf triangles, [2] occupied child slots, [3] max depth, [4] inner visits, [5] triangle tests */
+int ptc_bvh_selfcheck(const float *positions, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles,
+                      const ptc_ray *rays, uint32_t n_rays, float *t_bvh, uint32_t *prim_bvh, float *t_brute,
+                      uint32_t *prim_brute, uint64_t stats[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,8 @@ def build_cuda(force=False, verbose=False):
     target = os.path.join(PKG, "libpathed_cuda.so")
     deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(os.path.dirname(PKG), "include", "pathed_cuda.h")]
     if force or _stale(target, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + _sources(CSRC, (".cu",))
+        extra = os.environ.get("PTC_NVCC_DEFINES", "").split()  # tuning sweeps: e.g. -DPTC_POSTPONE_DIV=4
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + _sources(CSRC, (".cu",))
         subprocess.check_call(cmd)
     return target
 

@@ -155,43 +155,94 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
     b.build(root, 0, nPrims, 0);
     for (int a = 0; a < 3; a++) { out.sceneLo[a] = b.nodes[root].box.lo[a]; out.sceneHi[a] = b.nodes[root].box.hi[a]; }
 
-    // ---- collapse to 8-wide, breadth first so that the inner children of a node are contiguous
+    // ---- SAH-optimal collapse to 8-wide (Ylitie, Karras, Laine 2017, section 3.1): C(n, i) = cheapest way to represent the
+    // binary subtree n as a forest of at most i wide-BVH roots, bottom-up; a subtree of at most 3 triangles may become one leaf.
+    const float cNode = 1.0f, cPrim = 0.4f;
+    const size_t nBinary = b.nodeCount.load();
+    std::vector<float> cost(nBinary * 7);          // cost[n*7 + i-1] = C(n, i), i = 1..7
+    std::vector<uint8_t> splitAt(nBinary * 8, 0);  // splitAt[n*8 + j-1]: best k of C_distribute(n, j), j = 2..8
+    std::vector<uint8_t> rootIsLeaf(nBinary, 0);
+    std::vector<uint32_t> primCount(nBinary, 0);
+    {
+        std::vector<std::pair<uint32_t, bool>> todo;
+        todo.emplace_back(root, false);
+        while (!todo.empty()) {
+            const uint32_t n = todo.back().first;
+            const bool expanded = todo.back().second;
+            const Node2 &node = b.nodes[n];
+            float *c = &cost[(size_t)n * 7];
+            if (node.count) { // binary leaf
+                todo.pop_back();
+                primCount[n] = node.count;
+                for (int i = 0; i < 7; i++) { c[i] = node.box.halfArea() * (float)node.count * cPrim; }
+                rootIsLeaf[n] = 1;
+                continue;
+            }
+            if (!expanded) { todo.back().second = true; todo.emplace_back(node.left, false); todo.emplace_back(node.right, false); continue; }
+            todo.pop_back();
+            primCount[n] = primCount[node.left] + primCount[node.right];
+            const float *cl = &cost[(size_t)node.left * 7], *cr = &cost[(size_t)node.right * 7];
+            float distribute[9];
+            for (int j = 2; j <= 8; j++) {
+                float best = 3.0e38f; int bestK = 1;
+                for (int k = 1; k < j; k++) {
+                    if (k > 7 || j - k > 7) { continue; }
+                    const float v = cl[k - 1] + cr[j - k - 1];
+                    if (v < best) { best = v; bestK = k; }
+                }
+                distribute[j] = best; splitAt[(size_t)n * 8 + j - 1] = (uint8_t)bestK;
+            }
+            const float area = node.box.halfArea();
+            const float internal = distribute[8] + area * cNode;
+            const float leaf = primCount[n] <= Builder::MAX_LEAF ? area * (float)primCount[n] * cPrim : 3.0e38f;
+            rootIsLeaf[n] = leaf <= internal ? 1 : 0;
+            c[0] = std::min(leaf, internal);
+            for (int i = 2; i <= 7; i++) { c[i - 1] = std::min(distribute[i], c[i - 2]); }
+        }
+    }
+    // children of the wide node made from binary node n: follow the recorded decisions
+    struct Collector {
+        const Builder &b; const std::vector<float> &cost; const std::vector<uint8_t> &splitAt;
+        void distribute(uint32_t n, int j, uint32_t *out, int &count) const
+        {
+            const int k = splitAt[(size_t)n * 8 + j - 1];
+            place(b.nodes[n].left, k, out, count);
+            place(b.nodes[n].right, j - k, out, count);
+        }
+        void place(uint32_t m, int i, uint32_t *out, int &count) const
+        {
+            if (b.nodes[m].count) { out[count++] = m; return; }
+            const float *c = &cost[(size_t)m * 7];
+            while (i > 1 && c[i - 1] == c[i - 2]) { i--; } // C(m, i) took the C(m, i-1) branch
+            if (i == 1) { out[count++] = m; return; }
+            distribute(m, i, out, count);
+        }
+    };
+    const Collector collector = {b, cost, splitAt};
+
+    // ---- emit wide nodes breadth first so that the inner children of a node are contiguous
     struct Work { uint32_t wide, node2, depth; };
     std::queue<Work> work;
     out.nodes.emplace_back();
     work.push({0u, root, 1u});
-    if (b.nodes[root].count) {
-        // a single-leaf scene still needs an inner root: wrap the leaf as its only child
-    }
     while (!work.empty()) {
         const Work w = work.front(); work.pop();
         out.maxDepth = std::max(out.maxDepth, w.depth);
-        // gather up to 8 children: repeatedly open the inner child with the largest area
         uint32_t child[8]; int n = 0;
         const Node2 &self = b.nodes[w.node2];
-        if (self.count) { child[n++] = w.node2; }
-        else { child[n++] = self.left; child[n++] = self.right; }
-        while (n < 8) {
-            int best = -1; float bestArea = -1.f;
-            for (int i = 0; i < n; i++) {
-                const Node2 &c = b.nodes[child[i]];
-                if (c.count == 0 && c.box.halfArea() > bestArea) { bestArea = c.box.halfArea(); best = i; }
-            }
-            if (best < 0) { break; }
-            const Node2 &c = b.nodes[child[best]];
-            child[best] = c.left; child[n++] = c.right;
-        }
+        if (self.count || rootIsLeaf[w.node2]) { child[n++] = w.node2; } // a single-leaf scene still needs an inner root
+        else { collector.distribute(w.node2, 8, child, n); }
         // slot assignment: child -> slot minimising (centroid - node centroid) . octant direction, greedily,
         // so that visiting slots in (slot ^ ray octant) order approximates front-to-back
         float center[3];
         for (int a = 0; a < 3; a++) { center[a] = 0.5f * (self.box.lo[a] + self.box.hi[a]); }
-        float cost[8][8];
+        float slotCost[8][8];
         for (int c = 0; c < n; c++) {
             const Box &cb = b.nodes[child[c]].box;
             for (int s = 0; s < 8; s++) {
                 const float ds[3] = {(s & 4) ? -1.f : 1.f, (s & 2) ? -1.f : 1.f, (s & 1) ? -1.f : 1.f};
-                cost[c][s] = 0.f;
-                for (int a = 0; a < 3; a++) { cost[c][s] += (0.5f * (cb.lo[a] + cb.hi[a]) - center[a]) * ds[a]; }
+                slotCost[c][s] = 0.f;
+                for (int a = 0; a < 3; a++) { slotCost[c][s] += (0.5f * (cb.lo[a] + cb.hi[a]) - center[a]) * ds[a]; }
             }
         }
         int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false};
@@ -200,7 +251,7 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
             float bestCost = 3.0e38f; int bc = -1, bs = -1;
             for (int c = 0; c < n; c++) {
                 if (slotOf[c] >= 0) { continue; }
-                for (int s = 0; s < 8; s++) { if (!slotUsed[s] && cost[c][s] < bestCost) { bestCost = cost[c][s]; bc = c; bs = s; } }
+                for (int s = 0; s < 8; s++) { if (!slotUsed[s] && slotCost[c][s] < bestCost) { bestCost = slotCost[c][s]; bc = c; bs = s; } }
             }
             slotOf[bc] = bs; slotUsed[bs] = true;
         }
@@ -232,7 +283,8 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
                 uint8_t *hi = a == 0 ? node.qhix : (a == 1 ? node.qhiy : node.qhiz);
                 lo[s] = (uint8_t)qlo; hi[s] = (uint8_t)qhi;
             }
-            if (c.count == 0) {
+            const uint32_t leafPrims = c.count ? c.count : (rootIsLeaf[c2] ? primCount[c2] : 0u);
+            if (leafPrims == 0) {
                 node.imask |= (uint8_t)(1u << s);
                 node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 const uint32_t wideIndex = (uint32_t)out.nodes.size();
@@ -240,9 +292,9 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
                 work.push({wideIndex, c2, w.depth + 1});
             } else {
                 const uint32_t offset = (uint32_t)out.triangles.size() - node.triBase;
-                const uint32_t unary = c.count == 1 ? 1u : (c.count == 2 ? 3u : 7u);
+                const uint32_t unary = leafPrims == 1 ? 1u : (leafPrims == 2 ? 3u : 7u);
                 node.meta[s] = (uint8_t)((unary << 5) | offset);
-                for (uint32_t i = 0; i < c.count; i++) {
+                for (uint32_t i = 0; i < leafPrims; i++) {
                     const uint32_t p = b.order[c.first + i];
                     const float *v0 = positions4 + 4 * (size_t)indices4[4 * (size_t)p];
                     const float *v1 = positions4 + 4 * (size_t)indices4[4 * (size_t)p + 1];

@@ -132,8 +132,14 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 // Persistent warps with lane refill: every lane owns one ray; when a ray finishes its lane goes idle, and once at most
 // PTC_REFILL_BELOW lanes are still busy the warp pulls new rays for all idle lanes from the queue cursor with a single
 // atomic.  Keeps SIMT lanes busy although rays take very different numbers of steps (sky rays: 2-3, mesh rays: 20+).
+// Inside an iteration the warp runs the node phase for every busy ray, then triangle rounds (one triangle per ray and
+// round) while at least 1/PTC_POSTPONE_DIV of the busy rays have a triangle pending; the rays left over put their
+// triangle group back on their stack and test it in a later, fuller round.
 #ifndef PTC_REFILL_BELOW
 #define PTC_REFILL_BELOW 24
+#endif
+#ifndef PTC_POSTPONE_DIV
+#define PTC_POSTPONE_DIV 1000 /* off: measured slower on B200 (profiles/r01_sweep_postpone.txt) */
 #endif
 
 template <bool ANY, bool COUNT>
@@ -166,22 +172,34 @@ __global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers 
                         const float4 d = pb.rayD[p];
                         traversalInit(st, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR);
                     }
+                    if (!hasNodes) { st.ngroup.y = 0u; }
                     busy = true;
                 }
             }
             more = base + k < n;
         }
-        if (!__any_sync(0xFFFFFFFFu, busy)) { break; }
+        uint32_t active = __ballot_sync(0xFFFFFFFFu, busy);
+        if (active == 0u) { break; }
         for (;;) {
-            if (busy) {
-                if (!hasNodes || traversalStep<ANY, COUNT>(scene.bvh, st, &tc)) {
-                    const bool found = traversalSpheres<ANY>(scene.bvh, st);
-                    if (ANY) { pb.occluded[p] = found ? 1 : 0; }
-                    else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
-                    busy = false;
+            if (busy && hasNodes) { traversalNode<COUNT>(scene.bvh, st, &tc); }
+            bool done = false; // this ray needs no further BVH work
+            for (;;) { // triangle rounds, warp-uniform control flow
+                bool pending = busy && !done && st.tgroup.y != 0u;
+                const uint32_t want = __ballot_sync(0xFFFFFFFFu, pending);
+                if (want == 0u) { break; }
+                if (__popc(want) * PTC_POSTPONE_DIV < __popc(active)) {
+                    if (pending && traversalPostpone(st)) { pending = false; }
+                    if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
                 }
+                if (pending && traversalTriangle<COUNT>(scene.bvh, st, &tc) && ANY) { done = true; }
             }
-            const uint32_t active = __ballot_sync(0xFFFFFFFFu, busy);
+            if (busy && (done || traversalPop(st))) {
+                const bool found = traversalSpheres<ANY>(scene.bvh, st);
+                if (ANY) { pb.occluded[p] = found ? 1 : 0; }
+                else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
+                busy = false;
+            }
+            active = __ballot_sync(0xFFFFFFFFu, busy);
             if (active == 0u || (more && __popc(active) <= PTC_REFILL_BELOW)) { break; }
         }
     }
@@ -1351,6 +1369,42 @@ int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t 
     for (uint32_t i = 0; i < n; i++) { traverseReference(ctx->bvh, rays[i].origin, rays[i].direction, PTC_TNEAR, PTC_TFAR, false, nullptr, nullptr, &c); }
     if (inner) { *inner = c.innerVisits; }
     if (tris) { *tris = c.triangleTests; }
+    return PTC_OK;
+}
+
+int ptc_bvh_selfcheck(const float *P, uint32_t nv, const uint32_t *I, uint32_t nt, const ptc_ray *rays, uint32_t nRays, float *tBvh,
+                      uint32_t *primBvh, float *tBrute, uint32_t *primBrute, uint64_t stats[6])
+{
+    if (!P || !I || !stats || (nRays && (!rays || !tBvh || !primBvh || !tBrute || !primBrute))) { return PTC_ERR_INVALID; }
+    std::vector<float> positions4((size_t)nv * 4, 0.f);
+    std::vector<uint32_t> prims4((size_t)nt * 4, 0u);
+    for (uint32_t v = 0; v < nv; v++) { for (int a = 0; a < 3; a++) { positions4[4 * (size_t)v + a] = P[3 * (size_t)v + a]; } }
+    for (uint32_t t = 0; t < nt; t++) {
+        for (int a = 0; a < 3; a++) { if (I[3 * (size_t)t + a] >= nv) { return PTC_ERR_INVALID; } prims4[4 * (size_t)t + a] = I[3 * (size_t)t + a]; }
+    }
+    WideBVH bvh;
+    try { buildWideBVH(positions4.data(), prims4.data(), nt, bvh); } catch (const std::exception &) { return PTC_ERR_INVALID; }
+    uint64_t slots = 0;
+    for (const WideNode &n : bvh.nodes) { for (int s = 0; s < 8; s++) { slots += n.meta[s] ? 1 : 0; } }
+    TraversalCounts counts;
+    for (uint32_t r = 0; r < nRays; r++) {
+        const float *o = rays[r].origin, *d = rays[r].direction;
+        tBvh[r] = PTC_TFAR; primBvh[r] = PTC_MISS;
+        traverseReference(bvh, o, d, PTC_TNEAR, PTC_TFAR, false, &tBvh[r], &primBvh[r], &counts);
+        float best = PTC_TFAR; uint32_t bestPrim = PTC_MISS; bool found = false;
+        for (const LeafTriangle &tri : bvh.triangles) {
+            const float4 a = make_float4(tri.v0[0], tri.v0[1], tri.v0[2], 0.f), b = make_float4(tri.e1[0], tri.e1[1], tri.e1[2], 0.f),
+                         c = make_float4(tri.e2[0], tri.e2[1], tri.e2[2], 0.f);
+            float t, u, v;
+            if (triangleTest(a, b, c, o[0], o[1], o[2], d[0], d[1], d[2], PTC_TNEAR, best, t, u, v)) {
+                if (!(found && t == best && tri.prim < bestPrim)) { best = t; bestPrim = tri.prim; }
+                found = true;
+            }
+        }
+        tBrute[r] = best; primBrute[r] = bestPrim;
+    }
+    stats[0] = bvh.nodes.size(); stats[1] = bvh.triangles.size(); stats[2] = slots; stats[3] = bvh.maxDepth;
+    stats[4] = counts.innerVisits; stats[5] = counts.triangleTests;
     return PTC_OK;
 }
 

@@ -164,12 +164,11 @@ struct TraverseCounters { uint32_t inner, tris; };
 
 #define PTC_STACK_SIZE 40
 
-// Per-ray traversal state: lets a kernel interleave single steps of many rays (persistent warps that refill idle lanes)
-// while the per-ray visiting order stays exactly the one of the plain loop below.
+// Per-ray traversal state: lets a kernel interleave the phases of many rays (persistent warps that refill idle lanes).
 struct TraversalState {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tnear;
     uint32_t octInv;
-    uint2 ngroup;
+    uint2 ngroup, tgroup;
     int sp;
     bool found;
     RayHit hit;
@@ -186,17 +185,25 @@ PTC_HD void traversalInit(TraversalState &st, float ox, float oy, float oz, floa
     st.idz = 1.f / (fabsf(dz) > eps ? dz : (f2u(dz) & 0x80000000u ? -eps : eps));
     st.octInv = 7u - ((dx < 0.f ? 4u : 0u) | (dy < 0.f ? 2u : 0u) | (dz < 0.f ? 1u : 0u));
     st.ngroup = make_uint2(0u, 0x80000000u); // root = slot (7 ^ octInv) of a virtual parent with no siblings
+    st.tgroup = make_uint2(0u, 0u);
     st.sp = 0;
     st.found = false;
     st.hit.t = tfar; st.hit.u = 0.f; st.hit.v = 0.f; st.hit.prim = PTC_MISS;
 }
 
-// One step = visit one inner node (8 quantised child boxes), test the triangles of its leaf children that were hit,
-// pop the next node group.  Returns true when the BVH part of the traversal is finished (ANY: or a hit was found).
-template <bool ANY, bool COUNT>
-PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
+// The traversal is split into three per-ray phases so that a kernel can run each phase for all the rays of a warp that
+// need it (CWBVH-style triangle postponing, Ylitie et al. 2017): the node phase visits one inner node, the triangle phase
+// tests ONE triangle of the pending triangle group, the pop phase fetches the next group from the stack.  A stack entry is a
+// node group (child base, hit bits << 24 | inner mask) or a postponed triangle group (triangle base, triangle bits < 2^24).
+template <bool COUNT>
+PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
 {
     uint2 ngroup = st.ngroup;
+    if (!(ngroup.y & 0xFF000000u)) { // a postponed triangle group came off the stack
+        st.tgroup = ngroup;
+        st.ngroup = make_uint2(0u, 0u);
+        return;
+    }
     uint2 tgroup;
     {
         const uint32_t hitsImask = ngroup.y;
@@ -252,26 +259,43 @@ PTC_HD bool traversalStep(const BvhView &bvh, TraversalState &st, TraverseCounte
         ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
         tgroup.y = hitmask & 0x00FFFFFFu;
     }
-    while (tgroup.y) {
-        const uint32_t bit = highestBit(tgroup.y);
-        tgroup.y &= ~(1u << bit);
-        const float4 *tri = bvh.triangles + (size_t)(tgroup.x + bit) * 3;
-        const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
-        if (COUNT) { counters->tris++; }
-        float t, u, v;
-        if (triangleTest(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, u, v)) {
-            const uint32_t prim = f2u(a.w);
-            // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
-            if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.prim = prim; }
-            st.found = true;
-            if (ANY) { return true; }
-        }
-    }
-    if (!(ngroup.y & 0xFF000000u)) {
-        if (st.sp == 0) { return true; }
-        ngroup = st.stack[--st.sp];
-    }
     st.ngroup = ngroup;
+    st.tgroup = tgroup;
+}
+
+// Tests one triangle of the pending group (precondition: st.tgroup.y != 0).  Returns true when a hit was accepted.
+template <bool COUNT>
+PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
+{
+    const uint32_t bit = highestBit(st.tgroup.y);
+    st.tgroup.y &= ~(1u << bit);
+    const float4 *tri = bvh.triangles + (size_t)(st.tgroup.x + bit) * 3;
+    const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
+    if (COUNT) { counters->tris++; }
+    float t, u, v;
+    if (!triangleTest(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, u, v)) { return false; }
+    const uint32_t prim = f2u(a.w);
+    // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
+    if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.prim = prim; }
+    st.found = true;
+    return true;
+}
+
+// Puts the pending triangle group back on the stack (tested later, together with other rays' triangles); false = no room.
+PTC_HD bool traversalPostpone(TraversalState &st)
+{
+    if (st.sp >= PTC_STACK_SIZE) { return false; }
+    st.stack[st.sp++] = st.tgroup;
+    st.tgroup.y = 0u;
+    return true;
+}
+
+// Next group once the current node group has no inner hits left.  Returns true when the BVH part of the traversal is finished.
+PTC_HD bool traversalPop(TraversalState &st)
+{
+    if (st.ngroup.y & 0xFF000000u) { return false; }
+    if (st.sp == 0) { return true; }
+    st.ngroup = st.stack[--st.sp];
     return false;
 }
 
@@ -298,7 +322,14 @@ PTC_HD bool traverseBVH(const BvhView &bvh, float ox, float oy, float oz, float 
 {
     TraversalState st;
     traversalInit(st, ox, oy, oz, dx, dy, dz, tnear, tfar);
-    if (bvh.nNodes) { while (!traversalStep<ANY, COUNT>(bvh, st, counters)) {} }
+    if (bvh.nNodes) { // one ray on its own: node, all of its triangles, pop (nothing is postponed)
+        for (;;) {
+            traversalNode<COUNT>(bvh, st, counters);
+            bool stop = false;
+            while (st.tgroup.y) { if (traversalTriangle<COUNT>(bvh, st, counters) && ANY) { stop = true; break; } }
+            if (stop || traversalPop(st)) { break; }
+        }
+    }
     const bool found = traversalSpheres<ANY>(bvh, st);
     hit = st.hit;
     return found;
