@@ -102,7 +102,9 @@ def run_reference(workload, steps, warmup, spp_per_step=REF_SPP_PER_STEP):
         cmd = [binary, "--root", ROOT, job("timed", steps * spp_per_step)]
         if warmup > 0:
             cmd += ["--warmup", job("warmup", warmup * spp_per_step)]
-        out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core
+        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+        out = subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout
     line = [l for l in out.splitlines() if l.startswith("REF_RESULT")][-1]
     r = json.loads(line[len("REF_RESULT "):])
     r["spp_per_step"] = spp_per_step

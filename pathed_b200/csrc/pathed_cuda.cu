@@ -212,8 +212,9 @@ __global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers 
 __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;
-    uint32_t item;
-    while (fetchWork(&bc->logicCursor, n, item)) {
+    // uniform cost per path: static warp-strided assignment (whole warps stay in the loop together for the ballots below)
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t item = base + (threadIdx.x & 31u);
         int cls = -1;
         uint32_t p = 0;
         if (item < n) {
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
 {
     const uint32_t n = bc->classCount[TYPE];
     const uint32_t *queue = pb.classQueue[TYPE];
-    uint32_t item;
-    while (fetchWork(&bc->classCursor[TYPE], n, item)) {
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t item = base + (threadIdx.x & 31u);
         bool pushExtend = false, pushShadow = false;
         uint32_t p = 0;
         if (item < n) {
@@ -799,6 +800,7 @@ int ptc_add_sphere(ptc_ctx *ctx, const float cr[4], uint32_t material, uint32_t 
 int ptc_set_environment(ptc_ctx *ctx, const float *rgba, int w, int h, float scale, const float m2w[16], const float w2m[16])
 {
     if (!ctx || !rgba || w <= 0 || h <= 0 || !m2w || !w2m) { return PTC_ERR_INVALID; }
+    if (w > 65535 || h > 65535) { CTX_FAIL(ctx, PTC_ERR_INVALID, "environment map larger than 65535 texels on a side"); }
     if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
     ctx->envRgba.assign(rgba, rgba + (size_t)w * h * 4);
     ctx->envW = w; ctx->envH = h; ctx->envScale = scale;
@@ -827,6 +829,24 @@ int ptc_set_camera(ptc_ctx *ctx, const float o[3], const float t[3], const float
         ctx->scene.vfov = vfov; ctx->scene.width = w; ctx->scene.height = h;
     }
     return PTC_OK;
+}
+
+// guide[g] = first i with cdf[i] >= g / G, g = 0 .. G (n - 1 when there is none)
+static void buildGuide(const float *cdf, int n, int G, uint16_t *guide)
+{
+    int i = 0;
+    for (int g = 0; g <= G; g++) {
+        const float threshold = (float)g / (float)G;
+        while (i < n - 1 && cdf[i] < threshold) { i++; }
+        guide[g] = (uint16_t)i;
+    }
+}
+static int guideSize(int n)
+{
+    if (n > 65535) { return 1; }
+    int G = 1;
+    while (G * 8 <= n && G < 1024) { G *= 2; }
+    return G;
 }
 
 // src/distribution.cpp:6-33
@@ -934,6 +954,12 @@ int ptc_commit(ptc_ctx *ctx)
             theta[t] = thetaSum;
         }
         s.envThetaEmpty = buildCdf(theta.data(), h, thetaCdf.data()) ? 1 : 0;
+        s.envThetaG = guideSize(h); s.envPhiG = guideSize(w);
+        std::vector<uint16_t> thetaGuide((size_t)s.envThetaG + 1), phiGuide((size_t)h * (s.envPhiG + 1));
+        buildGuide(thetaCdf.data(), h, s.envThetaG, thetaGuide.data());
+        for (int t = 0; t < h; t++) { buildGuide(&phiCdf[(size_t)t * w], w, s.envPhiG, &phiGuide[(size_t)t * (s.envPhiG + 1)]); }
+        if ((rc = upload(ctx, thetaGuide.data(), thetaGuide.size(), &s.envThetaGuide, A))) { return rc; }
+        if ((rc = upload(ctx, phiGuide.data(), phiGuide.size(), &s.envPhiGuide, A))) { return rc; }
         if ((rc = upload(ctx, (const float4 *)ctx->envRgba.data(), (size_t)w * h, &s.envRgba, A))) { return rc; }
         if ((rc = upload(ctx, thetaCdf.data(), thetaCdf.size(), &s.envThetaCdf, A))) { return rc; }
         if ((rc = upload(ctx, phiCdf.data(), phiCdf.size(), &s.envPhiCdf, A))) { return rc; }

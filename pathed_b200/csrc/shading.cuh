@@ -28,7 +28,8 @@ __device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }            // src/vector.cpp:18-21
 __device__ __forceinline__ float length(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }          // :28-35
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x)); } // :37-44
-__device__ __forceinline__ V3 normalize(V3 a) { const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return mk(a.x / n, a.y / n, a.z / n); } // :46-62
+// :46-62
+__device__ __forceinline__ V3 normalize(V3 a) { const float n = sqrtIeee(a.x * a.x + a.y * a.y + a.z * a.z); return mk(divIeee(a.x, n), divIeee(a.y, n), divIeee(a.z, n)); }
 __device__ __forceinline__ V3 reflect(V3 w, V3 n) { return ((n * dot(w, n)) * 2.f) - w; }                    // :64-67
 __device__ __forceinline__ bool isBlack(V3 c) { return c.x == 0.f && c.y == 0.f && c.z == 0.f; }              // src/color.cpp:14-17
 __device__ __forceinline__ bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
@@ -67,6 +68,10 @@ struct DScene {
     const float4 *envRgba;
     const float *envThetaCdf, *envPhiCdf;
     const uint8_t *envPhiEmpty;
+    // guide tables: guide[g] = first index whose cdf value is >= g / G (G a power of two), so a sample in [g/G, (g+1)/G) only
+    // has to search cdf[guide[g] .. guide[g+1]]; same index as the full search, a handful of loads instead of log2(n)
+    const uint16_t *envThetaGuide, *envPhiGuide;
+    int32_t envThetaG, envPhiG;
     float envM2W[12], envW2M[12];
     float camToWorld[12];
     float vfov;
@@ -204,15 +209,15 @@ __device__ __forceinline__ void makeIsect(const DScene &s, V3 O, V3 D, const Ray
 // ------------------------------------------------------------------------------------------------ BSDFs
 // include/tangent_frame.h (local frame is y-up)
 __device__ __forceinline__ float tfCos2(V3 v) { return v.y * v.y; }
-__device__ __forceinline__ float tfSin(V3 v) { return sqrtf(fmaxf(0.f, 1.f - tfCos2(v))); }
+__device__ __forceinline__ float tfSin(V3 v) { return sqrtIeee(fmaxf(0.f, 1.f - tfCos2(v))); }
 __device__ __forceinline__ float tfSin2(V3 v) { return 1.f - tfCos2(v); }
 __device__ __forceinline__ float tfTan(V3 v) { return tfSin(v) / v.y; }
-__device__ __forceinline__ float tfTan2(V3 v) { return tfSin2(v) / tfCos2(v); }
+__device__ __forceinline__ float tfTan2(V3 v) { return divIeee(tfSin2(v), tfCos2(v)); }
 __device__ __forceinline__ float tfCosPhi(V3 v) // :69-76
 {
     const float s = tfSin(v);
     if (s == 0.f) { return 1.f; }
-    return clampf(v.x / s, -1.f, 1.f);
+    return clampf(divIeee(v.x, s), -1.f, 1.f);
 }
 __device__ __forceinline__ float tfSinPhi(V3 v) // :11-37, :83-92 (axis snap at +-0.9999)
 {
@@ -226,7 +231,7 @@ __device__ __forceinline__ float tfSinPhi(V3 v) // :11-37, :83-92 (axis snap at 
     else if (v.z <= -max) { c = mk(0.f, 0.f, -1.f); }
     const float s = tfSin(c);
     if (s == 0.f) { return 0.f; }
-    return clampf(c.z / s, -1.f, 1.f);
+    return clampf(divIeee(c.z, s), -1.f, 1.f);
 }
 
 __device__ __forceinline__ void cartToSph(V3 c, float &phi, float &theta) // src/coordinate.cpp:7-19
@@ -278,7 +283,7 @@ __device__ __forceinline__ float mfD(const DMaterial &m, V3 wh) // src/beckmann.
     const float cos4 = cos2 * cos2;
     if (m.distribution == PTC_BECKMANN) {
         const float cp = tfCosPhi(wh), sp = tfSinPhi(wh);
-        const float num = expf(-tan2 * (((cp * cp) / alpha2) + ((sp * sp) / alpha2)));
+        const float num = expf(-tan2 * (divIeee(cp * cp, alpha2) + divIeee(sp * sp, alpha2)));
         const float den = (float)(PTC_PI_D * (double)alpha2 * (double)cos4);
         return num / den;
     }
@@ -544,6 +549,17 @@ __device__ __forceinline__ int cdfSample(const float *cdf, int n, float xi, floa
     pdf = lo > 0 ? __ldg(cdf + lo) - __ldg(cdf + lo - 1) : __ldg(cdf);
     return lo;
 }
+__device__ __forceinline__ int cdfSampleGuided(const float *cdf, const uint16_t *guide, int G, float xi, float &pdf)
+{
+    const int g = (int)(xi * (float)G); // exact: G is a power of two, xi < 1
+    int lo = __ldg(guide + g), hi = __ldg(guide + g + 1);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (xi <= __ldg(cdf + mid)) { hi = mid; } else { lo = mid + 1; }
+    }
+    pdf = lo > 0 ? __ldg(cdf + lo) - __ldg(cdf + lo - 1) : __ldg(cdf);
+    return lo;
+}
 __device__ float envPdf(const DScene &s, V3 dir) // EnvironmentLight::emitPDF, src/environment_light.cpp:117-138
 {
     float phi, theta;
@@ -559,8 +575,8 @@ __device__ float envPdf(const DScene &s, V3 dir) // EnvironmentLight::emitPDF, s
 __device__ void envSample(const DScene &s, V3 ref, Rng &r, SurfSample &out) // src/environment_light.cpp:82-105
 {
     float tp, pp;
-    const int ts = cdfSample(s.envThetaCdf, s.envH, r.next(), tp);
-    const int ps = cdfSample(s.envPhiCdf + (size_t)ts * s.envW, s.envW, r.next(), pp);
+    const int ts = cdfSampleGuided(s.envThetaCdf, s.envThetaGuide, s.envThetaG, r.next(), tp);
+    const int ps = cdfSampleGuided(s.envPhiCdf + (size_t)ts * s.envW, s.envPhiGuide + (size_t)ts * (s.envPhiG + 1), s.envPhiG, r.next(), pp);
     const float phiC = (ps + 0.5f) / s.envW;
     const float thetaC = (ts + 0.5f) / s.envH;
     const float phi = phiC * PTC_TWO_PI_F;

@@ -36,6 +36,25 @@ PTC_HD float u2f(uint32_t u)
     union { float f; uint32_t u; } c; c.u = u; return c.f;
 #endif
 }
+// IEEE-rounded division / square root regardless of compiler flags: hit records must match Embree's, and unit vectors feed
+// 1 - cos^2 terms whose cancellation multiplies every ulp (a fast-math build was measured: Beckmann alpha = 0.005 eval and
+// sample fixtures miss the 1e-5 gate), so the library is built with the precise forms throughout.
+PTC_HD float divIeee(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+PTC_HD float sqrtIeee(float a)
+{
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
 PTC_HD uint32_t highestBit(uint32_t x) // x != 0
 {
 #if defined(__CUDA_ARCH__)
@@ -135,21 +154,21 @@ PTC_HD bool triangleTest(const float4 a, const float4 b, const float4 c, float o
     if (!(den != 0.f && U >= 0.f && V >= 0.f && U + V <= absDen)) { return false; }
     const float T = u2f(f2u(edot(ngx, ngy, ngz, cx, cy, cz)) ^ sgn);
     if (!(absDen * tnear < T && T <= absDen * tfar)) { return false; }
-    t = T / absDen; u = U / absDen; v = V / absDen;
+    t = divIeee(T, absDen); u = divIeee(U, absDen); v = divIeee(V, absDen);
     return true;
 }
 
 PTC_HD bool sphereTest(const float4 s, float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar,
                        float &t, float &ngx, float &ngy, float &ngz)
 {
-    const float rd2 = 1.f / edot(dx, dy, dz, dx, dy, dz);
+    const float rd2 = divIeee(1.f, edot(dx, dy, dz, dx, dy, dz));
     const float c0x = s.x - ox, c0y = s.y - oy, c0z = s.z - oz;
     const float projC0 = edot(c0x, c0y, c0z, dx, dy, dz) * rd2;
     const float px = c0x - dx * projC0, py = c0y - dy * projC0, pz = c0z - dz * projC0;
     const float l2 = edot(px, py, pz, px, py, pz);
     const float r2 = s.w * s.w;
     if (!(l2 <= r2)) { return false; }
-    float td = sqrtf((r2 - l2) * rd2);
+    float td = sqrtIeee((r2 - l2) * rd2);
     const float tIn = projC0 - td, tOut = projC0 + td;
     const bool validIn = (tIn > tnear) && (tIn < tfar);
     const bool validOut = !validIn && (tOut > tnear) && (tOut < tfar);
