@@ -142,10 +142,19 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 #define PTC_POSTPONE_DIV 1000 /* off: measured slower on B200 (profiles/r01_sweep_postpone.txt) */
 #endif
 
+// 48 registers -> 10 resident CTAs per SM; forcing 12 or 16 CTAs (40 / 32 registers) spills and was measured slower
+// (profiles/r01_sweep_occupancy.txt)
+#ifdef PTC_TRAVERSE_MIN_BLOCKS
+#define PTC_TRAVERSE_BOUNDS __launch_bounds__(128, PTC_TRAVERSE_MIN_BLOCKS)
+#else
+#define PTC_TRAVERSE_BOUNDS __launch_bounds__(128)
+#endif
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
+__global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
                                                       unsigned long long *work)
 {
+    __shared__ uint2 fastStack[(PTC_FAST_STACK > 0 ? PTC_FAST_STACK : 1) * PTC_FAST_STRIDE]; // [entry][thread]: conflict-free 64-bit accesses
+    uint2 *const fast = fastStack + threadIdx.x;
     const uint32_t n = *count;
     const uint32_t lane = threadIdx.x & 31u;
     TraverseCounters tc = {0, 0};
@@ -181,19 +190,19 @@ __global__ void __launch_bounds__(128) traverseKernel(DScene scene, PathBuffers 
         uint32_t active = __ballot_sync(0xFFFFFFFFu, busy);
         if (active == 0u) { break; }
         for (;;) {
-            if (busy && hasNodes) { traversalNode<COUNT>(scene.bvh, st, &tc); }
+            if (busy && hasNodes) { traversalNode<COUNT>(scene.bvh, st, &tc, fast); }
             bool done = false; // this ray needs no further BVH work
             for (;;) { // triangle rounds, warp-uniform control flow
                 bool pending = busy && !done && st.tgroup.y != 0u;
                 const uint32_t want = __ballot_sync(0xFFFFFFFFu, pending);
                 if (want == 0u) { break; }
                 if (__popc(want) * PTC_POSTPONE_DIV < __popc(active)) {
-                    if (pending && traversalPostpone(st)) { pending = false; }
+                    if (pending && traversalPostpone(st, fast)) { pending = false; }
                     if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
                 }
                 if (pending && traversalTriangle<COUNT>(scene.bvh, st, &tc) && ANY) { done = true; }
             }
-            if (busy && (done || traversalPop(st))) {
+            if (busy && (done || traversalPop(st, fast))) {
                 const bool found = traversalSpheres<ANY>(scene.bvh, st);
                 if (ANY) { pb.occluded[p] = found ? 1 : 0; }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }

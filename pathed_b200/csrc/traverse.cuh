@@ -194,6 +194,27 @@ struct TraversalState {
     uint2 stack[PTC_STACK_SIZE];
 };
 
+// The first PTC_FAST_STACK entries live in shared memory when a kernel provides a slice (fast != nullptr; entry e of this
+// ray at fast[e * PTC_FAST_STRIDE]): pushes and pops then cost no L1/L2 traffic, which the node fetches need.  Deeper entries,
+// and all entries of the scalar callers, go to the local-memory array.
+#ifndef PTC_FAST_STACK
+#define PTC_FAST_STACK 8
+#endif
+#define PTC_FAST_STRIDE 128 /* = threads per CTA of the traversal kernels */
+
+PTC_HD void stackPush(TraversalState &st, uint2 v, uint2 *fast)
+{
+    if (fast && st.sp < PTC_FAST_STACK) { fast[st.sp * PTC_FAST_STRIDE] = v; }
+    else { st.stack[st.sp] = v; }
+    st.sp++;
+}
+PTC_HD uint2 stackPop(TraversalState &st, uint2 *fast)
+{
+    st.sp--;
+    if (fast && st.sp < PTC_FAST_STACK) { return fast[st.sp * PTC_FAST_STRIDE]; }
+    return st.stack[st.sp];
+}
+
 PTC_HD void traversalInit(TraversalState &st, float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar)
 {
     st.ox = ox; st.oy = oy; st.oz = oz; st.dx = dx; st.dy = dy; st.dz = dz; st.tnear = tnear;
@@ -215,7 +236,7 @@ PTC_HD void traversalInit(TraversalState &st, float ox, float oy, float oz, floa
 // tests ONE triangle of the pending triangle group, the pop phase fetches the next group from the stack.  A stack entry is a
 // node group (child base, hit bits << 24 | inner mask) or a postponed triangle group (triangle base, triangle bits < 2^24).
 template <bool COUNT>
-PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
+PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounters *counters, uint2 *fast = nullptr)
 {
     uint2 ngroup = st.ngroup;
     if (!(ngroup.y & 0xFF000000u)) { // a postponed triangle group came off the stack
@@ -228,7 +249,7 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
         const uint32_t hitsImask = ngroup.y;
         const uint32_t childBit = highestBit(hitsImask);
         ngroup.y &= ~(1u << childBit);
-        if ((ngroup.y & 0xFF000000u) && st.sp < PTC_STACK_SIZE) { st.stack[st.sp++] = ngroup; }
+        if ((ngroup.y & 0xFF000000u) && st.sp < PTC_STACK_SIZE) { stackPush(st, ngroup, fast); }
         const uint32_t slot = (childBit - 24u) ^ st.octInv;
         const uint32_t relative = popCount(hitsImask & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4 *node = bvh.nodes + (size_t)(ngroup.x + relative) * 5;
@@ -301,20 +322,20 @@ PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCo
 }
 
 // Puts the pending triangle group back on the stack (tested later, together with other rays' triangles); false = no room.
-PTC_HD bool traversalPostpone(TraversalState &st)
+PTC_HD bool traversalPostpone(TraversalState &st, uint2 *fast = nullptr)
 {
     if (st.sp >= PTC_STACK_SIZE) { return false; }
-    st.stack[st.sp++] = st.tgroup;
+    stackPush(st, st.tgroup, fast);
     st.tgroup.y = 0u;
     return true;
 }
 
 // Next group once the current node group has no inner hits left.  Returns true when the BVH part of the traversal is finished.
-PTC_HD bool traversalPop(TraversalState &st)
+PTC_HD bool traversalPop(TraversalState &st, uint2 *fast = nullptr)
 {
     if (st.ngroup.y & 0xFF000000u) { return false; }
     if (st.sp == 0) { return true; }
-    st.ngroup = st.stack[--st.sp];
+    st.ngroup = stackPop(st, fast);
     return false;
 }
 

@@ -230,3 +230,12 @@ def test_empty_scene_renders_environment_only():
     ctx.commit()
     img = ctx.render(1, 0, 2, 0, 10)
     assert np.allclose(img, 2.0)  # 2 spp x (0.5 * scale 2)
+
+
+def test_reference_known_answers():
+    """the reference's own known-answer vectors (tests/known_answers.py) on the CUDA path"""
+    import known_answers as ka
+    ka.tangent_frame_maps_y_to_normal(gpu_context())
+    ka.reflect_follows_the_source(gpu_context())
+    from pathed_b200 import load_scene
+    ka.one_pixel_environment_map(load_scene("test_scenes/environment_map_sampling.json", 32, 24))
