@@ -59,8 +59,8 @@ struct WaveParams {
 struct BounceCounters {
     uint32_t extendCount, shadowCount;           // rays leaving vertex k / NEE shadow rays cast at vertex k
     uint32_t classCount[PTC_MATERIAL_CLASSES];   // survivors of logic(k) per material class
-    uint32_t extendCursor, shadowCursor, logicCursor, classCursor[PTC_MATERIAL_CLASSES];
-    uint32_t pad[15];
+    uint32_t extendCursor, shadowCursor;         // work cursors of the two traversal launches (lane refill)
+    uint32_t pad[22];
 };
 static_assert(sizeof(BounceCounters) == 128, "one cache line per bounce");
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
@@ -85,17 +85,6 @@ __device__ __forceinline__ uint32_t warpAppend(uint32_t *counter, bool pred)
     if (lane == leader) { base = atomicAdd(counter, __popc(mask)); }
     base = __shfl_sync(mask, base, leader);
     return base + __popc(mask & ((1u << lane) - 1u));
-}
-
-// every warp pulls 32 items at a time from a global cursor: balances rays of very different cost (persistent warps)
-__device__ __forceinline__ bool fetchWork(uint32_t *cursor, uint32_t count, uint32_t &item)
-{
-    uint32_t base = 0;
-    if ((threadIdx.x & 31u) == 0) { base = atomicAdd(cursor, 32u); }
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) { return false; }
-    item = base + (threadIdx.x & 31u);
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 generate
@@ -325,7 +314,9 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
             const bool wantDirect = checkCounts(wp.startBounce, wp.lastBounce, k + 1) && !__ldg(&m.emitter);
             if (wantDirect) {
                 V3 contribution, sd; float maxT;
-                if (directLightsSetup<TYPE>(scene, m, bi, bs, rng, contribution, sd, maxT)) {
+                // a contribution that is exactly black adds nothing whether or not the light is visible (src/path_tracer.cpp:
+                // 138-164: occluded -> 0, else the contribution), e.g. a light sampled below the surface: no shadow ray for it
+                if (directLightsSetup<TYPE>(scene, m, bi, bs, rng, contribution, sd, maxT) && !isBlack(contribution)) {
                     pb.nee[p] = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
                     pb.shadowD[p] = make_float4(sd.x, sd.y, sd.z, maxT);
                     pushShadow = true;

@@ -239,3 +239,29 @@ def test_reference_known_answers():
     ka.reflect_follows_the_source(gpu_context())
     from pathed_b200 import load_scene
     ka.one_pixel_environment_map(load_scene("test_scenes/environment_map_sampling.json", 32, 24))
+
+
+def test_full_size_dragon_properties():
+    """BASELINE's full configuration (dragon.json, 1024 x 1024) through size-independent properties: (1) the box pixel filter
+    makes a 16 x 16 block average of the full-size render the same estimator as the 64 x 64 render, so 16 spp at 1024^2
+    (= 4096 samples per block) must match the reference's converged 64 x 64 image; (2) splitting the samples over two calls
+    (what the multi-GPU spp split does) is bit-exact; (3) every sample is finite and the ray counters are consistent."""
+    import os
+    from parity import GOLDEN
+    cfg = SCENES["dragon"]
+    g = np.load(os.path.join(GOLDEN, "image_dragon.npz"))
+    ref = g["image"].astype(np.float32)
+    ctx = gpu_scene("dragon", 1024, 1024)
+    ctx.reset_stats()
+    img = ctx.render(31, 0, 16, 0, cfg["last_bounce"])
+    st = ctx.stats()
+    assert np.isfinite(img).all()
+    assert st.samples == 1024 * 1024 * 16 and st.closest_rays >= st.samples and st.shadow_rays <= st.closest_rays
+    blocks = img.reshape(64, 16, 64, 16, 3).sum((1, 3)) / np.float32(16 * 16 * 16)
+    e = rel_mse(blocks, ref)
+    print("full-size dragon, block-averaged vs reference 64x64 render: relMSE", e)
+    assert e <= 1e-3 * (1.0 + 4096.0 / float(g["spp"])), e
+    assert abs(blocks.mean() - ref.mean()) <= 0.02 * ref.mean()
+    half = ctx.render(31, 0, 8, 0, cfg["last_bounce"])
+    half = ctx.render(31, 8, 8, 0, cfg["last_bounce"], accum=half)
+    assert np.array_equal(half, img)
