@@ -46,7 +46,7 @@ enum {
     PTC_PLASTIC = 5     /* src/plastic.cpp */
 };
 enum { PTC_BECKMANN = 0 /* src/beckmann.cpp */, PTC_GGX = 1 /* src/ggx.cpp */ };
-enum { PTC_ALBEDO_CONSTANT = 0, PTC_ALBEDO_CHECKERBOARD = 1 /* src/checkerboard.cpp */ };
+enum { PTC_ALBEDO_CONSTANT = 0, PTC_ALBEDO_CHECKERBOARD = 1 /* src/checkerboard.cpp */, PTC_ALBEDO_TEXTURE = 2 /* src/texture.cpp */ };
 
 /* Flat form of what the reference's Material constructors receive
  * (include/lambertian.h, oren_nayar.h, glass.h, microfacet.h, plastic.h, checkerboard.h). */
@@ -62,6 +62,7 @@ typedef struct ptc_material_desc {
     float checker_on[3];
     float checker_off[3];
     float checker_resolution[2];
+    uint32_t texture;     /* albedo_kind == PTC_ALBEDO_TEXTURE (Lambertian, Plastic's diffuse lobe): id from ptc_add_texture */
 } ptc_material_desc;
 
 /* Ray as Scene::testIntersect / testOcclusion take it (include/ray.h): origin + direction.
@@ -139,6 +140,10 @@ int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *positions, const float *nor
                           uint32_t n_triangles, uint32_t *geom_id_out);
 /* replaces Sphere::create (src/sphere.cpp:16-48): RTC_GEOMETRY_TYPE_SPHERE_POINT, one item */
 int ptc_add_sphere(ptc_ctx *ctx, const float center_radius[4], uint32_t material, uint32_t *geom_id_out);
+/* replaces Texture::load (src/texture.cpp:12-32): the 8-bit RGB texels stbi_load(..., 3) returns, row 0 = top of the
+ * image, width * height * 3 bytes.  Texture::lookup (:34-49: wrap, flip v, nearest texel, pow(c / 255, 2.2)) runs on the
+ * device.  Register textures before the materials that name them. */
+int ptc_add_texture(ptc_ctx *ctx, const uint8_t *rgb, int width, int height, uint32_t *texture_id_out);
 /* replaces the Material subclass constructors */
 int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *material_id_out);
 /* replaces EnvironmentLight::EnvironmentLight (src/environment_light.cpp:14-54): RGBA fp32 lat-long

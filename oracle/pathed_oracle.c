@@ -112,7 +112,10 @@ static inline float rng_next(rng_t *r)
 typedef struct {
     ptc_material_desc d;
     float A, B; /* OrenNayar, src/oren_nayar.cpp:11-19 */
+    const unsigned char *tex; int tex_w, tex_h; /* Texture::m_data / m_width / m_height, src/texture.cpp:23-27 */
 } material_t;
+
+typedef struct { unsigned char *rgb; int w, h; } texture_t;
 
 typedef struct {
     uint32_t first_vertex, first_prim, n_prims;
@@ -139,6 +142,7 @@ struct orc_ctx {
     uint32_t n_prims, cap_prims;  /* triangle prims only */
     geom_t *geoms; uint32_t n_geoms;
     material_t *materials; uint32_t n_materials;
+    texture_t *textures; uint32_t n_textures;
     uint32_t *sphere_geoms; uint32_t n_spheres; uint32_t *sphere_material;
     /* lights (src/scene_parser.cpp:173-190) */
     light_t *lights; uint32_t n_lights;
@@ -179,17 +183,40 @@ void orc_destroy(orc_ctx *c)
     free(c->prim_local); free(c->geoms); free(c->materials); free(c->sphere_geoms); free(c->sphere_material);
     free(c->lights); free(c->env_rgba); free(c->env_theta_cdf); free(c->env_phi_cdf); free(c->env_phi_empty);
     free(c->nodes); free(c->order);
+    for (uint32_t t = 0; t < c->n_textures; t++) { free(c->textures[t].rgb); }
+    free(c->textures);
     free(c);
 }
 
 const char *orc_last_error(orc_ctx *c) { return c ? c->err : "null context"; }
 
+/* Texture::load, src/texture.cpp:12-32: keeps the 8-bit RGB texels as stbi_load(..., 3) returns them */
+int orc_add_texture(orc_ctx *c, const uint8_t *rgb, int width, int height, uint32_t *id)
+{
+    if (!rgb || width <= 0 || height <= 0) { FAIL(c, PTC_ERR_INVALID, "Error loading texture"); }
+    c->textures = (texture_t *)realloc(c->textures, (c->n_textures + 1) * sizeof(texture_t));
+    texture_t *t = &c->textures[c->n_textures];
+    t->w = width; t->h = height;
+    t->rgb = (unsigned char *)malloc((size_t)width * height * 3);
+    memcpy(t->rgb, rgb, (size_t)width * height * 3);
+    if (id) { *id = c->n_textures; }
+    c->n_textures++;
+    return PTC_OK;
+}
+
 int orc_add_material(orc_ctx *c, const ptc_material_desc *d, uint32_t *id)
 {
     if (!d || d->type < 0 || d->type > PTC_PLASTIC) { FAIL(c, PTC_ERR_INVALID, "Unimplemented material"); }
+    if (d->albedo_kind == PTC_ALBEDO_TEXTURE && ((d->type != PTC_LAMBERTIAN && d->type != PTC_PLASTIC) || d->texture >= c->n_textures)) {
+        FAIL(c, PTC_ERR_INVALID, "bad texture reference");
+    }
     c->materials = (material_t *)realloc(c->materials, (c->n_materials + 1) * sizeof(material_t));
     material_t *m = &c->materials[c->n_materials];
     m->d = *d;
+    m->tex = NULL; m->tex_w = m->tex_h = 0;
+    if (d->albedo_kind == PTC_ALBEDO_TEXTURE) { /* the texel storage itself never moves (malloc'd per texture) */
+        m->tex = c->textures[d->texture].rgb; m->tex_w = c->textures[d->texture].w; m->tex_h = c->textures[d->texture].h;
+    }
     const float sigma2 = d->sigma * d->sigma;
     m->A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
     m->B = (0.45f * sigma2) / (sigma2 + 0.09f);
@@ -570,6 +597,14 @@ static v3 cosine_sample(rng_t *r)
 /* src/checkerboard.cpp:9-20 */
 static v3 lambert_albedo(const material_t *m, const isect_t *i)
 {
+    if (m->d.albedo_kind == PTC_ALBEDO_TEXTURE) { /* Texture::lookup, src/texture.cpp:34-49 */
+        const float u = i->u - (int)floorf(i->u);
+        const float v = 1.f - (i->v - (int)floorf(i->v));
+        const int x = (int)roundf(u * (m->tex_w - 1));
+        const int y = (int)roundf(v * (m->tex_h - 1));
+        const unsigned char *t = m->tex + 3 * ((size_t)y * m->tex_w + x);
+        return V(powf(t[0] / 255.f, 2.2f), powf(t[1] / 255.f, 2.2f), powf(t[2] / 255.f, 2.2f));
+    }
     if (m->d.albedo_kind == PTC_ALBEDO_CHECKERBOARD) {
         const int ui = (int)floorf(i->u * m->d.checker_resolution[0]);
         const int vi = (int)floorf(i->v * m->d.checker_resolution[1]);

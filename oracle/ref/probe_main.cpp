@@ -27,6 +27,7 @@
 #include "oren_nayar.h"
 #include "path_tracer.h"
 #include "plastic.h"
+#include "texture.h"
 #include "ray.h"
 #include "scene.h"
 #include "scene_parser.h"
@@ -219,6 +220,29 @@ void *ref_material_new(int type, const float *p)
     case 5: m = new Plastic(diffuse, dist()); break;
     }
     return m;
+}
+
+// Texture::load's decode: stbi_load(path, &w, &h, &channels, 3) of the reference's vendored stb_image (src/texture.cpp:16-21).
+// Returns 0 and the size; fills rgb when it has room.
+int ref_load_image(const char *path, unsigned char *rgb, int capacity, int *width, int *height)
+{
+    int channels = 0;
+    unsigned char *data = stbi_load(path, width, height, &channels, 3);
+    if (!data) { return -1; }
+    if (rgb && capacity >= *width * *height * 3) { memcpy(rgb, data, (size_t)*width * *height * 3); }
+    stbi_image_free(data);
+    return 0;
+}
+
+// N1: Lambertian / Plastic whose albedo is an image texture, built the way parseMaterial does (src/scene_parser.cpp:625-647)
+void *ref_material_new_textured(int type, const float *p, const char *texturePath)
+{
+    auto texture = std::make_shared<Texture>(texturePath);
+    texture->load();
+    if (type == 0) { return new Lambertian(texture, Color(p[3], p[4], p[5])); }
+    std::unique_ptr<MicrofacetDistribution> dist;
+    if (p[7] == 0.f) { dist = std::make_unique<Beckmann>(p[8]); } else { dist = std::make_unique<GGX>(p[8]); }
+    return new Plastic(std::make_unique<Lambertian>(texture, Color(0.f)), std::move(dist));
 }
 
 static Intersection makeIsect(const float *wo, const float *ng, const float *ns, const float *uv, Material *m)

@@ -23,7 +23,7 @@ class MaterialDesc(ctypes.Structure):
     _fields_ = [("type", ctypes.c_int32), ("diffuse", ctypes.c_float * 3), ("emit", ctypes.c_float * 3),
                 ("sigma", ctypes.c_float), ("ior", ctypes.c_float), ("distribution", ctypes.c_int32),
                 ("alpha", ctypes.c_float), ("albedo_kind", ctypes.c_int32), ("checker_on", ctypes.c_float * 3),
-                ("checker_off", ctypes.c_float * 3), ("checker_resolution", ctypes.c_float * 2)]
+                ("checker_off", ctypes.c_float * 3), ("checker_resolution", ctypes.c_float * 2), ("texture", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):
@@ -51,7 +51,7 @@ assert RAY_DTYPE.itemsize == 24 and HIT_DTYPE.itemsize == 32 and ISECT_DTYPE.ite
 class SceneSink(ctypes.Structure):
     _fields_ = [("ctx", ctypes.c_void_p), ("add_material", ctypes.c_void_p), ("add_triangle_mesh", ctypes.c_void_p),
                 ("add_sphere", ctypes.c_void_p), ("set_environment", ctypes.c_void_p), ("set_camera", ctypes.c_void_p),
-                ("commit", ctypes.c_void_p)]
+                ("commit", ctypes.c_void_p), ("add_texture", ctypes.c_void_p)]
 
 
 class PathedError(RuntimeError):
@@ -111,9 +111,17 @@ class Api:
     def sink(self):
         addr = lambda name: ctypes.cast(self._fn(name), ctypes.c_void_p).value
         return SceneSink(self.ctx.value, addr("add_material"), addr("add_triangle_mesh"), addr("add_sphere"),
-                         addr("set_environment"), addr("set_camera"), addr("commit"))
+                         addr("set_environment"), addr("set_camera"), addr("commit"), addr("add_texture"))
 
     # ---- scene description
+    def add_texture(self, rgb):
+        """rgb: uint8 array (height, width, 3), row 0 = top of the image (what stbi_load returns)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        out = ctypes.c_uint32()
+        self._call("add_texture", _ptr(rgb), ctypes.c_int(rgb.shape[1]), ctypes.c_int(rgb.shape[0]), ctypes.byref(out))
+        return out.value
+
     def add_material(self, desc):
         out = ctypes.c_uint32()
         self._call("add_material", ctypes.byref(desc), ctypes.byref(out))
@@ -341,6 +349,19 @@ class SceneFile:
             self.close()
         except Exception:
             pass
+
+
+def load_image_rgb8(path):
+    """The C++ host layer's Texture::load decode (pathed_b200/host/image_loader.cpp): uint8 array (height, width, 3)."""
+    lib = host_lib()
+    w, h = ctypes.c_int(), ctypes.c_int()
+    err = ctypes.create_string_buffer(512)
+    lib.pth_image_load_rgb8.restype = ctypes.c_int
+    if lib.pth_image_load_rgb8(path.encode(), None, ctypes.c_size_t(0), ctypes.byref(w), ctypes.byref(h), err, ctypes.c_int(512)) != 0:
+        raise PathedError(err.value.decode())
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    lib.pth_image_load_rgb8(path.encode(), _ptr(out), ctypes.c_size_t(out.nbytes), ctypes.byref(w), ctypes.byref(h), err, ctypes.c_int(512))
+    return out
 
 
 def job_describe(job_path):

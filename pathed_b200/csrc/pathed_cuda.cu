@@ -138,12 +138,106 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 #else
 #define PTC_TRAVERSE_BOUNDS __launch_bounds__(128)
 #endif
+// Cooperative triangle phase.  After a node phase only a few lanes of a warp hold pending triangles (measured: 3.3 of 32
+// lanes per sequential round, 4.4 rounds per node phase), so the (ray, triangle) pairs of all lanes are compacted with a
+// warp prefix sum and spread over the 32 lanes: lane w tests pair w with the owner's ray fetched by shuffles, and owners
+// collect accepted candidates in the order a sequential scan would have met them (highest group bit first), re-applying the
+// upper end of the depth interval with their current hit distance -- the result is bit-identical to one-triangle-per-round.
+#ifndef PTC_COOP_TRI
+#define PTC_COOP_TRI 0
+#endif
+// Triangle rounds per node phase in the one-triangle-per-lane scheme.  Running a ray's whole triangle group before the
+// warp's next node phase (the classic while-while loop) leaves 3 of 32 lanes active for 4.4 rounds per node phase on the
+// dragon workload; with a bound, rays with triangles left skip node phases until their group is finished, so triangle
+// rounds fill up with the leftovers of several node phases.  Per-ray order of operations, hence every result, is unchanged.
+#ifndef PTC_TRI_ROUNDS
+#define PTC_TRI_ROUNDS 1
+#endif
+template <bool ANY>
+__device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState &st, bool eligible, uint8_t *ownerOf)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool done = false;
+    for (;;) {
+        const uint32_t y = (eligible && !done) ? st.tgroup.y : 0u;
+        const uint32_t want = __ballot_sync(FULL, y != 0u);
+        if (want == 0u) { break; }
+        const uint32_t c = __popc(y);
+        uint32_t incl = c;
+#pragma unroll
+        for (uint32_t o = 1; o < 32u; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) { incl += v; }
+        }
+        const uint32_t S = incl - c;                       // first pair index of this owner
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (c) { ownerOf[__popc(want & ((1u << lane) - 1u))] = (uint8_t)lane; }
+        const uint32_t starts = __reduce_or_sync(FULL, (c && S < 32u) ? 1u << S : 0u);
+        __syncwarp();
+        const bool work = lane < total;
+        const uint32_t owner = work ? ownerOf[__popc(starts & (FULL >> (31u - lane))) - 1u] : lane;
+        __syncwarp();
+        const uint32_t So = __shfl_sync(FULL, S, owner);
+        uint32_t yo = __brev(__shfl_sync(FULL, y, owner)); // highest group bit first
+        const uint32_t base = __shfl_sync(FULL, st.tgroup.x, owner);
+        const float ox = __shfl_sync(FULL, st.ox, owner), oy = __shfl_sync(FULL, st.oy, owner), oz = __shfl_sync(FULL, st.oz, owner);
+        const float dx = __shfl_sync(FULL, st.dx, owner), dy = __shfl_sync(FULL, st.dy, owner), dz = __shfl_sync(FULL, st.dz, owner);
+        const float tfar = __shfl_sync(FULL, st.hit.t, owner);
+        bool accepted = false;
+        float T = 0.f, U = 0.f, V = 0.f, absDen = 1.f;
+        uint32_t prim = 0;
+        if (work) {
+            for (uint32_t k = lane - So; k; k--) { yo &= yo - 1u; }
+            const uint32_t bit = 32u - (uint32_t)__ffs((int)yo);
+            const float4 *tri = bvh.triangles + (size_t)(base + bit) * 3;
+            const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), cc = loadNodeWord(tri + 2);
+            accepted = triangleTestRaw(a, b, cc, ox, oy, oz, dx, dy, dz, PTC_TNEAR, tfar, T, U, V, absDen);
+            prim = f2u(a.w);
+        }
+        const uint32_t acc = __ballot_sync(FULL, accepted);
+        // owners retire the triangles that were tested this round (all of them unless the warp had more than 32 pairs)
+        uint32_t n = 0;
+        if (c && S < 32u) {
+            n = min(c, 32u - S);
+            if (n == c) { st.tgroup.y = 0u; }
+            else {
+                uint32_t yr = __brev(y);
+                for (uint32_t k = n; k; k--) { yr &= yr - 1u; }
+                st.tgroup.y = __brev(yr);
+            }
+        }
+        uint32_t seg = n ? (acc >> S) & (FULL >> (32u - n)) : 0u;
+        if (ANY) {
+            if (seg) { done = true; st.found = true; }
+        } else if (acc) {
+            const float t = divIeee(T, absDen), u = divIeee(U, absDen), v = divIeee(V, absDen);
+            while (__any_sync(FULL, seg != 0u)) {
+                const uint32_t src = seg ? S + (uint32_t)__ffs((int)seg) - 1u : lane;
+                const float ct = __shfl_sync(FULL, t, src), cu = __shfl_sync(FULL, u, src), cv = __shfl_sync(FULL, v, src);
+                const float cT = __shfl_sync(FULL, T, src), cA = __shfl_sync(FULL, absDen, src);
+                const uint32_t cp = __shfl_sync(FULL, prim, src);
+                if (seg) {
+                    seg &= seg - 1u;
+                    if (cT <= cA * st.hit.t) { // the candidate passed (tnear, round-start tfar]; tfar may have shrunk since
+                        if (!(st.found && ct == st.hit.t && cp < st.hit.prim)) { st.hit.t = ct; st.hit.u = cu; st.hit.v = cv; st.hit.prim = cp; }
+                        st.found = true;
+                    }
+                }
+            }
+        }
+    }
+    return done;
+}
+
 template <bool ANY, bool COUNT>
 __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
                                                       unsigned long long *work)
 {
     __shared__ uint2 fastStack[(PTC_FAST_STACK > 0 ? PTC_FAST_STACK : 1) * PTC_FAST_STRIDE]; // [entry][thread]: conflict-free 64-bit accesses
     uint2 *const fast = fastStack + threadIdx.x;
+    __shared__ uint8_t ownerSlots[128];
+    uint8_t *const ownerOf = ownerSlots + (threadIdx.x & ~31u); // this warp's 32 entries
     const uint32_t n = *count;
     const uint32_t lane = threadIdx.x & 31u;
     TraverseCounters tc = {0, 0};
@@ -179,19 +273,23 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
         uint32_t active = __ballot_sync(0xFFFFFFFFu, busy);
         if (active == 0u) { break; }
         for (;;) {
-            if (busy && hasNodes) { traversalNode<COUNT>(scene.bvh, st, &tc, fast); }
+            // a ray whose triangle group is not finished yet (more triangles than PTC_TRI_ROUNDS) sits out this node phase
+            if (busy && hasNodes && st.tgroup.y == 0u) { traversalNode<COUNT>(scene.bvh, st, &tc, fast); }
             bool done = false; // this ray needs no further BVH work
-            for (;;) { // triangle rounds, warp-uniform control flow
-                bool pending = busy && !done && st.tgroup.y != 0u;
-                const uint32_t want = __ballot_sync(0xFFFFFFFFu, pending);
-                if (want == 0u) { break; }
-                if (__popc(want) * PTC_POSTPONE_DIV < __popc(active)) {
-                    if (pending && traversalPostpone(st, fast)) { pending = false; }
-                    if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
+            if (PTC_COOP_TRI && !COUNT) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
+            else {
+                for (int round = 0; round < PTC_TRI_ROUNDS; round++) { // triangle rounds, warp-uniform control flow
+                    bool pending = busy && !done && st.tgroup.y != 0u;
+                    const uint32_t want = __ballot_sync(0xFFFFFFFFu, pending);
+                    if (want == 0u) { break; }
+                    if (__popc(want) * PTC_POSTPONE_DIV < __popc(active)) {
+                        if (pending && traversalPostpone(st, fast)) { pending = false; }
+                        if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
+                    }
+                    if (pending && traversalTriangle<COUNT>(scene.bvh, st, &tc) && ANY) { done = true; }
                 }
-                if (pending && traversalTriangle<COUNT>(scene.bvh, st, &tc) && ANY) { done = true; }
             }
-            if (busy && (done || traversalPop(st, fast))) {
+            if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
                 const bool found = traversalSpheres<ANY>(scene.bvh, st);
                 if (ANY) { pb.occluded[p] = found ? 1 : 0; }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
@@ -599,6 +697,8 @@ struct ptc_ctx {
     bool committed = false;
     // staging (host)
     std::vector<ptc_material_desc> materials;
+    struct HostTexture { std::vector<uint32_t> texels; int width, height; };
+    std::vector<HostTexture> textures;
     std::vector<float> positions4, normals4, uvs2;
     std::vector<uint32_t> prims4, primIds2;
     std::vector<HostGeometry> geometries;
@@ -742,11 +842,31 @@ void ptc_destroy(ptc_ctx *ctx)
 
 const char *ptc_last_error(ptc_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
+int ptc_add_texture(ptc_ctx *ctx, const uint8_t *rgb, int width, int height, uint32_t *id)
+{
+    if (!ctx || !rgb) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (width <= 0 || height <= 0) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Error loading texture: %d x %d", width, height); }
+    ptc_ctx::HostTexture t;
+    t.width = width; t.height = height;
+    t.texels.resize((size_t)width * height);
+    for (size_t i = 0; i < t.texels.size(); i++) { t.texels[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16); }
+    ctx->textures.push_back(std::move(t));
+    if (id) { *id = (uint32_t)ctx->textures.size() - 1; }
+    return PTC_OK;
+}
+
 int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *id)
 {
     if (!ctx || !desc) { return PTC_ERR_INVALID; }
     if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
     if (desc->type < PTC_LAMBERTIAN || desc->type > PTC_PLASTIC) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented material type %d", desc->type); }
+    if (desc->albedo_kind == PTC_ALBEDO_TEXTURE) {
+        if (desc->type != PTC_LAMBERTIAN && desc->type != PTC_PLASTIC) { CTX_FAIL(ctx, PTC_ERR_INVALID, "only Lambertian and Plastic take a texture (src/scene_parser.cpp:625-647)"); }
+        if (desc->texture >= ctx->textures.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "texture id %u out of range", desc->texture); }
+    } else if (desc->albedo_kind != PTC_ALBEDO_CONSTANT && desc->albedo_kind != PTC_ALBEDO_CHECKERBOARD) {
+        CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented albedo kind %d", desc->albedo_kind);
+    }
     if ((desc->type == PTC_MICROFACET || desc->type == PTC_PLASTIC) && desc->distribution != PTC_BECKMANN && desc->distribution != PTC_GGX) {
         CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented distribution %d", desc->distribution);
     }
@@ -873,6 +993,18 @@ int ptc_commit(ptc_ctx *ctx)
     try { buildWideBVH(ctx->positions4.data(), ctx->prims4.data(), nPrims, ctx->bvh); }
     catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
 
+    // textures: packed texels per image, one gamma table for all (Texture::lookup's powf(c / 255.f, 2.2f), src/texture.cpp:44-48)
+    std::vector<const uint32_t *> deviceTexels(ctx->textures.size(), nullptr);
+    for (size_t t = 0; t < ctx->textures.size(); t++) {
+        const int rcTex = upload(ctx, ctx->textures[t].texels.data(), ctx->textures[t].texels.size(), &deviceTexels[t], ctx->allocations);
+        if (rcTex) { return rcTex; }
+    }
+    {
+        float gamma[256];
+        for (int c = 0; c < 256; c++) { gamma[c] = powf(c / 255.f, 2.2f); }
+        CUDA_TRY(ctx, cudaMemcpyToSymbol(c_gammaTable, gamma, sizeof(gamma)));
+    }
+
     std::vector<DMaterial> dm(ctx->materials.size());
     ctx->classMask = 0;
     for (size_t i = 0; i < dm.size(); i++) {
@@ -887,6 +1019,9 @@ int ptc_commit(ptc_ctx *ctx)
         m.sigmaA = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
         m.sigmaB = (0.45f * sigma2) / (sigma2 + 0.09f);
         m.ior = d.ior; m.alpha = d.alpha; m.resU = d.checker_resolution[0]; m.resV = d.checker_resolution[1];
+        if (d.albedo_kind == PTC_ALBEDO_TEXTURE) {
+            m.texW = ctx->textures[d.texture].width; m.texH = ctx->textures[d.texture].height; m.texels = deviceTexels[d.texture];
+        }
     }
 
     // light table: emissive surfaces in registration order, environment light last (src/scene_parser.cpp:173-190)

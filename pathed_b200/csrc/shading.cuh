@@ -41,8 +41,10 @@ struct DMaterial {
     float diffuse[3], sigmaA;  // sigmaA / sigmaB: OrenNayar's A and B (src/oren_nayar.cpp:11-19)
     float emit[3], sigmaB;
     float ior, alpha, resU, resV;
-    float on[3], pad0;
-    float off[3], pad1;
+    float on[3]; int32_t texW;   // texW, texH, texels: albedoKind == PTC_ALBEDO_TEXTURE
+    float off[3]; int32_t texH;
+    const uint32_t *texels;      // r | g << 8 | b << 16 per texel, row 0 = top of the image (stbi_load order)
+    uint64_t pad0;
 };
 
 struct DLight {
@@ -254,8 +256,20 @@ __device__ __forceinline__ V3 cosineSample(Rng &r) // src/monte_carlo.cpp:24-41
     return mk(rad * cosf(phi), sqrtf(1.f - xi1), rad * sinf(phi));
 }
 
-__device__ __forceinline__ V3 lambertAlbedo(const DMaterial &m, const Isect &i) // src/checkerboard.cpp:9-20
+// pow(c / 255.f, 2.2f) for the 256 byte values, tabulated by the host's powf at ptc_commit (bit-identical to the reference's
+// per-lookup powf, src/texture.cpp:44-48)
+__constant__ float c_gammaTable[256];
+
+__device__ __forceinline__ V3 lambertAlbedo(const DMaterial &m, const Isect &i) // src/checkerboard.cpp:9-20, src/texture.cpp:34-49
 {
+    if (m.albedoKind == PTC_ALBEDO_TEXTURE) {
+        // wrap, flip v, nearest texel by roundf on (size - 1)
+        const float u = i.u - (int)floorf(i.u);
+        const float v = 1.f - (i.v - (int)floorf(i.v));
+        const int x = (int)roundf(u * (m.texW - 1)), y = (int)roundf(v * (m.texH - 1));
+        const uint32_t texel = __ldg(m.texels + (size_t)y * m.texW + x);
+        return mk(c_gammaTable[texel & 0xFFu], c_gammaTable[(texel >> 8) & 0xFFu], c_gammaTable[(texel >> 16) & 0xFFu]);
+    }
     if (m.albedoKind == PTC_ALBEDO_CHECKERBOARD) {
         const int ui = (int)floorf(i.u * m.resU), vi = (int)floorf(i.v * m.resV);
         if (ui % 2 == vi % 2) { return mk(m.on[0], m.on[1], m.on[2]); }

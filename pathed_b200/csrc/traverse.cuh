@@ -158,6 +158,24 @@ PTC_HD bool triangleTest(const float4 a, const float4 b, const float4 c, float o
     return true;
 }
 
+// The same test with the divisions left to the caller: T, U, V are the sign-corrected numerators over absDen.  Used by the
+// cooperative triangle phase, where the ray's owner re-applies the depth interval with its current hit distance.
+PTC_HD bool triangleTestRaw(const float4 a, const float4 b, const float4 c, float ox, float oy, float oz, float dx, float dy,
+                            float dz, float tnear, float tfar, float &T, float &U, float &V, float &absDen)
+{
+    const float ngx = fmaf(c.y, b.z, -(c.z * b.y)), ngy = fmaf(c.z, b.x, -(c.x * b.z)), ngz = fmaf(c.x, b.y, -(c.y * b.x));
+    const float cx = a.x - ox, cy = a.y - oy, cz = a.z - oz;
+    const float rx = fmaf(cy, dz, -(cz * dy)), ry = fmaf(cz, dx, -(cx * dz)), rz = fmaf(cx, dy, -(cy * dx));
+    const float den = edot(ngx, ngy, ngz, dx, dy, dz);
+    absDen = fabsf(den);
+    const uint32_t sgn = f2u(den) & 0x80000000u;
+    U = u2f(f2u(edot(rx, ry, rz, c.x, c.y, c.z)) ^ sgn);
+    V = u2f(f2u(edot(rx, ry, rz, b.x, b.y, b.z)) ^ sgn);
+    if (!(den != 0.f && U >= 0.f && V >= 0.f && U + V <= absDen)) { return false; }
+    T = u2f(f2u(edot(ngx, ngy, ngz, cx, cy, cz)) ^ sgn);
+    return absDen * tnear < T && T <= absDen * tfar;
+}
+
 PTC_HD bool sphereTest(const float4 s, float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar,
                        float &t, float &ngx, float &ngy, float &ngz)
 {

@@ -3,6 +3,7 @@
 // these wrappers only expose the parsers so scripts can load a scene file into any library that
 // exports the ptc_* scene-description calls.
 #include "exr_io.hpp"
+#include "image_loader.hpp"
 #include "pathed.hpp"
 #include "scene_description.hpp"
 #include "scene_parser.hpp"
@@ -58,6 +59,20 @@ int pth_scene_material(void *scene, uint32_t id, ptc_material_desc *out)
     if (id >= s.materials.size()) { return -1; }
     *out = s.materials[id];
     return 0;
+}
+
+// Texture::load's decode step: returns 0 and the size; copies the texels when `rgb` has room for them
+int pth_image_load_rgb8(const char *path, uint8_t *rgb, size_t capacityBytes, int *width, int *height, char *err, int errLen)
+{
+    try {
+        std::vector<uint8_t> data;
+        loadImageRGB8(path, data, *width, *height);
+        if (rgb && capacityBytes >= data.size()) { memcpy(rgb, data.data(), data.size()); }
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errLen > 0) { snprintf(err, (size_t)errLen, "%s", e.what()); }
+        return -1;
+    }
 }
 
 int pth_exr_write_rgb_f32(const char *path, int width, int height, const float *rgb /*interleaved, top row first*/)

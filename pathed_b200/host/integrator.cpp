@@ -39,6 +39,7 @@ int sinkCamera(void *c, const float *o, const float *t, const float *u, float f,
     return ptc_set_camera((ptc_ctx *)c, o, t, u, f, w, h, flip);
 }
 int sinkCommit(void *c) { return ptc_commit((ptc_ctx *)c); }
+int sinkTexture(void *c, const uint8_t *rgb, int w, int h, uint32_t *id) { return ptc_add_texture((ptc_ctx *)c, rgb, w, h, id); }
 
 double now()
 {
@@ -57,7 +58,7 @@ Scene::Scene(const SceneDescription &description, int gpus) : m_width(descriptio
             throw std::runtime_error("Failed to create device " + std::to_string(device) + " (no CUDA device? there is no CPU path)");
         }
         m_contexts.push_back(ctx);
-        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit};
+        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture};
         const int status = feedScene(description, sink);
         if (status != PTC_OK) {
             const std::string message = ptc_last_error(ctx);

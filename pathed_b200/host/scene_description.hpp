@@ -37,7 +37,14 @@ struct EnvironmentDesc {
     float mapToWorld[16], worldToMap[16];
 };
 
+struct TextureDesc { // Texture (include/texture.h): decoded at parse time like Texture::load
+    std::string filename;
+    std::vector<uint8_t> rgb;
+    int width = 0, height = 0;
+};
+
 struct SceneDescription {
+    std::vector<TextureDesc> textures; // ptc_material_desc::texture indexes this list
     std::vector<ptc_material_desc> materials;
     std::vector<GeometryDesc> geometries; // index == Embree geomID
     CameraDesc camera;
@@ -55,6 +62,7 @@ struct SceneSink {
     int (*set_environment)(void *, const float *, int, int, float, const float *, const float *);
     int (*set_camera)(void *, const float *, const float *, const float *, float, int, int, int);
     int (*commit)(void *);
+    int (*add_texture)(void *, const uint8_t *, int, int, uint32_t *);
 };
 
 // returns the first non-zero status of the sink, 0 on success

@@ -1,6 +1,7 @@
 #include "scene_parser.hpp"
 
 #include "exr_io.hpp"
+#include "image_loader.hpp"
 #include "json.hpp"
 #include "obj_parser.hpp"
 #include "transform.hpp"
@@ -83,6 +84,20 @@ void parseDistribution(const Json &j, ptc_material_desc &d) // src/scene_parser.
     else { throw std::runtime_error("Unimplemented distribution: " + type); }
 }
 
+thread_local std::string g_sceneRoot; // directory that repo-relative asset paths resolve against (the reference uses the cwd)
+
+// std::make_shared<Texture>(path) + load(), src/scene_parser.cpp:630-632, 646-648: every mention decodes the file again in the
+// reference; here a file is decoded once and shared.  Paths are relative to the working directory (the scene root).
+uint32_t parseTexture(const std::string &path, SceneDescription &scene)
+{
+    for (size_t t = 0; t < scene.textures.size(); t++) { if (scene.textures[t].filename == path) { return (uint32_t)t; } }
+    TextureDesc texture;
+    texture.filename = path;
+    loadImageRGB8(resolve(g_sceneRoot, path), texture.rgb, texture.width, texture.height);
+    scene.textures.push_back(std::move(texture));
+    return (uint32_t)scene.textures.size() - 1;
+}
+
 // parseMaterial, src/scene_parser.cpp:604-700.  Returns -1 for "no bsdf given" (nullptr in the reference).
 int parseMaterial(const Json &j, const MaterialMap &lookup, SceneDescription &scene)
 {
@@ -112,13 +127,18 @@ int parseMaterial(const Json &j, const MaterialMap &lookup, SceneDescription &sc
         d.type = PTC_PLASTIC;
         parseColor(j["diffuseReflectance"], d.diffuse, 0.f);
         parseDistribution(j["distribution"], d);
-        if (j["texture"].isString()) { throw std::runtime_error("image textures are not supported yet (SURVEY N1): " + j["texture"].asString()); }
+        if (j["texture"].isString()) { // Plastic(Lambertian(texture, 0), distribution): diffuseReflectance is ignored, src/scene_parser.cpp:629-639
+            d.albedo_kind = PTC_ALBEDO_TEXTURE;
+            d.texture = parseTexture(j["texture"].asString(), scene);
+        }
     } else if (type == "lambertian") {
         d.type = PTC_LAMBERTIAN;
         parseColor(j["diffuseReflectance"], d.diffuse, 0.f);
         parseColor(j["emit"], d.emit, 0.f);
-        if (j["texture"].isString()) { throw std::runtime_error("image textures are not supported yet (SURVEY N1): " + j["texture"].asString()); }
-        if (j["albedo"].isObject() && parseString(j["albedo"]["type"], "") == "checkerboard") {
+        if (j["texture"].isString()) { // the texture wins over "albedo", src/scene_parser.cpp:645-651
+            d.albedo_kind = PTC_ALBEDO_TEXTURE;
+            d.texture = parseTexture(j["texture"].asString(), scene);
+        } else if (j["albedo"].isObject() && parseString(j["albedo"]["type"], "") == "checkerboard") {
             const Json &albedo = j["albedo"];
             d.albedo_kind = PTC_ALBEDO_CHECKERBOARD;
             parseColor(albedo["onColor"], d.checker_on, 0.f);
@@ -158,6 +178,7 @@ GeometryDesc makeQuad(const Transform &transform, uint32_t material, bool zUp) /
 
 SceneDescription parseScene(const std::string &sceneJsonPath, const std::string &root, int width, int height)
 {
+    g_sceneRoot = root;
     std::ifstream file(resolve(root, sceneJsonPath));
     if (!file) { throw std::runtime_error("cannot open scene file: " + sceneJsonPath); }
     std::stringstream buffer;
@@ -257,6 +278,10 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
 int feedScene(const SceneDescription &scene, const SceneSink &sink)
 {
     int status = 0;
+    for (const TextureDesc &texture : scene.textures) {
+        if (!sink.add_texture) { return PTC_ERR_INVALID; }
+        if ((status = sink.add_texture(sink.ctx, texture.rgb.data(), texture.width, texture.height, nullptr))) { return status; }
+    }
     for (const ptc_material_desc &material : scene.materials) {
         if ((status = sink.add_material(sink.ctx, &material, nullptr))) { return status; }
     }

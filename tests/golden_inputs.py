@@ -58,7 +58,15 @@ BSDF_CONFIGS = {
     "plastic_dragon": dict(type=PLASTIC, diffuse=(0.1, 0.1, 0.4), distribution=BECKMANN, alpha=0.1),
     "plastic_plate1": dict(type=PLASTIC, diffuse=(0.07, 0.09, 0.13), distribution=BECKMANN, alpha=0.005),
     "plastic_ggx": dict(type=PLASTIC, diffuse=(0.5, 0.4, 0.3), distribution=GGX, alpha=0.3),
+    # N1 image textures (src/texture.cpp): the albedo comes from tests/golden/texture_test.png, diffuse is ignored
+    "lambertian_textured": dict(type=LAMBERTIAN, diffuse=(1, 1, 1), textured=True),
+    "plastic_textured": dict(type=PLASTIC, diffuse=(1, 1, 1), distribution=BECKMANN, alpha=0.1, textured=True),
 }
+
+
+# input seeds are tied to this order: the round-1 configs sorted by name, later additions appended (keeps old fixtures stable)
+_LATER_CONFIGS = ["lambertian_textured", "plastic_textured"]
+_SEED_ORDER = sorted(n for n in BSDF_CONFIGS if n not in _LATER_CONFIGS) + _LATER_CONFIGS
 
 
 def material_params(cfg):
@@ -76,8 +84,10 @@ def material_params(cfg):
     return p
 
 
-def material_desc(cfg):
-    """The same material as a ptc_material_desc."""
+def material_desc(cfg, api=None):
+    """The same material as a ptc_material_desc; a textured config registers test_texture() with `api` first."""
+    if cfg.get("textured"):
+        cfg = dict(cfg, texture_id=api.add_texture(make_test_texture()))
     from pathed_b200._binding import MaterialDesc
     d = MaterialDesc()
     d.type = cfg["type"]
@@ -91,13 +101,117 @@ def material_desc(cfg):
         on, off, res = cfg["checker"]
         d.albedo_kind = 1
         d.checker_on[:] = on; d.checker_off[:] = off; d.checker_resolution[:] = res
+    if "texture_id" in cfg:  # the caller registered test_texture() with add_texture first
+        d.albedo_kind = 2
+        d.texture = cfg["texture_id"]
     return d
+
+
+def write_png(path, rgb):
+    """8-bit RGB, non-interlaced PNG with per-row filter type 0..4 cycling (exercises every unfilter of a decoder)."""
+    import struct
+    import zlib
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h, w, _ = rgb.shape
+    raw = bytearray()
+    prev = np.zeros(w * 3, np.int32)
+    for y in range(h):
+        cur = rgb[y].reshape(-1).astype(np.int32)
+        left = np.concatenate([np.zeros(3, np.int32), cur[:-3]])
+        upleft = np.concatenate([np.zeros(3, np.int32), prev[:-3]])
+        ft = y % 5
+        if ft == 0: out = cur
+        elif ft == 1: out = cur - left
+        elif ft == 2: out = cur - prev
+        elif ft == 3: out = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - upleft
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+            out = cur - pred
+        raw.append(ft)
+        raw += (out & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(kind, data):
+        return struct.pack(">I", len(data)) + kind + data + struct.pack(">I", zlib.crc32(kind + data) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(bytes(raw), 9)) + chunk(b"IEND", b""))
+
+
+def png_variants():
+    """name -> PNG file bytes covering what a decoder must handle: every colour type, bit depths 1-16, Adam7 interlacing,
+    a palette with fewer than 256 entries, several IDAT chunks.  Filter type 0 only (write_png covers the filters)."""
+    import struct
+    import zlib
+
+    def chunk(kind, data):
+        return struct.pack(">I", len(data)) + kind + data + struct.pack(">I", zlib.crc32(kind + data) & 0xFFFFFFFF)
+
+    def pack_rows(samples, depth):  # samples: (h, w * channels) integers
+        rows = []
+        for row in samples:
+            if depth == 8:
+                rows.append(bytes(int(v) for v in row))
+            elif depth == 16:
+                rows.append(b"".join(struct.pack(">H", int(v)) for v in row))
+            else:
+                bits = "".join(format(int(v), "0%db" % depth) for v in row)
+                bits += "0" * (-len(bits) % 8)
+                rows.append(bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)))
+        return rows
+
+    def encode(samples, w, h, channels, depth, color_type, interlace=False, palette=None, split=1):
+        samples = np.asarray(samples).reshape(h, w, channels)
+        raw = b""
+        if not interlace:
+            raw = b"".join(b"\x00" + r for r in pack_rows(samples.reshape(h, w * channels), depth))
+        else:
+            for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+                sub = samples[y0::dy, x0::dx]
+                if sub.shape[0] and sub.shape[1]:
+                    raw += b"".join(b"\x00" + r for r in pack_rows(sub.reshape(sub.shape[0], -1), depth))
+        z = zlib.compress(raw, 6)
+        parts = [z[i * len(z) // split:(i + 1) * len(z) // split] for i in range(split)]
+        out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 1 if interlace else 0))
+        if palette is not None:
+            out += chunk(b"PLTE", bytes(int(v) for v in np.asarray(palette).reshape(-1)))
+        return out + b"".join(chunk(b"IDAT", part) for part in parts) + chunk(b"IEND", b"")
+
+    w, h = 13, 9
+    u = (uniform_floats(4242, (h, w, 4)) * 65536).astype(np.int64)
+    out = {
+        "rgb8": encode(u[..., :3] >> 8, w, h, 3, 8, 2),
+        "rgb8_interlaced": encode(u[..., :3] >> 8, w, h, 3, 8, 2, interlace=True, split=3),
+        "rgba8": encode(u >> 8, w, h, 4, 8, 6),
+        "rgb16": encode(u[..., :3], w, h, 3, 16, 2),
+        "rgba16_interlaced": encode(u, w, h, 4, 16, 6, interlace=True),
+        "gray8": encode(u[..., :1] >> 8, w, h, 1, 8, 0),
+        "gray16": encode(u[..., :1], w, h, 1, 16, 0),
+        "gray_alpha8": encode(u[..., :2] >> 8, w, h, 2, 8, 4),
+        "gray4": encode(u[..., :1] >> 12, w, h, 1, 4, 0),
+        "gray2_interlaced": encode(u[..., :1] >> 14, w, h, 1, 2, 0, interlace=True),
+        "gray1": encode(u[..., :1] >> 15, w, h, 1, 1, 0),
+        "palette8": encode(u[..., :1] % 200, w, h, 1, 8, 3, palette=(uniform_floats(4343, (200, 3)) * 256).astype(np.int64)),
+        "palette4_interlaced": encode(u[..., :1] >> 12, w, h, 1, 4, 3, interlace=True, palette=(uniform_floats(4344, (16, 3)) * 256).astype(np.int64)),
+        "palette1": encode(u[..., :1] >> 15, w, h, 1, 1, 3, palette=[[10, 20, 30], [200, 210, 220]]),
+    }
+    return out
+
+
+def make_test_texture(width=37, height=23):
+    """Deterministic 8-bit RGB test image (row 0 = top): smooth ramps plus a hash pattern, every byte value occurs."""
+    y, x = np.mgrid[0:height, 0:width].astype(np.uint32)
+    h = (x * np.uint32(2654435761) + y * np.uint32(40503) + np.uint32(12345)) >> np.uint32(7)
+    rgb = np.stack([(x * 255 // (width - 1)) ^ (h & 31), (y * 255 // (height - 1)) ^ ((h >> 5) & 63), (h >> 11) & 255], -1)
+    return np.ascontiguousarray(rgb & 255, dtype=np.uint8)
 
 
 def bsdf_inputs(name, n):
     """(wo, ng, ns, uv, wi, xi): normals uniform on the sphere; wo/wi uniform on the sphere for the first half
     (exercises every back-side branch), forced into the +n hemisphere for the second half."""
-    seed = 1000 + sorted(BSDF_CONFIGS).index(name) * 10
+    seed = 1000 + _SEED_ORDER.index(name) * 10
     ns = unit_vectors(seed + 1, n)
     wo = unit_vectors(seed + 2, n)
     wi = unit_vectors(seed + 3, n)
@@ -140,6 +254,9 @@ SCENES = {
                    image_width=96, image_height=54, image_spp=2048),
     "dragon": dict(scene="scenes/dragon.json", width=64, height=64, last_bounce=10, seed=15, n_rays=8192, n_paths=1024,
                    image_width=64, image_height=64, image_spp=2048),
+    # image textures on Lambertian and Plastic (PNG assets, uv outside [0, 1] on the box), area light
+    "textured": dict(scene="scenes/textured.json", width=64, height=48, last_bounce=10, seed=17, n_rays=4096, n_paths=2048,
+                     image_width=64, image_height=48, image_spp=2048),
     "env_sampling": dict(scene="test_scenes/environment_map_sampling.json", width=64, height=48, last_bounce=4, seed=16,
                          n_rays=2048, n_paths=1024, image_width=64, image_height=48, image_spp=1024),
 }

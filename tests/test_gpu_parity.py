@@ -22,7 +22,7 @@ def gpu_scene(name, width=None, height=None):
 
 
 def _tiny_scene(ctx, materials):
-    ids = [ctx.add_material(material_desc(m)) for m in materials]
+    ids = [ctx.add_material(material_desc(m, ctx)) for m in materials]
     ctx.add_triangle_mesh([[0, 0, 0], [1, 0, 0], [0, 1, 0]], None, None, [[0, 1, 2]], ids[0])
     ctx.set_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 0.5, 8, 8)
     ctx.commit()
@@ -137,7 +137,7 @@ def test_paths_match_reference_with_replayed_stream(name):
     assert abs(rgb.mean() - g["path_rgb"].mean()) <= 0.02 * abs(g["path_rgb"].mean()) + 1e-6
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_glass", "mis", "env_sampling", "teapot"])
+@pytest.mark.parametrize("name", ["cornell", "cornell_glass", "mis", "env_sampling", "teapot", "textured"])
 def test_wavefront_render_matches_oracle_per_pixel(name):
     """same Philox streams (pixel, sample, bounce) on both sides: the wavefront stages must reproduce the oracle's
     per-pixel sums, up to the rare path whose branch flips on a last-bit difference in libm"""
@@ -217,6 +217,15 @@ def test_error_statuses():
         ctx.add_triangle_mesh([[0, 0, 0], [1, 0, 0], [0, 1, 0]], None, None, [[0, 1, 5]], m)  # index out of range
     with pytest.raises(PathedError):
         ctx.add_sphere((0, 0, 0), 1.0, 9)  # unknown material
+    textured = material_desc(dict(type=0, diffuse=(1, 1, 1)))
+    textured.albedo_kind, textured.texture = 2, 3
+    with pytest.raises(PathedError):
+        ctx.add_material(textured)  # texture id out of range
+    with pytest.raises(PathedError):
+        ctx.add_texture(np.zeros((0, 4, 3), np.uint8))  # Texture::load: "Error loading texture"
+    textured.type, textured.texture = 3, ctx.add_texture(np.zeros((2, 2, 3), np.uint8))
+    with pytest.raises(PathedError):
+        ctx.add_material(textured)  # only Lambertian / Plastic take a texture
     with pytest.raises(PathedError):
         ctx.commit()  # no camera
 

@@ -29,7 +29,7 @@ def test_bsdf_matches_reference(name):
     g = golden("bsdf_" + name)
     wo, ng, ns, uv, wi, xi = bsdf_inputs(name, len(g["pdf"]))
     o = oracle_context()
-    mat = o.add_material(material_desc(BSDF_CONFIGS[name]))
+    mat = o.add_material(material_desc(BSDF_CONFIGS[name], o))
     isects = make_isects(wo, ng, ns, uv, mat)
     f, pdf = o.bsdf_eval(mat, isects, wi)
     assert frac_within(f, g["f"])[0] == 1.0, rel_err(f, g["f"]).max()

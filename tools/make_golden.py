@@ -24,7 +24,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from golden_inputs import (BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, material_params, ray_inputs, uniform_floats)  # noqa: E402
+from golden_inputs import (BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, make_test_texture, material_params, png_variants,  # noqa: E402
+                           ray_inputs, uniform_floats, write_png)
 
 PROBE = os.path.join(ROOT, "oracle", "_ref", "libpathed_ref_probe.so")
 HEADLESS = os.path.join(ROOT, "oracle", "_ref", "pathed_ref_headless")
@@ -37,17 +38,23 @@ def fptr(a):
 def probe():
     lib = ctypes.CDLL(PROBE)
     lib.ref_material_new.restype = ctypes.c_void_p
+    lib.ref_material_new_textured.restype = ctypes.c_void_p
     lib.ref_env_new.restype = ctypes.c_void_p
     return lib
 
 
 def gen_bsdf():
     lib = probe()
+    texture_png = os.path.join(GOLDEN, "texture_test.png")
+    write_png(texture_png, make_test_texture())  # decoded by the reference's stb_image inside the probe
     for name, cfg in BSDF_CONFIGS.items():
         n = 512
         wo, ng, ns, uv, wi, xi = bsdf_inputs(name, n)
         params = material_params(cfg)
-        mat = ctypes.c_void_p(lib.ref_material_new(ctypes.c_int(cfg["type"]), fptr(params)))
+        if cfg.get("textured"):
+            mat = ctypes.c_void_p(lib.ref_material_new_textured(ctypes.c_int(cfg["type"]), fptr(params), texture_png.encode()))
+        else:
+            mat = ctypes.c_void_p(lib.ref_material_new(ctypes.c_int(cfg["type"]), fptr(params)))
         f = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
         lib.ref_bsdf_eval(mat, n, fptr(wo), fptr(ng), fptr(ns), fptr(uv), fptr(wi), fptr(f), fptr(pdf))
         swi = np.zeros((n, 3), np.float32); spdf = np.zeros(n, np.float32); sthr = np.zeros((n, 3), np.float32)
@@ -58,6 +65,27 @@ def gen_bsdf():
         np.savez_compressed(os.path.join(GOLDEN, "bsdf_%s.npz" % name), f=f, pdf=pdf, sample_wi=swi, sample_pdf=spdf,
                             sample_throughput=sthr, consumed=used, frame=frame)
         print("bsdf", name, "f mean", f.mean(), "nonzero", (f.sum(1) != 0).mean())
+
+
+def gen_images_decode():
+    """What the reference's stb_image returns for every PNG variant (and a binary PPM): the decoder's known answers."""
+    import tempfile
+    lib = probe()
+    out = {}
+    files = dict(png_variants())
+    files["ppm_p6"] = b"P6\n# comment\n5 3\n255\n" + bytes(range(45))
+    files["pgm_p5"] = b"P5 4 2 255\n" + bytes(range(100, 108))
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, data in files.items():
+            path = os.path.join(tmp, name)
+            open(path, "wb").write(data)
+            w, h = ctypes.c_int(), ctypes.c_int()
+            assert lib.ref_load_image(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h)) == 0, name
+            rgb = np.zeros((h.value, w.value, 3), np.uint8)
+            lib.ref_load_image(path.encode(), fptr(rgb), rgb.size, ctypes.byref(w), ctypes.byref(h))
+            out[name] = rgb
+            print("decode", name, rgb.shape, int(rgb.sum()))
+    np.savez_compressed(os.path.join(GOLDEN, "image_decode.npz"), **out)
 
 
 def gen_lights():
@@ -195,11 +223,13 @@ def gen_images(names):
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
-    groups = sys.argv[1:] or ["bsdf", "lights", "scenes", "images"]
+    groups = sys.argv[1:] or ["bsdf", "lights", "decode", "scenes", "images"]
     if "bsdf" in groups:
         gen_bsdf()
     if "lights" in groups:
         gen_lights()
+    if "decode" in groups:
+        gen_images_decode()
     if "scenes" in groups:
         gen_scenes(list(SCENES))
     if "images" in groups:
