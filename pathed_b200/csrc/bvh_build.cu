@@ -4,6 +4,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <future>
@@ -139,6 +142,7 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
     for (int a = 0; a < 3; a++) { out.sceneLo[a] = 0.f; out.sceneHi[a] = 0.f; }
     if (nPrims == 0) { return; }
 
+    const auto t0 = std::chrono::steady_clock::now();
     Builder b;
     b.pos = positions4; b.idx = indices4;
     b.primBox.resize(nPrims); b.centroid.resize(3 * (size_t)nPrims); b.order.resize(nPrims);
@@ -155,6 +159,7 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
     b.build(root, 0, nPrims, 0);
     for (int a = 0; a < 3; a++) { out.sceneLo[a] = b.nodes[root].box.lo[a]; out.sceneHi[a] = b.nodes[root].box.hi[a]; }
 
+    const auto t1 = std::chrono::steady_clock::now();
     // ---- SAH-optimal collapse to 8-wide (Ylitie, Karras, Laine 2017, section 3.1): C(n, i) = cheapest way to represent the
     // binary subtree n as a forest of at most i wide-BVH roots, bottom-up; a subtree of at most 3 triangles may become one leaf.
     const float cNode = 1.0f, cPrim = 0.4f;
@@ -220,6 +225,7 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
     };
     const Collector collector = {b, cost, splitAt};
 
+    const auto t2 = std::chrono::steady_clock::now();
     // ---- emit wide nodes breadth first so that the inner children of a node are contiguous
     struct Work { uint32_t wide, node2, depth; };
     std::queue<Work> work;
@@ -308,6 +314,12 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
             }
         }
         out.nodes[w.wide] = node;
+    }
+    if (getenv("PTC_BUILD_TIMING")) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "buildWideBVH: %u prims: binary SAH %.1f ms, collapse DP %.1f ms, emit %.1f ms -> %zu wide nodes\n", nPrims,
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), out.nodes.size());
     }
     if (out.maxDepth + 2 > PTC_STACK_SIZE) { throw std::runtime_error("BVH deeper than the traversal stack"); }
 }

@@ -151,7 +151,7 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 // dragon workload; with a bound, rays with triangles left skip node phases until their group is finished, so triangle
 // rounds fill up with the leftovers of several node phases.  Per-ray order of operations, hence every result, is unchanged.
 #ifndef PTC_TRI_ROUNDS
-#define PTC_TRI_ROUNDS 1
+#define PTC_TRI_ROUNDS 2 /* sweep on the dragon workload: 1000 (while-while) 560, 1: 602, 2: 607, 3: 590 Msamples/s */
 #endif
 template <bool ANY>
 __device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState &st, bool eligible, uint8_t *ownerOf)
@@ -211,16 +211,16 @@ __device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState
         if (ANY) {
             if (seg) { done = true; st.found = true; }
         } else if (acc) {
-            const float t = divIeee(T, absDen), u = divIeee(U, absDen), v = divIeee(V, absDen);
+            const float t = divIeee(T, absDen);
             while (__any_sync(FULL, seg != 0u)) {
                 const uint32_t src = seg ? S + (uint32_t)__ffs((int)seg) - 1u : lane;
-                const float ct = __shfl_sync(FULL, t, src), cu = __shfl_sync(FULL, u, src), cv = __shfl_sync(FULL, v, src);
+                const float ct = __shfl_sync(FULL, t, src), cu = __shfl_sync(FULL, U, src), cv = __shfl_sync(FULL, V, src);
                 const float cT = __shfl_sync(FULL, T, src), cA = __shfl_sync(FULL, absDen, src);
                 const uint32_t cp = __shfl_sync(FULL, prim, src);
                 if (seg) {
                     seg &= seg - 1u;
                     if (cT <= cA * st.hit.t) { // the candidate passed (tnear, round-start tfar]; tfar may have shrunk since
-                        if (!(st.found && ct == st.hit.t && cp < st.hit.prim)) { st.hit.t = ct; st.hit.u = cu; st.hit.v = cv; st.hit.prim = cp; }
+                        if (!(st.found && ct == st.hit.t && cp < st.hit.prim)) { st.hit.t = ct; st.hit.u = cu; st.hit.v = cv; st.hitDen = cA; st.hit.prim = cp; }
                         st.found = true;
                     }
                 }
@@ -305,6 +305,8 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
 // ------------------------------------------------------------------------------------------------ K5-K6 logic
 // Handles the result of the ray that left vertex k (k = 0: the camera ray): everything in PathTracer::L between two
 // BSDF samples.  Cheap per path (the Intersection is only built for emitter hits); survivors go to the class queues.
+// 78-86 registers -> 3 CTAs of 256 (logic) / 6 CTAs of 128 (material) per SM.  Forcing 64 registers (4 / 8 CTAs) spills and was
+// measured equal (shade 42.7 ms per 4 steps either way), so the compiler's allocation stands.
 __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;

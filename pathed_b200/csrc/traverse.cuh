@@ -208,7 +208,8 @@ struct TraversalState {
     uint2 ngroup, tgroup;
     int sp;
     bool found;
-    RayHit hit;
+    RayHit hit;     // while the BVH is being traversed hit.u / hit.v hold the numerators U, V of the closest triangle so far
+    float hitDen;   // and hitDen its |den|: the two divisions are done once per ray (traversalSpheres), not once per accepted hit
     uint2 stack[PTC_STACK_SIZE];
 };
 
@@ -247,6 +248,7 @@ PTC_HD void traversalInit(TraversalState &st, float ox, float oy, float oz, floa
     st.sp = 0;
     st.found = false;
     st.hit.t = tfar; st.hit.u = 0.f; st.hit.v = 0.f; st.hit.prim = PTC_MISS;
+    st.hitDen = 1.f;
 }
 
 // The traversal is split into three per-ray phases so that a kernel can run each phase for all the rays of a warp that
@@ -330,11 +332,12 @@ PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCo
     const float4 *tri = bvh.triangles + (size_t)(st.tgroup.x + bit) * 3;
     const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
     if (COUNT) { counters->tris++; }
-    float t, u, v;
-    if (!triangleTest(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, u, v)) { return false; }
+    float T, U, V, absDen;
+    if (!triangleTestRaw(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
+    const float t = divIeee(T, absDen);
     const uint32_t prim = f2u(a.w);
     // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
-    if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = u; st.hit.v = v; st.hit.prim = prim; }
+    if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = U; st.hit.v = V; st.hitDen = absDen; st.hit.prim = prim; }
     st.found = true;
     return true;
 }
@@ -362,6 +365,7 @@ template <bool ANY>
 PTC_HD bool traversalSpheres(const BvhView &bvh, TraversalState &st)
 {
     if (ANY && st.found) { return true; }
+    if (st.found) { st.hit.u = divIeee(st.hit.u, st.hitDen); st.hit.v = divIeee(st.hit.v, st.hitDen); } // u = U / |den|, v = V / |den|
     for (uint32_t s = 0; s < bvh.nSpheres; s++) {
         float t, nx, ny, nz;
         if (sphereTest(loadNodeWord(bvh.spheres + s), st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, nx, ny, nz)) {
