@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--paths-per-wave", type=int, default=0, help="override the library's wave size (paths resident per wave)")
+    ap.add_argument("--bvh-builder", type=int, default=1, choices=[0, 1], help="1: device builder (default), 0: host binned-SAH builder")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -173,8 +174,9 @@ def main():
     width, height, last = w["width"], w["height"], w["last_bounce"]
     spp = args.spp_per_step
     t0 = time.time()
-    ctx = load_scene(w["scene"], width, height, device=local_rank)
+    ctx = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder})
     build_s = time.time() - t0
+    tst0 = ctx.stats()
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
     ppw = args.paths_per_wave or (1 << 24)
@@ -317,7 +319,9 @@ def main():
             "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], width, height, last), "spp_per_step": spp,
                        "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 148 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
-                       "scene_build_s": build_s},
+                       "scene_build_s": build_s,
+                       "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
+                                     "ms": tst0.bvh_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},
             "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu,

@@ -121,6 +121,10 @@ typedef struct ptc_stats {
     uint64_t extend_launches, shadow_launches, shade_launches;
     float extend_ms, shadow_ms, shade_ms, other_ms;
     float last_render_ms; /* device time of the last ptc_render call (CUDA events, copies included) */
+    /* BVH build of ptc_commit (rtcCommitScene, src/scene.cpp:39): wall time of the build incl. its synchronisations,
+     * builder used (1 = device: Morton sort + PLOC clustering + wide collapse in kernels, 0 = host binned SAH) */
+    float bvh_build_ms;
+    uint32_t bvh_builder, bvh_depth, bvh_ploc_iterations;
 } ptc_stats;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -226,7 +230,8 @@ int ptc_reset_stats(ptc_ctx *ctx);
 /* queue sizes of the most recent wave: extend_counts[k] = rays that left vertex k (k = 0: camera rays), shadow_counts[k] =
  * NEE shadow rays cast at vertex k; up to `capacity` (<= PTC_MAX_BOUNCES + 2) entries each */
 int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend_counts, uint32_t *shadow_counts, uint32_t capacity);
-int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave" */
+int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave",
+                                                                      "bvh_builder" (before ptc_commit: 1 device, 0 host) */
 /* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
  * visits and triangle tests per ray (algorithmic bytes per ray) */
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);
@@ -238,6 +243,13 @@ int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t 
 int ptc_bvh_selfcheck(const float *positions, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles,
                       const ptc_ray *rays, uint32_t n_rays, float *t_bvh, uint32_t *prim_bvh, float *t_brute,
                       uint32_t *prim_brute, uint64_t stats[6]);
+
+/* the same check with the builder chosen: 0 = the host binned-SAH builder, 1 = the DEVICE builder's per-element code
+ * (Morton order, PLOC clustering, collapse, emission) executed serially on the host -- a test hook for the CPU suite;
+ * ptc_commit runs that code only as CUDA kernels.  sah_cost: cost of the wide BVH under the collapse's cost model. */
+int ptc_bvh_selfcheck_builder(int builder, const float *positions, uint32_t n_vertices, const uint32_t *indices,
+                              uint32_t n_triangles, const ptc_ray *rays, uint32_t n_rays, float *t_bvh, uint32_t *prim_bvh,
+                              float *t_brute, uint32_t *prim_brute, uint64_t stats[6], double *sah_cost);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,8 @@ class Stats(ctypes.Structure):
                                                "bvh_triangles", "bvh_bytes", "extend_inner_visits", "extend_triangle_tests",
                                                "shadow_inner_visits", "shadow_triangle_tests", "extend_launches",
                                                "shadow_launches", "shade_launches")] + \
-               [(n, ctypes.c_float) for n in ("extend_ms", "shadow_ms", "shade_ms", "other_ms", "last_render_ms")]
+               [(n, ctypes.c_float) for n in ("extend_ms", "shadow_ms", "shade_ms", "other_ms", "last_render_ms", "bvh_build_ms")] + \
+               [(n, ctypes.c_uint32) for n in ("bvh_builder", "bvh_depth", "bvh_ploc_iterations")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -434,8 +435,11 @@ def create_context(device=0):
     return Api(cuda_lib(), "ptc_", device)
 
 
-def load_scene(scene_json, width, height, device=0, root=REPO_ROOT):
-    """parseScene + upload: the Python spelling of what app/main.cpp does before Integrator::run."""
+def load_scene(scene_json, width, height, device=0, root=REPO_ROOT, options=None):
+    """parseScene + upload: the Python spelling of what app/main.cpp does before Integrator::run.
+    options: ptc_set_option pairs applied before the commit (e.g. {"bvh_builder": 0} for the host SAH builder)."""
     api = create_context(device)
+    for name, value in (options or {}).items():
+        api.set_option(name, value)
     SceneFile(scene_json, width, height, root).feed(api)
     return api

@@ -4,6 +4,8 @@
 // rtcCommitScene (src/scene.cpp:39).
 #pragma once
 
+#include <cuda_runtime.h>
+
 #include <cstdint>
 #include <vector>
 
@@ -44,6 +46,23 @@ struct WideBVH {
 
 // positions: float4 per vertex (xyz used); indices: 4 uint32 per primitive (i0, i1, i2, material)
 void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nPrims, WideBVH &out);
+
+// Device builder (bvh_build_gpu.cu): Morton sort -> PLOC clustering -> the same SAH-optimal 8-wide collapse and
+// node encoding, all in kernels on `stream`.  Inputs and outputs are device pointers; `nodes` / `triangles` are cudaMalloc'ed
+// and owned by the caller.  Throws std::runtime_error on CUDA errors.
+struct DeviceWideBVH {
+    float4 *nodes = nullptr;     // 5 float4 per node
+    float4 *triangles = nullptr; // 3 float4 per triangle
+    uint32_t nNodes = 0, nTriangles = 0, maxDepth = 0, plocIterations = 0;
+    float buildMs[4] = {0, 0, 0, 0}; // boxes + sort, clustering, emission, total (host clock around synchronised phases)
+};
+void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t nPrims, cudaStream_t stream, DeviceWideBVH &out);
+// The device builder's per-element code run serially on the host (ptc_bvh_selfcheck_builder: CPU tests of the algorithm).
+// Never used by ptc_commit.
+void buildWideBVHEmulated(const float *positions4, const uint32_t *indices4, uint32_t nPrims, WideBVH &out);
+// SAH cost of a wide BVH: sum over nodes of area(node) * 1.0 + sum over leaf slots of area(slot box) * 0.4 * triangles, divided
+// by the root area (the collapse's own cost model)
+double wideBVHCost(const WideBVH &bvh);
 
 // Scalar reference traversal of the wide BVH (same node/triangle decoding as the kernels) that counts work:
 // SURVEY §8(d) defines the algorithmic bytes per ray from these counts.  Returns true on a hit.

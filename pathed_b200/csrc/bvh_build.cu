@@ -324,6 +324,46 @@ void buildWideBVH(const float *positions4, const uint32_t *indices4, uint32_t nP
     if (out.maxDepth + 2 > PTC_STACK_SIZE) { throw std::runtime_error("BVH deeper than the traversal stack"); }
 }
 
+double wideBVHCost(const WideBVH &bvh)
+{
+    if (bvh.nodes.empty()) { return 0.0; }
+    struct Entry { uint32_t node; double area; };
+    std::vector<Entry> todo;
+    auto slotArea = [](const WideNode &n, int s) {
+        double e[3];
+        const uint8_t *lo[3] = {n.qlox, n.qloy, n.qloz}, *hi[3] = {n.qhix, n.qhiy, n.qhiz};
+        for (int a = 0; a < 3; a++) { e[a] = (double)u2f((uint32_t)n.exponent[a] << 23) * (double)((int)hi[a][s] - (int)lo[a][s]); }
+        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    };
+    double rootArea = 0.0;
+    {
+        const WideNode &r = bvh.nodes[0];
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        const uint8_t *ql[3] = {r.qlox, r.qloy, r.qloz}, *qh[3] = {r.qhix, r.qhiy, r.qhiz};
+        for (int s = 0; s < 8; s++) {
+            if (!r.meta[s]) { continue; }
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], (double)ql[a][s]); hi[a] = std::max(hi[a], (double)qh[a][s]); }
+        }
+        double e[3];
+        for (int a = 0; a < 3; a++) { e[a] = (double)u2f((uint32_t)r.exponent[a] << 23) * std::max(0.0, hi[a] - lo[a]); }
+        rootArea = e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    }
+    double cost = 0.0;
+    todo.push_back({0u, rootArea});
+    while (!todo.empty()) {
+        const Entry en = todo.back(); todo.pop_back();
+        const WideNode &n = bvh.nodes[en.node];
+        cost += en.area * 1.0;
+        uint32_t inner = 0;
+        for (int s = 0; s < 8; s++) {
+            if (!n.meta[s]) { continue; }
+            if (n.imask & (1u << s)) { todo.push_back({n.childBase + inner, slotArea(n, s)}); inner++; }
+            else { cost += slotArea(n, s) * 0.4 * (double)popCount((uint32_t)n.meta[s] >> 5); }
+        }
+    }
+    return rootArea > 0.0 ? cost / rootArea : 0.0;
+}
+
 bool traverseReference(const WideBVH &bvh, const float o[3], const float d[3], float tnear, float tfar, bool anyHit,
                        float *tOut, uint32_t *primOut, TraversalCounts *counts)
 {

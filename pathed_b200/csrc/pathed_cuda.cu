@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 using namespace ptc;
@@ -727,6 +728,8 @@ struct ptc_ctx {
     // options / stats
     int64_t pathsPerWave = 1 << 24; // 16.8 M paths x 157 B = 2.6 GB of path state per wave: long queues keep 148 SMs busy through the late bounces
     bool stageTiming = false, countTraversal = false;
+    int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
+    float bvhBuildMs = 0.f; uint32_t bvhPlocIterations = 0;
     uint64_t samples = 0, launches = 0;
     float lastRenderMs = 0.f;
     // stage timing: CUDA events on the launching stream around every launch, summed per kernel class
@@ -991,9 +994,37 @@ int ptc_commit(ptc_ctx *ctx)
     DScene &s = ctx->scene;
     const uint32_t nPrims = (uint32_t)(ctx->prims4.size() / 4);
 
-    // rtcCommitScene: BVH over all triangle geometries; spheres are kept in a flat list
-    try { buildWideBVH(ctx->positions4.data(), ctx->prims4.data(), nPrims, ctx->bvh); }
-    catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
+    // rtcCommitScene: BVH over all triangle geometries; spheres are kept in a flat list.  The geometry goes to the device first:
+    // the default builder runs there (option "bvh_builder" = 0 selects the host binned-SAH builder instead).
+    int rc;
+    auto &A = ctx->allocations;
+    if ((rc = upload(ctx, (const float4 *)ctx->positions4.data(), ctx->positions4.size() / 4, &s.positions, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint4 *)ctx->prims4.data(), ctx->prims4.size() / 4, &s.prims, A))) { return rc; }
+    {
+        const auto buildStart = std::chrono::steady_clock::now();
+        try {
+            if (ctx->bvhBuilder == 1) {
+                DeviceWideBVH built;
+                buildWideBVHDevice(s.positions, s.prims, nPrims, ctx->stream, built);
+                if (built.nodes) { A.push_back(built.nodes); }
+                if (built.triangles) { A.push_back(built.triangles); }
+                s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
+                ctx->bvhPlocIterations = built.plocIterations;
+                // host copy for the scalar counting traversal (ptc_count_traversal) and the statistics
+                ctx->bvh.nodes.resize(built.nNodes); ctx->bvh.triangles.resize(built.nTriangles); ctx->bvh.maxDepth = built.maxDepth;
+                if (built.nNodes) {
+                    CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.nodes.data(), built.nodes, (size_t)built.nNodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+                    CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.triangles.data(), built.triangles, (size_t)built.nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
+                }
+            } else {
+                buildWideBVH(ctx->positions4.data(), ctx->prims4.data(), nPrims, ctx->bvh);
+                if ((rc = upload(ctx, (const float4 *)ctx->bvh.nodes.data(), ctx->bvh.nodes.size() * 5, &s.bvh.nodes, A))) { return rc; }
+                if ((rc = upload(ctx, (const float4 *)ctx->bvh.triangles.data(), ctx->bvh.triangles.size() * 3, &s.bvh.triangles, A))) { return rc; }
+                s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
+            }
+        } catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
+        ctx->bvhBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - buildStart).count();
+    }
 
     // textures: packed texels per image, one gamma table for all (Texture::lookup's powf(c / 255.f, 2.2f), src/texture.cpp:44-48)
     std::vector<const uint32_t *> deviceTexels(ctx->textures.size(), nullptr);
@@ -1056,17 +1087,10 @@ int ptc_commit(ptc_ctx *ctx)
     if (ctx->hasEnv) { DLight l; memset(&l, 0, sizeof(l)); l.kind = 2; lights.push_back(l); }
     ctx->nLights = (uint32_t)lights.size();
 
-    int rc;
-    auto &A = ctx->allocations;
-    if ((rc = upload(ctx, (const float4 *)ctx->bvh.nodes.data(), ctx->bvh.nodes.size() * 5, &s.bvh.nodes, A))) { return rc; }
-    if ((rc = upload(ctx, (const float4 *)ctx->bvh.triangles.data(), ctx->bvh.triangles.size() * 3, &s.bvh.triangles, A))) { return rc; }
     if ((rc = upload(ctx, (const float4 *)spheres4.data(), spheres4.size() / 4, &s.bvh.spheres, A))) { return rc; }
     s.bvh.nSpheres = (uint32_t)(spheres4.size() / 4);
-    s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
-    if ((rc = upload(ctx, (const float4 *)ctx->positions4.data(), ctx->positions4.size() / 4, &s.positions, A))) { return rc; }
     if ((rc = upload(ctx, (const float4 *)ctx->normals4.data(), ctx->normals4.size() / 4, &s.normals, A))) { return rc; }
     if ((rc = upload(ctx, (const float2 *)ctx->uvs2.data(), ctx->uvs2.size() / 2, &s.uvs, A))) { return rc; }
-    if ((rc = upload(ctx, (const uint4 *)ctx->prims4.data(), ctx->prims4.size() / 4, &s.prims, A))) { return rc; }
     if ((rc = upload(ctx, (const uint2 *)ctx->primIds2.data(), ctx->primIds2.size() / 2, &s.primIds, A))) { return rc; }
     if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
     if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }
@@ -1490,6 +1514,8 @@ int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
     out->extend_ms = (float)ctx->stageMs[STAGE_EXTEND]; out->shadow_ms = (float)ctx->stageMs[STAGE_SHADOW];
     out->shade_ms = (float)ctx->stageMs[STAGE_SHADE]; out->other_ms = (float)ctx->stageMs[STAGE_OTHER];
     out->last_render_ms = ctx->lastRenderMs;
+    out->bvh_build_ms = ctx->bvhBuildMs; out->bvh_builder = (uint32_t)ctx->bvhBuilder; out->bvh_depth = ctx->bvh.maxDepth;
+    out->bvh_ploc_iterations = ctx->bvhPlocIterations;
     return PTC_OK;
 }
 
@@ -1522,6 +1548,11 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "paths_per_wave")) { if (value < 1024) { CTX_FAIL(ctx, PTC_ERR_INVALID, "paths_per_wave must be >= 1024"); } ctx->pathsPerWave = value; return PTC_OK; }
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
+    if (!strcmp(name, "bvh_builder")) { // before ptc_commit; 1 = device (default), 0 = host binned SAH
+        if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "bvh_builder must be set before ptc_commit"); }
+        if (value != 0 && value != 1) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bvh_builder must be 0 (host) or 1 (device)"); }
+        ctx->bvhBuilder = (int)value; return PTC_OK;
+    }
     CTX_FAIL(ctx, PTC_ERR_INVALID, "unknown option %s", name);
 }
 
@@ -1538,6 +1569,14 @@ int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t 
 int ptc_bvh_selfcheck(const float *P, uint32_t nv, const uint32_t *I, uint32_t nt, const ptc_ray *rays, uint32_t nRays, float *tBvh,
                       uint32_t *primBvh, float *tBrute, uint32_t *primBrute, uint64_t stats[6])
 {
+    double cost = 0;
+    return ptc_bvh_selfcheck_builder(0, P, nv, I, nt, rays, nRays, tBvh, primBvh, tBrute, primBrute, stats, &cost);
+}
+
+int ptc_bvh_selfcheck_builder(int builder, const float *P, uint32_t nv, const uint32_t *I, uint32_t nt, const ptc_ray *rays, uint32_t nRays,
+                              float *tBvh, uint32_t *primBvh, float *tBrute, uint32_t *primBrute, uint64_t stats[6], double *sahCost)
+{
+    if (builder != 0 && builder != 1) { return PTC_ERR_INVALID; }
     if (!P || !I || !stats || (nRays && (!rays || !tBvh || !primBvh || !tBrute || !primBrute))) { return PTC_ERR_INVALID; }
     std::vector<float> positions4((size_t)nv * 4, 0.f);
     std::vector<uint32_t> prims4((size_t)nt * 4, 0u);
@@ -1546,7 +1585,11 @@ int ptc_bvh_selfcheck(const float *P, uint32_t nv, const uint32_t *I, uint32_t n
         for (int a = 0; a < 3; a++) { if (I[3 * (size_t)t + a] >= nv) { return PTC_ERR_INVALID; } prims4[4 * (size_t)t + a] = I[3 * (size_t)t + a]; }
     }
     WideBVH bvh;
-    try { buildWideBVH(positions4.data(), prims4.data(), nt, bvh); } catch (const std::exception &) { return PTC_ERR_INVALID; }
+    try {
+        if (builder == 1) { buildWideBVHEmulated(positions4.data(), prims4.data(), nt, bvh); }
+        else { buildWideBVH(positions4.data(), prims4.data(), nt, bvh); }
+    } catch (const std::exception &) { return PTC_ERR_INVALID; }
+    if (sahCost) { *sahCost = wideBVHCost(bvh); }
     uint64_t slots = 0;
     for (const WideNode &n : bvh.nodes) { for (int s = 0; s < 8; s++) { slots += n.meta[s] ? 1 : 0; } }
     TraversalCounts counts;

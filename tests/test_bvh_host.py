@@ -9,18 +9,22 @@ from golden_inputs import uniform_floats, unit_vectors
 from pathed_b200._binding import RAY_DTYPE, cuda_lib, rays_array
 
 
-def selfcheck(positions, indices, rays):
+def selfcheck(positions, indices, rays, builder=0):
     lib = cuda_lib()
     positions = np.ascontiguousarray(positions, np.float32); indices = np.ascontiguousarray(indices, np.uint32)
     n = len(rays)
     t_bvh = np.zeros(n, np.float32); p_bvh = np.zeros(n, np.uint32); t_bf = np.zeros(n, np.float32); p_bf = np.zeros(n, np.uint32)
     stats = (ctypes.c_uint64 * 6)()
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.ptc_bvh_selfcheck(ptr(positions), ctypes.c_uint32(len(positions)), ptr(indices), ctypes.c_uint32(len(indices)), ptr(rays),
-                               ctypes.c_uint32(n), ptr(t_bvh), ptr(p_bvh), ptr(t_bf), ptr(p_bf), stats)
+    cost = ctypes.c_double(0)
+    rc = lib.ptc_bvh_selfcheck_builder(ctypes.c_int(builder), ptr(positions), ctypes.c_uint32(len(positions)), ptr(indices),
+                                       ctypes.c_uint32(len(indices)), ptr(rays), ctypes.c_uint32(n), ptr(t_bvh), ptr(p_bvh), ptr(t_bf),
+                                       ptr(p_bf), stats, ctypes.byref(cost))
     assert rc == 0
     keys = ("nodes", "triangles", "slots", "max_depth", "inner_visits", "triangle_tests")
-    return t_bvh, p_bvh, t_bf, p_bf, dict(zip(keys, [int(x) for x in stats]))
+    st = dict(zip(keys, [int(x) for x in stats]))
+    st["sah_cost"] = cost.value
+    return t_bvh, p_bvh, t_bf, p_bf, st
 
 
 def bumpy_sphere(n_u, n_v, seed):
@@ -35,7 +39,11 @@ def bumpy_sphere(n_u, n_v, seed):
     return pts.astype(np.float32), faces.astype(np.uint32)
 
 
-def test_wide_bvh_matches_brute_force_on_a_mesh():
+BUILDERS = [pytest.param(0, id="host-sah"), pytest.param(1, id="device-algorithm")]
+
+
+@pytest.mark.parametrize("builder", BUILDERS)
+def test_wide_bvh_matches_brute_force_on_a_mesh(builder):
     pts, faces = bumpy_sphere(96, 64, 3)
     n = 3000
     origins = unit_vectors(5, n) * np.float32(3.0)
@@ -44,7 +52,7 @@ def test_wide_bvh_matches_brute_force_on_a_mesh():
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     inside = np.zeros((200, 3), np.float32)  # rays from inside the mesh always hit
     rays = rays_array(np.concatenate([origins, inside]), np.concatenate([d, unit_vectors(8, 200)]))
-    t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays)
+    t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays, builder)
     assert np.array_equal(p_bvh, p_bf) and np.array_equal(t_bvh, t_bf)  # bit-exact: same triangle arithmetic, same tie rule
     assert (p_bvh[-200:] != 0xFFFFFFFF).all() and (p_bvh != 0xFFFFFFFF).mean() > 0.5
     assert st["triangles"] == len(faces)
@@ -53,8 +61,9 @@ def test_wide_bvh_matches_brute_force_on_a_mesh():
     assert st["inner_visits"] / len(rays) < 40 and st["triangle_tests"] / len(rays) < 30, st
 
 
+@pytest.mark.parametrize("builder", BUILDERS)
 @pytest.mark.parametrize("case", ["single", "degenerate", "coincident", "soup"])
-def test_wide_bvh_edge_cases(case):
+def test_wide_bvh_edge_cases(case, builder):
     if case == "single":
         pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32); faces = np.array([[0, 1, 2]], np.uint32)
     elif case == "degenerate":  # zero-area and repeated triangles, all centroids identical
@@ -76,8 +85,27 @@ def test_wide_bvh_edge_cases(case):
     if case == "soup":
         o = unit_vectors(23, n) * np.float32(3); d = -o / np.linalg.norm(o, axis=1, keepdims=True) + 0.2 * unit_vectors(24, n)
     rays = rays_array(o, d)
-    t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays)
+    t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays, builder)
     assert np.array_equal(p_bvh, p_bf) and np.array_equal(t_bvh, t_bf)
+    assert st["triangles"] == len(faces)
     if case == "coincident":
         hit = p_bvh != 0xFFFFFFFF
         assert hit.any() and (p_bvh[hit] >= 50).all()
+
+
+def test_device_builder_quality_is_close_to_the_host_sah_builder():
+    """PLOC clustering (the device builder's algorithm, run here through its host emulation) against the binned-SAH host
+    builder on the same mesh and rays: SAH cost and counted traversal work within 15 %."""
+    pts, faces = bumpy_sphere(160, 96, 5)
+    n = 4000
+    origins = unit_vectors(31, n) * np.float32(3.0)
+    d = unit_vectors(32, n) * np.float32(0.9) - origins
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = rays_array(origins, d)
+    host = selfcheck(pts, faces, rays, 0)[4]
+    dev = selfcheck(pts, faces, rays, 1)[4]
+    print("host", host, "device", dev)
+    assert dev["sah_cost"] < 1.15 * host["sah_cost"], (host, dev)
+    work = lambda st: 80 * st["inner_visits"] + 48 * st["triangle_tests"]
+    assert work(dev) < 1.15 * work(host), (host, dev)
+    assert dev["slots"] / dev["nodes"] > 5.0
