@@ -5,7 +5,8 @@
 //   2. 63-bit Morton codes of the centroids, radix sort        (cub::DeviceRadixSort)
 //   3. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): every cluster looks for the neighbour within
 //      +-PLOC_RADIUS positions of the Morton order that gives the smallest merged surface area; mutual nearest neighbours
-//      merge; the cluster list is compacted with a prefix sum; repeat until one cluster is left.  The SAH-optimal 8-wide
+//      merge; the cluster list is compacted with a prefix sum; repeat until PLOC_TOP_CLUSTERS clusters are left.  The top of the
+//      tree (visited by every ray) is then built over those clusters top-down with a binned SAH.  The SAH-optimal 8-wide
 //      collapse table C(n, 1..7) of Ylitie et al. 2017 is computed at the moment a node is created (its children are final).
 //   4. level-by-level emission of the compressed 80-byte nodes: children chosen from the collapse table, octant-ordered slot
 //      assignment, outward quantisation, leaf triangles in Embree's (v0, e1, e2) form.  Node and triangle indices come from
@@ -36,8 +37,14 @@ namespace {
 #ifndef PLOC_RADIUS
 #define PLOC_RADIUS 16
 #endif
+#ifndef PLOC_TOP_CLUSTERS
+#define PLOC_TOP_CLUSTERS 512
+#endif
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
-constexpr float kCostNode = 1.0f, kCostPrim = 0.4f; // same constants as the host builder's collapse
+#ifndef PTC_COST_PRIM
+#define PTC_COST_PRIM 0.4f
+#endif
+constexpr float kCostNode = 1.0f, kCostPrim = PTC_COST_PRIM; // same constants as the host builder's collapse
 constexpr uint32_t kMaxLeaf = 3;
 constexpr float kInf = 3.0e38f;
 
@@ -89,6 +96,8 @@ struct BuildArrays {
     float4 *clusterLo[2], *clusterHi[2];
     uint32_t *nearest;
     uint64_t *scanIn, *scanOut; // packed counters: high word / low word scanned together
+    uint4 *topTasks;            // task stack of the top-level SAH pass
+    uint32_t *topResults;
     // emission
     uint32_t *items[2];     // binary node of every wide node of the current / next level
     uint32_t *itemChildren; // 8 per item, slot order, kInvalid = empty
@@ -159,13 +168,13 @@ struct LeafOp {
 struct NearestOp {
     BuildArrays a;
     int buffer;
-    uint32_t nClusters;
+    uint32_t nClusters, radius;
     PTC_HD void operator()(uint32_t i) const
     {
         const float4 *lo = a.clusterLo[buffer], *hi = a.clusterHi[buffer];
         const float4 l = lo[i], h = hi[i];
-        const uint32_t first = i > PLOC_RADIUS ? i - PLOC_RADIUS : 0u;
-        const uint32_t last = i + PLOC_RADIUS < nClusters - 1u ? i + PLOC_RADIUS : nClusters - 1u;
+        const uint32_t first = i > radius ? i - radius : 0u;
+        const uint32_t last = i + radius < nClusters - 1u ? i + radius : nClusters - 1u;
         float best = kInf; uint32_t bestJ = kInvalid;
         for (uint32_t j = first; j <= last; j++) {
             if (j == i) { continue; }
@@ -242,6 +251,97 @@ struct MergeOp {
         }
         a.clusterLo[buffer ^ 1][slot] = lo;
         a.clusterHi[buffer ^ 1][slot] = hi;
+    }
+};
+
+// ---- step 3b: top of the tree ----------------------------------------------------------------------------------------------
+// Agglomerative clustering decides well near the leaves but the last few hundred merges (the top of the tree, visited by every
+// ray) are taken between whatever clusters happen to be left.  So PLOC stops at `count` clusters and the top is built over them
+// top-down with a 16-bin SAH over all three axes (the host builder's split rule), by one thread: a few thousand clusters.
+struct TopDownOp {
+    BuildArrays a;
+    int buffer;
+    uint32_t count, firstNewNode;
+    PTC_HD void operator()(uint32_t) const
+    {
+        float4 *lo = a.clusterLo[buffer], *hi = a.clusterHi[buffer];
+        uint4 *tasks = a.topTasks; // first, count, state, mid
+        uint32_t *results = a.topResults;
+        uint32_t sp = 0, rp = 0, nextNode = firstNewNode;
+        tasks[sp++] = make_uint4(0u, count, 0u, 0u);
+        while (sp) {
+            const uint4 t = tasks[sp - 1];
+            if (t.z == 1u) { // both halves are built
+                const uint32_t right = results[--rp], left = results[--rp];
+                const float4 l0 = a.nodeLo[left], h0 = a.nodeHi[left], l1 = a.nodeLo[right], h1 = a.nodeHi[right];
+                const float4 l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), u2f(left));
+                const float4 h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), u2f(right));
+                a.nodeLo[nextNode] = l; a.nodeHi[nextNode] = h;
+                a.dp[nextNode] = combineDP(a.dp[left], a.dp[right], halfArea(l.x, l.y, l.z, h.x, h.y, h.z));
+                results[rp++] = nextNode++;
+                sp--;
+                continue;
+            }
+            if (t.y == 1u) { results[rp++] = f2u(lo[t.x].w); sp--; continue; }
+            const uint32_t first = t.x, end = t.x + t.y;
+            float cl[3] = {kInf, kInf, kInf}, ch[3] = {-kInf, -kInf, -kInf};
+            for (uint32_t i = first; i < end; i++) {
+                float c[3];
+                centroidOf(lo[i], hi[i], c);
+                for (int k = 0; k < 3; k++) { cl[k] = fminf(cl[k], c[k]); ch[k] = fmaxf(ch[k], c[k]); }
+            }
+            const int BINS = 16;
+            float bestCost = kInf; int bestAxis = -1, bestBin = -1;
+            for (int axis = 0; axis < 3; axis++) {
+                const float extent = ch[axis] - cl[axis];
+                if (!(extent > 0.f)) { continue; }
+                float bl[BINS][3], bh[BINS][3]; uint32_t bn[BINS];
+                for (int b = 0; b < BINS; b++) { bn[b] = 0; for (int k = 0; k < 3; k++) { bl[b][k] = kInf; bh[b][k] = -kInf; } }
+                const float scale = (float)BINS / extent;
+                for (uint32_t i = first; i < end; i++) {
+                    const float4 l = lo[i], h = hi[i];
+                    const float c = 0.5f * (axis == 0 ? l.x + h.x : (axis == 1 ? l.y + h.y : l.z + h.z));
+                    int b = (int)((c - cl[axis]) * scale);
+                    b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+                    bn[b]++;
+                    bl[b][0] = fminf(bl[b][0], l.x); bl[b][1] = fminf(bl[b][1], l.y); bl[b][2] = fminf(bl[b][2], l.z);
+                    bh[b][0] = fmaxf(bh[b][0], h.x); bh[b][1] = fmaxf(bh[b][1], h.y); bh[b][2] = fmaxf(bh[b][2], h.z);
+                }
+                float rightArea[BINS]; uint32_t rightCount[BINS];
+                float al[3] = {kInf, kInf, kInf}, ah[3] = {-kInf, -kInf, -kInf}; uint32_t m = 0;
+                for (int b = BINS - 1; b > 0; b--) {
+                    for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
+                    m += bn[b]; rightArea[b] = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]); rightCount[b] = m;
+                }
+                for (int k = 0; k < 3; k++) { al[k] = kInf; ah[k] = -kInf; }
+                m = 0;
+                for (int b = 0; b < BINS - 1; b++) {
+                    for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
+                    m += bn[b];
+                    if (m == 0 || rightCount[b + 1] == 0) { continue; }
+                    // clusters are not unit cost: weigh a side by its count (every cluster holds a similar number of primitives)
+                    const float cost = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]) * (float)m + rightArea[b + 1] * (float)rightCount[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+                }
+            }
+            uint32_t mid = first + t.y / 2; // identical centroids: split by index
+            if (bestAxis >= 0) {
+                const float scale = (float)BINS / (ch[bestAxis] - cl[bestAxis]);
+                uint32_t i = first, j = end;
+                while (i < j) {
+                    const float4 l = lo[i], h = hi[i];
+                    const float c = 0.5f * (bestAxis == 0 ? l.x + h.x : (bestAxis == 1 ? l.y + h.y : l.z + h.z));
+                    int b = (int)((c - cl[bestAxis]) * scale);
+                    b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
+                    if (b <= bestBin) { i++; }
+                    else { j--; lo[i] = lo[j]; hi[i] = hi[j]; lo[j] = l; hi[j] = h; }
+                }
+                if (i != first && i != end) { mid = i; }
+            }
+            tasks[sp - 1] = make_uint4(first, t.y, 1u, mid);
+            tasks[sp++] = make_uint4(mid, end - mid, 0u, 0u);
+            tasks[sp++] = make_uint4(first, mid - first, 0u, 0u); // left half first
+        }
     }
 };
 
@@ -589,8 +689,12 @@ BuildResult runBuild(Exec &exec, BuildArrays &a)
     // PLOC: the host only learns the cluster count of the next iteration (8 bytes back per iteration)
     uint32_t nClusters = n, nextNode = n;
     int buffer = 0;
-    while (nClusters > 1) {
-        exec.forEach(nClusters, NearestOp{a, buffer, nClusters});
+    uint32_t radius = PLOC_RADIUS;
+    if (const char *r = getenv("PTC_PLOC_RADIUS")) { radius = (uint32_t)std::max(1, atoi(r)); } // tuning hook (tools/compare_builders.py)
+    uint32_t topCount = PLOC_TOP_CLUSTERS;
+    if (const char *r = getenv("PTC_PLOC_TOP")) { topCount = (uint32_t)std::max(0, atoi(r)); }
+    while (nClusters > 1 && nClusters > topCount) {
+        exec.forEach(nClusters, NearestOp{a, buffer, nClusters, radius});
         exec.forEach(nClusters, MergeFlagOp{a});
         const uint64_t total = exec.scan(a, nClusters);
         const uint32_t created = (uint32_t)(total >> 32), survivors = (uint32_t)(total & 0xFFFFFFFFu);
@@ -598,6 +702,12 @@ BuildResult runBuild(Exec &exec, BuildArrays &a)
         exec.forEach(nClusters, MergeOp{a, buffer, nClusters, nextNode});
         nextNode += created; nClusters = survivors; buffer ^= 1;
         result.plocIterations++;
+    }
+    if (nClusters > 1) { // top of the tree: SAH over the remaining clusters
+        a.topTasks = exec.template alloc<uint4>(2 * (size_t)nClusters + 2);
+        a.topResults = exec.template alloc<uint32_t>((size_t)nClusters + 2);
+        exec.forEach(1u, TopDownOp{a, buffer, nClusters, nextNode});
+        nextNode += nClusters - 1u;
     }
     exec.sync();
     const uint32_t root = nextNode - 1; // n == 1: the only leaf

@@ -1577,7 +1577,7 @@ int ptc_bvh_selfcheck_builder(int builder, const float *P, uint32_t nv, const ui
                               float *tBvh, uint32_t *primBvh, float *tBrute, uint32_t *primBrute, uint64_t stats[6], double *sahCost)
 {
     if (builder != 0 && builder != 1) { return PTC_ERR_INVALID; }
-    if (!P || !I || !stats || (nRays && (!rays || !tBvh || !primBvh || !tBrute || !primBrute))) { return PTC_ERR_INVALID; }
+    if (!P || !I || !stats || (nRays && (!rays || !tBvh || !primBvh))) { return PTC_ERR_INVALID; }
     std::vector<float> positions4((size_t)nv * 4, 0.f);
     std::vector<uint32_t> prims4((size_t)nt * 4, 0u);
     for (uint32_t v = 0; v < nv; v++) { for (int a = 0; a < 3; a++) { positions4[4 * (size_t)v + a] = P[3 * (size_t)v + a]; } }
@@ -1597,6 +1597,7 @@ int ptc_bvh_selfcheck_builder(int builder, const float *P, uint32_t nv, const ui
         const float *o = rays[r].origin, *d = rays[r].direction;
         tBvh[r] = PTC_TFAR; primBvh[r] = PTC_MISS;
         traverseReference(bvh, o, d, PTC_TNEAR, PTC_TFAR, false, &tBvh[r], &primBvh[r], &counts);
+        if (!tBrute || !primBrute) { continue; } // statistics only
         float best = PTC_TFAR; uint32_t bestPrim = PTC_MISS; bool found = false;
         for (const LeafTriangle &tri : bvh.triangles) {
             const float4 a = make_float4(tri.v0[0], tri.v0[1], tri.v0[2], 0.f), b = make_float4(tri.e1[0], tri.e1[1], tri.e1[2], 0.f),

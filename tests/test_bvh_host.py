@@ -9,7 +9,7 @@ from golden_inputs import uniform_floats, unit_vectors
 from pathed_b200._binding import RAY_DTYPE, cuda_lib, rays_array
 
 
-def selfcheck(positions, indices, rays, builder=0):
+def selfcheck(positions, indices, rays, builder=0, brute_force=True):
     lib = cuda_lib()
     positions = np.ascontiguousarray(positions, np.float32); indices = np.ascontiguousarray(indices, np.uint32)
     n = len(rays)
@@ -18,8 +18,8 @@ def selfcheck(positions, indices, rays, builder=0):
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     cost = ctypes.c_double(0)
     rc = lib.ptc_bvh_selfcheck_builder(ctypes.c_int(builder), ptr(positions), ctypes.c_uint32(len(positions)), ptr(indices),
-                                       ctypes.c_uint32(len(indices)), ptr(rays), ctypes.c_uint32(n), ptr(t_bvh), ptr(p_bvh), ptr(t_bf),
-                                       ptr(p_bf), stats, ctypes.byref(cost))
+                                       ctypes.c_uint32(len(indices)), ptr(rays), ctypes.c_uint32(n), ptr(t_bvh), ptr(p_bvh),
+                                       ptr(t_bf) if brute_force else None, ptr(p_bf) if brute_force else None, stats, ctypes.byref(cost))
     assert rc == 0
     keys = ("nodes", "triangles", "slots", "max_depth", "inner_visits", "triangle_tests")
     st = dict(zip(keys, [int(x) for x in stats]))

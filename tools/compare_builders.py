@@ -39,10 +39,11 @@ def main():
     d1 = rng.normal(size=(n, 3)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
     for name, rays in (("primary", rays_array(np.tile(eye, (n, 1)).astype(np.float32), d0.astype(np.float32))),
                        ("incoherent", rays_array((surf + 1e-2 * d1).astype(np.float32), d1))):
-        for builder in (0, 1):
+        for builder in [int(b) for b in os.environ.get('BUILDERS', '0,1').split(',')]:
             t0 = time.time()
-            t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays, builder)
-            ok = np.array_equal(p_bvh, p_bf) and np.array_equal(t_bvh, t_bf)
+            brute = os.environ.get('BRUTE', '0') == '1'
+            t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays, builder, brute)
+            ok = (np.array_equal(p_bvh, p_bf) and np.array_equal(t_bvh, t_bf)) if brute else None
             print("%-10s builder %d: exact %s nodes %d slots/node %.2f depth %d sah %.2f inner/ray %.2f tris/ray %.2f bytes/ray %.0f (%.1f s)" % (
                 name, builder, ok, st["nodes"], st["slots"] / st["nodes"], st["max_depth"], st["sah_cost"], st["inner_visits"] / n,
                 st["triangle_tests"] / n, (80 * st["inner_visits"] + 48 * st["triangle_tests"]) / n, time.time() - t0))
