@@ -43,8 +43,15 @@ enum {
     PTC_MIRROR = 2,     /* src/mirror.cpp */
     PTC_GLASS = 3,      /* src/glass.cpp */
     PTC_MICROFACET = 4, /* src/microfacet.cpp */
-    PTC_PLASTIC = 5     /* src/plastic.cpp */
+    PTC_PLASTIC = 5,    /* src/plastic.cpp */
+    PTC_PASSTHROUGH = 6 /* src/passthrough.cpp: the container material of participating media (isContainer, isDelta) */
 };
+/* Job::integrator (src/job.cpp:66-75) */
+enum { PTC_INTEGRATOR_PATH_TRACER = 0 /* src/path_tracer.cpp */, PTC_INTEGRATOR_VOLUME_PATH_TRACER = 1 /* src/volume_path_tracer.cpp */ };
+#define PTC_NO_MEDIUM 0xFFFFFFFFu
+/* volume events kept per ray by the volumetric queries (the reference's std::vector<VolumeEvent>, include/volume_event.h);
+ * the reference only ever distinguishes 0, 1, 2 and "more" events (src/volume_helper.cpp:42-63, :80-120) */
+#define PTC_MAX_EVENTS 8
 enum { PTC_BECKMANN = 0 /* src/beckmann.cpp */, PTC_GGX = 1 /* src/ggx.cpp */ };
 enum { PTC_ALBEDO_CONSTANT = 0, PTC_ALBEDO_CHECKERBOARD = 1 /* src/checkerboard.cpp */, PTC_ALBEDO_TEXTURE = 2 /* src/texture.cpp */ };
 
@@ -150,6 +157,17 @@ int ptc_add_sphere(ptc_ctx *ctx, const float center_radius[4], uint32_t material
 int ptc_add_texture(ptc_ctx *ctx, const uint8_t *rgb, int width, int height, uint32_t *texture_id_out);
 /* replaces the Material subclass constructors */
 int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *material_id_out);
+/* replaces HomogeneousMedium::HomogeneousMedium (src/homogeneous_medium.cpp:7-11) as parseMedia builds it
+ * (src/scene_parser.cpp:202-229): sigma_t and sigma_s per channel (sigma_s defaults to 0 in the parser) */
+int ptc_add_medium(ptc_ctx *ctx, const float sigma_t[3], const float sigma_s[3], uint32_t *medium_id_out);
+/* replaces the `internal_medium` argument of Surface::Surface (include/surface.h:18-30) as the parsers pass it for every
+ * surface of an obj / ply / sphere model (src/scene_parser.cpp:324-343, :370-381, :503-514): all primitives of geometry
+ * `geom_id` enclose `medium_id`.  A Passthrough surface WITH a medium is skipped by the volumetric queries and by
+ * Scene::testOcclusion, and leaves a volume event instead (the occlusion filter, src/scene.cpp:42-84). */
+int ptc_set_internal_medium(ptc_ctx *ctx, uint32_t geom_id, uint32_t medium_id);
+/* replaces Job::integrator (src/job.cpp:66-75): which L() ptc_render / ptc_framebuffer_render / ptc_radiance_replay run.
+ * May be changed between renders. */
+int ptc_set_integrator(ptc_ctx *ctx, int integrator);
 /* replaces EnvironmentLight::EnvironmentLight (src/environment_light.cpp:14-54): RGBA fp32 lat-long
  * texels as tinyexr's LoadEXR returns them, scale, and both 4x4 row-major matrices of `mapToWorld` */
 int ptc_set_environment(ptc_ctx *ctx, const float *rgba, int width, int height, float scale,
@@ -197,6 +215,15 @@ int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t n_peer
 int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);        /* rtcIntersect1 */
 int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out);  /* Scene::testIntersect */
 int ptc_occluded(ptc_ctx *ctx, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded); /* Scene::testOcclusion */
+/* Scene::testVolumetricOcclusion (src/scene.cpp:383-424): occlusion with container surfaces filtered out; n_events[i] = number
+ * of distinct volume events on an unoccluded ray, event_t / event_medium[PTC_MAX_EVENTS * i ...] = the first PTC_MAX_EVENTS of
+ * them sorted by t (either may be NULL) */
+int ptc_occluded_volumetric(ptc_ctx *ctx, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded,
+                            uint32_t *n_events, float *event_t, uint32_t *event_medium);
+/* Scene::testVolumetricIntersect (src/scene.cpp:225-353): closest hit that is not a container-with-medium surface, plus the
+ * volume events in front of it */
+int ptc_intersect_volumetric(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *n_events, float *event_t,
+                             uint32_t *event_medium);
 /* device-resident variants used by the benchmark (rays/hits already in HBM) */
 int ptc_intersect_device(ptc_ctx *ctx, const ptc_ray *rays_device, uint32_t n, ptc_hit *hits_device, void *cuda_stream);
 int ptc_occluded_device(ptc_ctx *ctx, const ptc_ray *rays_device, const float *max_t_device, uint32_t n,
@@ -218,7 +245,7 @@ int ptc_light_sample(ptc_ctx *ctx, const float *ref_points, const float *xi, uin
 int ptc_light_pdf(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, float *pdf);
 /* Scene::environmentL(direction) */
 int ptc_environment_radiance(ptc_ctx *ctx, const float *directions, uint32_t n, float *rgb);
-/* body of SampleIntegrator::samplePixel + PathTracer::L for explicit primary rays, the random stream
+/* body of SampleIntegrator::samplePixel + PathTracer::L (or VolumePathTracer::L, see ptc_set_integrator) for explicit primary rays, the random stream
  * replayed sequentially from xi[i*stride ...] (test hook: same draws in the same order as the reference) */
 int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n,
                         int start_bounce, int last_bounce, float *rgb);

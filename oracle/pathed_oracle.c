@@ -121,7 +121,10 @@ typedef struct {
     uint32_t first_vertex, first_prim, n_prims;
     int is_sphere;
     float center_radius[4];
+    int medium; /* Surface::m_internalMedium of the geometry's surfaces, stored + 1 (0 = none, so memset-initialised geometries have none) */
 } geom_t;
+
+typedef struct { v3 sigma_t, sigma_s; } medium_t; /* HomogeneousMedium, include/homogeneous_medium.h */
 
 typedef struct {
     int kind; /* 0 triangle, 1 sphere, 2 environment */
@@ -156,6 +159,11 @@ struct orc_ctx {
     /* acceleration */
     int committed, brute_force, threads;
     bnode_t *nodes; uint32_t n_nodes; uint32_t *order;
+    /* participating media: media, per-prim / per-sphere filter table (medium of a Passthrough surface that encloses
+     * one, else -1; src/scene.cpp:42-84), integrator choice (src/job.cpp:66-75) */
+    medium_t *media; uint32_t n_media;
+    int *prim_event, *sphere_event; int has_filter;
+    int integrator;
     /* stats */
     uint64_t closest_rays, shadow_rays, samples;
 };
@@ -206,7 +214,7 @@ int orc_add_texture(orc_ctx *c, const uint8_t *rgb, int width, int height, uint3
 
 int orc_add_material(orc_ctx *c, const ptc_material_desc *d, uint32_t *id)
 {
-    if (!d || d->type < 0 || d->type > PTC_PLASTIC) { FAIL(c, PTC_ERR_INVALID, "Unimplemented material"); }
+    if (!d || d->type < 0 || d->type > PTC_PASSTHROUGH) { FAIL(c, PTC_ERR_INVALID, "Unimplemented material"); }
     if (d->albedo_kind == PTC_ALBEDO_TEXTURE && ((d->type != PTC_LAMBERTIAN && d->type != PTC_PLASTIC) || d->texture >= c->n_textures)) {
         FAIL(c, PTC_ERR_INVALID, "bad texture reference");
     }
@@ -222,6 +230,33 @@ int orc_add_material(orc_ctx *c, const ptc_material_desc *d, uint32_t *id)
     m->B = (0.45f * sigma2) / (sigma2 + 0.09f);
     if (id) { *id = c->n_materials; }
     c->n_materials++;
+    return PTC_OK;
+}
+
+int orc_add_medium(orc_ctx *c, const float sigma_t[3], const float sigma_s[3], uint32_t *id)
+{
+    if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
+    c->media = (medium_t *)realloc(c->media, (c->n_media + 1) * sizeof(medium_t));
+    c->media[c->n_media].sigma_t = V(sigma_t[0], sigma_t[1], sigma_t[2]);
+    c->media[c->n_media].sigma_s = sigma_s ? V(sigma_s[0], sigma_s[1], sigma_s[2]) : V(0, 0, 0);
+    if (id) { *id = c->n_media; }
+    c->n_media++;
+    return PTC_OK;
+}
+
+int orc_set_internal_medium(orc_ctx *c, uint32_t geom, uint32_t medium)
+{
+    if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
+    if (geom >= c->n_geoms) { FAIL(c, PTC_ERR_INVALID, "geometry id out of range"); }
+    if (medium != PTC_NO_MEDIUM && medium >= c->n_media) { FAIL(c, PTC_ERR_INVALID, "medium id out of range"); }
+    c->geoms[geom].medium = medium == PTC_NO_MEDIUM ? 0 : (int)medium + 1;
+    return PTC_OK;
+}
+
+int orc_set_integrator(orc_ctx *c, int integrator)
+{
+    if (integrator != PTC_INTEGRATOR_PATH_TRACER && integrator != PTC_INTEGRATOR_VOLUME_PATH_TRACER) { FAIL(c, PTC_ERR_INVALID, "Unimplemented integrator"); }
+    c->integrator = integrator;
     return PTC_OK;
 }
 
@@ -506,11 +541,10 @@ static inline v3 to_world(const isect_t *i, v3 l) { return V(i->tx.x * l.x + i->
 static inline v3 to_local(const isect_t *i, v3 w) { return V(i->tx.x * w.x + i->tx.y * w.y + i->tx.z * w.z, i->ns.x * w.x + i->ns.y * w.y + i->ns.z * w.z, i->tz.x * w.x + i->tz.y * w.y + i->tz.z * w.z); }
 
 /* Scene::testIntersect, src/scene.cpp:91-223 */
-static isect_t test_intersect(orc_ctx *c, v3 O, v3 D)
+static isect_t make_isect(const orc_ctx *c, v3 O, v3 D, int found, rawhit_t h)
 {
     isect_t r; memset(&r, 0, sizeof(r));
-    rawhit_t h;
-    if (!trace(c, O, D, TNEAR, TFAR, 0, &h)) { r.t = 3.402823466e+38f; return r; }
+    if (!found) { r.t = 3.402823466e+38f; return r; }
     v3 ns = V(0.f, 0.f, 0.f);
     const v3 ng = vnorm(h.ng);
     if (!h.sphere) {
@@ -532,11 +566,75 @@ static isect_t test_intersect(orc_ctx *c, v3 O, v3 D)
     make_frame(r.ns, r.wo, &r.tx, &r.tz);
     return r;
 }
+static isect_t test_intersect(orc_ctx *c, v3 O, v3 D)
+{
+    rawhit_t h; memset(&h, 0, sizeof(h));
+    const int found = trace(c, O, D, TNEAR, TFAR, 0, &h);
+    return make_isect(c, O, D, found, h);
+}
 
-/* Scene::testOcclusion, src/scene.cpp:355-381 */
+/* ---- occlusion filter (src/scene.cpp:42-84, registered for both query kinds by src/rtc_manager.cpp:85-92) ---- */
+typedef struct { uint32_t count; float t[PTC_MAX_EVENTS]; int medium[PTC_MAX_EVENTS]; } events_t; /* std::vector<VolumeEvent> */
+
+static void event_add(events_t *ev, float t, int medium) /* src/scene.cpp:66-81: an event with the same t is not added twice */
+{
+    const uint32_t stored = ev->count < PTC_MAX_EVENTS ? ev->count : PTC_MAX_EVENTS;
+    for (uint32_t i = 0; i < stored; i++) { if (ev->t[i] == t) { return; } }
+    if (ev->count < PTC_MAX_EVENTS) { ev->t[ev->count] = t; ev->medium[ev->count] = medium; }
+    ev->count++;
+}
+static void events_sort(events_t *ev) /* std::sort by t, src/scene.cpp:337-343, :412-418 */
+{
+    const uint32_t stored = ev->count < PTC_MAX_EVENTS ? ev->count : PTC_MAX_EVENTS;
+    for (uint32_t i = 1; i < stored; i++) {
+        const float t = ev->t[i]; const int m = ev->medium[i];
+        uint32_t j = i;
+        while (j > 0 && ev->t[j - 1] > t) { ev->t[j] = ev->t[j - 1]; ev->medium[j] = ev->medium[j - 1]; j--; }
+        ev->t[j] = t; ev->medium[j] = m;
+    }
+}
+
+/* rtcIntersect1 / rtcOccluded1 with shouldIntersectPassthroughs = false: a Passthrough surface that encloses a medium is
+ * rejected by the filter and leaves an event.  Brute force over every primitive (the scenes with media are small), triangles
+ * first, then spheres -- Embree keeps one acceleration structure per geometry type and visits them in that order.
+ * Closest hit: the filter sees every candidate nearer than the closest accepted hit so far, so which containers BEHIND the
+ * final hit leave an event depends on Embree's traversal order; this restatement keeps the order-independent part, the
+ * containers in front of the final triangle hit.  Any hit: every container in the interval when unoccluded. */
+static int trace_filtered(const orc_ctx *c, v3 O, v3 D, float tnear, float tfar, int any, rawhit_t *out, events_t *ev)
+{
+    int found = 0;
+    float best = tfar;
+    rawhit_t h; memset(&h, 0, sizeof(h));
+    ev->count = 0;
+    events_t all; all.count = 0;
+    for (uint32_t p = 0; p < c->n_prims && !(any && found); p++) {
+        float t, u, v; v3 ng;
+        if (!tri_test(c, p, O, D, tnear, any ? tfar : best, &t, &u, &v, &ng)) { continue; }
+        if (c->prim_event && c->prim_event[p] >= 0) { event_add(any ? ev : &all, t, c->prim_event[p]); continue; }
+        best = t; h.t = t; h.u = u; h.v = v; h.prim = p; h.sphere = 0; h.ng = ng; found = 1;
+    }
+    if (!any) { /* a brute-force scan meets containers before it knows the final hit: keep those in front of it */
+        const uint32_t stored = all.count < PTC_MAX_EVENTS ? all.count : PTC_MAX_EVENTS;
+        for (uint32_t i = 0; i < stored; i++) { if (all.t[i] <= best) { event_add(ev, all.t[i], all.medium[i]); } }
+        if (all.count > PTC_MAX_EVENTS) { ev->count = all.count; }
+    }
+    for (uint32_t s = 0; s < c->n_spheres && !(any && found); s++) {
+        float t; v3 ng;
+        if (!sphere_test(c->geoms[c->sphere_geoms[s]].center_radius, O, D, tnear, best, &t, &ng)) { continue; }
+        /* a rejected near side does not make Embree try the far side (sphere_intersector.h:91-92) */
+        if (c->sphere_event && c->sphere_event[s] >= 0) { event_add(ev, t, c->sphere_event[s]); continue; }
+        best = t; h.t = t; h.u = 0.f; h.v = 0.f; h.prim = s; h.sphere = 1; h.ng = ng; found = 1;
+    }
+    events_sort(ev);
+    if (found) { *out = h; }
+    return found;
+}
+
+/* Scene::testOcclusion, src/scene.cpp:355-381 (shouldIntersectPassthroughs = false, :369-370) */
 static int test_occlusion(orc_ctx *c, v3 O, v3 D, float maxT)
 {
     rawhit_t h;
+    if (c->has_filter) { events_t ev; return trace_filtered(c, O, D, TNEAR, maxT - 1e-3f, 1, &h, &ev); }
     return trace(c, O, D, TNEAR, maxT - 1e-3f, 1, &h);
 }
 
@@ -754,7 +852,7 @@ static v3 bsdf_f(const material_t *m, const isect_t *i, v3 wiW, float *pdf)
 
 typedef struct { v3 wi; float pdf; v3 thr; int delta; } bsdf_sample_t;
 
-static int is_delta(const material_t *m) { return m->d.type == PTC_MIRROR || m->d.type == PTC_GLASS; }
+static int is_delta(const material_t *m) { return m->d.type == PTC_MIRROR || m->d.type == PTC_GLASS || m->d.type == PTC_PASSTHROUGH; }
 
 static bsdf_sample_t lambert_sample(const material_t *m, const isect_t *i, rng_t *r) /* src/lambertian.cpp:43-58 */
 {
@@ -830,6 +928,12 @@ static bsdf_sample_t bsdf_sample(const material_t *m, const isect_t *i, rng_t *r
             float pl; const v3 fl = lambert_f(m, i, s.wi, &pl);
             s.pdf = (s.pdf + pl) / 2.f; s.thr = vadd(s.thr, fl);
         }
+        return s;
+    }
+    case PTC_PASSTHROUGH: { /* src/passthrough.cpp:26-40; Color(1.f) / cosTheta multiplies by 1 / cosTheta (src/color.cpp:127-134) */
+        const float cosTheta = fabsf(vdot(vneg(i->ns), vneg(i->wo)));
+        const float t = 1.f * (1.f / cosTheta);
+        s.wi = vneg(i->wo); s.pdf = 1.f; s.thr = V(t, t, t); s.delta = 1;
         return s;
     }
     }
@@ -1057,10 +1161,198 @@ static v3 direct_bsdf(orc_ctx *c, const isect_t *i, const bsdf_sample_t *bs, con
     return V(out.x / bs->pdf, out.y / bs->pdf, out.z / bs->pdf);
 }
 
+/* ------------------------------------------------------------------------------------------ participating media (N3) */
+/* Scene::testVolumetricIntersect, src/scene.cpp:225-353 */
+static isect_t test_volumetric_intersect(orc_ctx *c, v3 O, v3 D, events_t *ev)
+{
+    rawhit_t h; memset(&h, 0, sizeof(h));
+    const int found = trace_filtered(c, O, D, TNEAR, TFAR, 0, &h, ev);
+    return make_isect(c, O, D, found, h);
+}
+/* Scene::testVolumetricOcclusion, src/scene.cpp:383-424 */
+static int test_volumetric_occlusion(orc_ctx *c, v3 O, v3 D, float maxT, events_t *ev)
+{
+    rawhit_t h;
+    return trace_filtered(c, O, D, TNEAR, maxT - 1e-3f, 1, &h, ev);
+}
+/* Surface::getInternalMedium of the surface an intersection lies on (-1 none) */
+static int internal_medium(const orc_ctx *c, const isect_t *i)
+{
+    const uint32_t geom = i->sphere ? c->sphere_geoms[i->prim] : c->prim_geom[i->prim];
+    return c->geoms[geom].medium - 1;
+}
+/* HomogeneousMedium::transmittance, src/homogeneous_medium.cpp:13-17 */
+static v3 medium_transmittance(const orc_ctx *c, int medium, v3 a, v3 b)
+{
+    const v3 st = c->media[medium].sigma_t;
+    const float d = vlen(vsub(b, a));
+    return V(expf(-st.x * d), expf(-st.y * d), expf(-st.z * d));
+}
+static inline v3 ray_at(v3 O, v3 D, float t) { return vadd(O, vmul(D, t)); }
+/* VolumeHelper::rayTransmission, src/volume_helper.cpp:72-123 */
+static v3 ray_transmission(const orc_ctx *c, v3 O, v3 D, const events_t *ev, int current)
+{
+    v3 tr = V(1.f, 1.f, 1.f);
+    if (ev->count == 0) { return tr; }
+    if (current >= 0) {
+        if (ev->count == 1) { tr = vmulv(tr, medium_transmittance(c, current, O, ray_at(O, D, ev->t[0]))); }
+        else if (ev->count == 2) { tr = vmulv(tr, medium_transmittance(c, current, ray_at(O, D, ev->t[0]), ray_at(O, D, ev->t[1]))); }
+    } else {
+        const int m = ev->medium[0];
+        if (ev->count == 2) { tr = vmulv(tr, medium_transmittance(c, m, ray_at(O, D, ev->t[0]), ray_at(O, D, ev->t[1]))); }
+        else if (ev->count == 1) { tr = vmulv(tr, medium_transmittance(c, m, O, ray_at(O, D, ev->t[0]))); }
+    }
+    return tr; /* more than two events: asserts are compiled out (F8), nothing is applied */
+}
+/* VolumeHelper::directSampleLights, src/volume_helper.cpp:12-70 */
+static v3 volume_direct_lights(orc_ctx *c, int medium, v3 point, rng_t *r, counts_t *n)
+{
+    const light_sample_t ls = sample_direct_lights(c, point, r);
+    const v3 sd = vsub(ls.s.point, point);
+    const v3 wi = vnorm(sd);
+    if (vdot(ls.s.normal, wi) >= 0.f) { return V(0, 0, 0); }
+    const float dist = vlen(sd);
+    events_t ev;
+    n->shadow++;
+    if (test_volumetric_occlusion(c, point, wi, dist, &ev)) { return V(0, 0, 0); }
+    const float pdf = solid_angle_pdf(&ls.s, point);
+    const v3 lwo = vneg(vnorm(sd));
+    v3 tr = V(0, 0, 0);
+    if (ev.count == 1) { tr = medium_transmittance(c, medium, point, ray_at(point, wi, ev.t[0])); }
+    else if (ev.count == 2) { tr = medium_transmittance(c, medium, ray_at(point, wi, ev.t[0]), ray_at(point, wi, ev.t[1])); }
+    const v3 Le = ls.light->kind == 2 ? env_radiance(c, vneg(lwo)) : ls.light->emit;
+    v3 out = vmul(vmulv(Le, tr), 1.f);
+    const float fourPi = (float)(4.f * M_PI);
+    out = V(out.x / fourPi, out.y / fourPi, out.z / fourPi);
+    return V(out.x / pdf, out.y / pdf, out.z / pdf);
+}
+/* VolumePathTracer::scatter -> HomogeneousMedium::integrate, src/volume_path_tracer.cpp:112-131, src/homogeneous_medium.cpp:36-66 */
+static v3 medium_scatter(orc_ctx *c, int medium, v3 entry, v3 exit_, rng_t *r, counts_t *n)
+{
+    if (medium < 0) { return V(0, 0, 0); }
+    const float sigmaT = c->media[medium].sigma_t.x;
+    const v3 travel = vsub(exit_, entry);
+    const float distance = vlen(travel);
+    const float xi = rng_next(r);
+    const float sampleT = -logf(1 - xi) / sigmaT;
+    if (sampleT >= distance) { return V(0, 0, 0); }
+    const v3 samplePoint = ray_at(entry, vnorm(travel), sampleT);
+    return volume_direct_lights(c, medium, samplePoint, r, n);
+}
+/* DirectLightingHelper::Ld, src/direct_lighting_helper.cpp:37-187 */
+static v3 volume_ld(orc_ctx *c, const isect_t *i, int medium, const bsdf_sample_t *bs, rng_t *r, counts_t *n)
+{
+    const material_t *m = &c->materials[i->material];
+    if (m->d.type == PTC_PASSTHROUGH) { return V(0, 0, 0); }
+    if (!black(V(m->d.emit[0], m->d.emit[1], m->d.emit[2]))) { return V(0, 0, 0); }
+    v3 result = V(0, 0, 0);
+    if (!bs->delta) { /* directSampleLights, :75-137 */
+        const light_sample_t ls = sample_direct_lights(c, i->point, r);
+        const v3 ld = vsub(ls.s.point, i->point);
+        const v3 wi = vnorm(ld);
+        if (!(vdot(ls.s.normal, wi) >= 0.f)) {
+            const float dist = vlen(ld);
+            events_t ev;
+            n->shadow++;
+            if (!test_volumetric_occlusion(c, i->point, wi, dist, &ev)) {
+                const v3 tr = ray_transmission(c, i->point, wi, &ev, medium);
+                const float pdf = solid_angle_pdf(&ls.s, i->point);
+                float brdfPDF;
+                const v3 f = bsdf_f(m, i, wi, &brdfPDF);
+                const float w = (1 * pdf) / (1 * pdf + 1 * brdfPDF);
+                const v3 lwo = vneg(vnorm(ld));
+                const v3 Le = ls.light->kind == 2 ? env_radiance(c, vneg(lwo)) : ls.light->emit;
+                v3 out = vmulv(Le, tr);
+                out = vmul(out, w);
+                out = vmulv(out, f);
+                out = vmul(out, fabsf(vdot(i->ns, wi)));
+                result = vadd(result, V(out.x / pdf, out.y / pdf, out.z / pdf));
+            }
+        }
+    }
+    { /* directSampleBSDF, :139-187: no front-side test, no transmittance */
+        events_t ev;
+        n->closest++;
+        const isect_t bi = test_volumetric_intersect(c, i->point, bs->wi, &ev);
+        v3 Le; float lightPDF; int contributes = 1;
+        if (bi.hit) {
+            const material_t *bm = &c->materials[bi.material];
+            Le = V(bm->d.emit[0], bm->d.emit[1], bm->d.emit[2]);
+            if (black(Le)) { contributes = 0; } else { lightPDF = lights_pdf(c, i->point, &bi); }
+        } else {
+            Le = env_radiance(c, bs->wi);
+            if (black(Le)) { contributes = 0; } else { lightPDF = env_pdf(c, bs->wi) / (float)c->n_lights; }
+        }
+        if (contributes) {
+            const float w = bs->delta ? 1.f : (1 * bs->pdf) / (1 * bs->pdf + 1 * lightPDF);
+            v3 out = vmul(Le, w);
+            out = vmulv(out, bs->thr);
+            out = vmul(out, fabsf(vdot(i->ns, bs->wi)));
+            result = vadd(result, V(out.x / bs->pdf, out.y / bs->pdf, out.z / bs->pdf));
+        }
+    }
+    return result;
+}
+/* the container branch of SampleIntegrator::samplePixel, src/sample_integrator.cpp:35-51 */
+static v3 camera_container_term(orc_ctx *c, v3 O, v3 D, counts_t *n)
+{
+    events_t ev;
+    n->closest++;
+    const isect_t vi = test_volumetric_intersect(c, O, D, &ev);
+    const v3 tr = ray_transmission(c, O, D, &ev, -1);
+    if (vi.hit) { const material_t *vm = &c->materials[vi.material]; return vmulv(V(vm->d.emit[0], vm->d.emit[1], vm->d.emit[2]), tr); }
+    return vmulv(env_radiance(c, D), tr);
+}
+/* SampleIntegrator::samplePixel body + VolumePathTracer::L, src/volume_path_tracer.cpp:14-95 */
+static v3 volume_radiance(orc_ctx *c, v3 O, v3 D, rng_t *r, int start, int last, counts_t *n)
+{
+    v3 color = V(0, 0, 0);
+    n->closest++;
+    isect_t lastI = test_intersect(c, O, D);
+    if (!lastI.hit) { return env_radiance(c, D); }
+    if (check_counts(start, last, 0)) {
+        const material_t *m = &c->materials[lastI.material];
+        const v3 emit = V(m->d.emit[0], m->d.emit[1], m->d.emit[2]);
+        if (!black(emit) && !(vdot(lastI.n, lastI.wo) < 0.f)) { color = vadd(color, emit); }
+        if (m->d.type == PTC_PASSTHROUGH) { color = vadd(color, camera_container_term(c, O, D, n)); }
+    }
+    int medium = -1;
+    rng_begin_vertex(r, 1);
+    bsdf_sample_t bs = bsdf_sample(&c->materials[lastI.material], &lastI, r);
+    v3 result = V(0, 0, 0);
+    if (check_counts(start, last, 1)) { result = volume_ld(c, &lastI, medium, &bs, r, n); }
+    v3 modulation = V(1.f, 1.f, 1.f);
+    for (int bounce = 2; !check_done(last, bounce); bounce++) {
+        if (vdot(lastI.wo, bs.wi) < 0.f) { /* refraction: the medium changes, :42-50 */
+            if (vdot(lastI.n, bs.wi) < 0.f) { medium = internal_medium(c, &lastI); }
+            else { medium = -1; }
+        }
+        n->closest++;
+        const isect_t bi = test_intersect(c, lastI.point, bs.wi);
+        if (!bi.hit) { break; }
+        const float invPDF = 1.f / bs.pdf;
+        const float cosT = fabsf(vdot(lastI.ns, bs.wi));
+        modulation = vmulv(modulation, vmul(vmul(bs.thr, cosT), invPDF));
+        rng_begin_vertex(r, (uint32_t)bounce);
+        const v3 Ls = medium_scatter(c, medium, lastI.point, bi.point, r, n);
+        result = vadd(result, vmulv(Ls, modulation));
+        if (medium >= 0) { modulation = vmulv(modulation, medium_transmittance(c, medium, lastI.point, bi.point)); }
+        if (black(modulation)) { break; }
+        bs = bsdf_sample(&c->materials[bi.material], &bi, r);
+        lastI = bi;
+        if (check_counts(start, last, bounce)) {
+            const v3 Ld = volume_ld(c, &bi, medium, &bs, r, n);
+            result = vadd(result, vmulv(Ld, modulation));
+        }
+    }
+    return vadd(color, result);
+}
+
 /* SampleIntegrator::samplePixel body (src/sample_integrator.cpp:18-59) + PathTracer::L (src/path_tracer.cpp:19-77).
  * The MIS probe ray (path_tracer.cpp:175) and the continuation ray (:44) are the same ray; traced once (Q6). */
 static v3 radiance(orc_ctx *c, v3 O, v3 D, rng_t *r, int start, int last, counts_t *n)
 {
+    if (c->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { return volume_radiance(c, O, D, r, start, last, n); }
     v3 color = V(0, 0, 0);
     n->closest++;
     isect_t isect = test_intersect(c, O, D);
@@ -1069,6 +1361,7 @@ static v3 radiance(orc_ctx *c, v3 O, v3 D, rng_t *r, int start, int last, counts
         const material_t *m = &c->materials[isect.material];
         const v3 emit = V(m->d.emit[0], m->d.emit[1], m->d.emit[2]);
         if (!black(emit) && !(vdot(isect.n, isect.wo) < 0.f)) { color = vadd(color, emit); }
+        if (c->has_filter && m->d.type == PTC_PASSTHROUGH) { color = vadd(color, camera_container_term(c, O, D, n)); }
     }
     rng_begin_vertex(r, 1);
     bsdf_sample_t bs = bsdf_sample(&c->materials[isect.material], &isect, r);
@@ -1172,6 +1465,22 @@ int orc_commit(orc_ctx *c)
         }
     }
     if (c->has_env) { light_t l; memset(&l, 0, sizeof(l)); l.kind = 2; c->lights[c->n_lights++] = l; }
+    /* the occlusion filter's table: Passthrough surfaces that enclose a medium (src/scene.cpp:59-63) */
+    c->has_filter = 0;
+    if (c->n_media) {
+        c->prim_event = (int *)malloc(((size_t)c->n_prims + 1) * sizeof(int));
+        c->sphere_event = (int *)malloc(((size_t)c->n_spheres + 1) * sizeof(int));
+        for (uint32_t p = 0; p < c->n_prims; p++) {
+            const int medium = c->geoms[c->prim_geom[p]].medium - 1;
+            c->prim_event[p] = (medium >= 0 && c->materials[c->prim_material[p]].d.type == PTC_PASSTHROUGH) ? medium : -1;
+            if (c->prim_event[p] >= 0) { c->has_filter = 1; }
+        }
+        for (uint32_t s = 0; s < c->n_spheres; s++) {
+            const int medium = c->geoms[c->sphere_geoms[s]].medium - 1;
+            c->sphere_event[s] = (medium >= 0 && c->materials[c->sphere_material[s]].d.type == PTC_PASSTHROUGH) ? medium : -1;
+            if (c->sphere_event[s] >= 0) { c->has_filter = 1; }
+        }
+    }
     if (c->n_prims) {
         c->order = (uint32_t *)malloc((size_t)c->n_prims * sizeof(uint32_t));
         for (uint32_t p = 0; p < c->n_prims; p++) { c->order[p] = p; }
@@ -1235,12 +1544,50 @@ int orc_intersect_full(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_isect *o
     return PTC_OK;
 }
 
+static void export_events(const events_t *ev, uint32_t i, uint32_t *n_events, float *event_t, uint32_t *event_medium)
+{
+    if (n_events) { n_events[i] = ev->count; }
+    for (uint32_t e = 0; e < PTC_MAX_EVENTS; e++) {
+        const int have = e < ev->count;
+        if (event_t) { event_t[(size_t)i * PTC_MAX_EVENTS + e] = have ? ev->t[e] : 0.f; }
+        if (event_medium) { event_medium[(size_t)i * PTC_MAX_EVENTS + e] = have ? (uint32_t)ev->medium[e] : PTC_NO_MEDIUM; }
+    }
+}
+
+int orc_intersect_volumetric(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *n_events, float *event_t, uint32_t *event_medium)
+{
+    NEED_COMMIT(c);
+    #pragma omp parallel for schedule(dynamic, 256) num_threads(c->threads)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        events_t ev;
+        const isect_t s = test_volumetric_intersect(c, V(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), V(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]), &ev);
+        export_isect(&s, &out[i]);
+        export_events(&ev, (uint32_t)i, n_events, event_t, event_medium);
+    }
+    return PTC_OK;
+}
+
 int orc_occluded(orc_ctx *c, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded)
 {
     NEED_COMMIT(c);
     #pragma omp parallel for schedule(dynamic, 256) num_threads(c->threads)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         occluded[i] = (uint8_t)test_occlusion(c, V(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), V(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]), max_t[i]);
+    }
+    return PTC_OK;
+}
+
+int orc_occluded_volumetric(orc_ctx *c, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded, uint32_t *n_events,
+                            float *event_t, uint32_t *event_medium)
+{
+    NEED_COMMIT(c);
+    #pragma omp parallel for schedule(dynamic, 256) num_threads(c->threads)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        events_t ev;
+        const int occ = test_volumetric_occlusion(c, V(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), V(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]), max_t[i], &ev);
+        if (occ) { ev.count = 0; }
+        occluded[i] = (uint8_t)occ;
+        export_events(&ev, (uint32_t)i, n_events, event_t, event_medium);
     }
     return PTC_OK;
 }

@@ -33,6 +33,8 @@
 #include "scene_parser.h"
 #include "sphere.h"
 #include "triangle.h"
+#include "volume_helper.h"
+#include "volume_path_tracer.h"
 
 #include <embree3/rtcore.h>
 #define STB_IMAGE_WRITE_IMPLEMENTATION
@@ -58,6 +60,8 @@ RTCScene g_rtcScene;
 
 static Scene *s_scene = nullptr;
 static std::shared_ptr<PathTracer> s_pathTracer;
+static std::shared_ptr<VolumePathTracer> s_volumeTracer;
+static int s_integrator = 0; // 0 PathTracer, 1 VolumePathTracer (ref_set_integrator)
 
 static inline Vector3 vec(const float *p) { return Vector3(p[0], p[1], p[2]); }
 static inline Point3 pnt(const float *p) { return Point3(p[0], p[1], p[2]); }
@@ -100,8 +104,12 @@ int ref_init(const char *root, const char *sceneJson, int width, int height, int
     if (!sceneFile) { return -4; }
     s_scene = new Scene(parseScene(sceneFile));
     s_pathTracer = std::make_shared<PathTracer>(g_job->bounceController());
+    s_volumeTracer = std::make_shared<VolumePathTracer>(g_job->bounceController());
     return 0;
 }
+
+// which L() ref_radiance calls: Job::integrator (src/job.cpp:66-75)
+void ref_set_integrator(int integrator) { s_integrator = integrator; }
 
 int ref_num_lights() { return s_scene ? (int)s_scene->lights().size() : -1; }
 
@@ -187,6 +195,38 @@ void ref_occluded(int n, const float *rays, const float *maxT, unsigned char *oc
     for (int i = 0; i < n; i++) {
         const Ray ray(pnt(rays + 6 * i), vec(rays + 6 * i + 3));
         occluded[i] = s_scene->testOcclusion(ray, maxT[i]) ? 1 : 0;
+    }
+}
+
+// Scene::testVolumetricOcclusion (src/scene.cpp:383-424): events of unoccluded rays, up to `maxEvents` stored per ray
+void ref_volumetric_occluded(int n, const float *rays, const float *maxT, unsigned char *occluded, int *nEvents, float *eventT, int maxEvents)
+{
+    #pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        const Ray ray(pnt(rays + 6 * i), vec(rays + 6 * i + 3));
+        const OcclusionResult result = s_scene->testVolumetricOcclusion(ray, maxT[i]);
+        occluded[i] = result.isOccluded ? 1 : 0;
+        nEvents[i] = result.isOccluded ? 0 : (int)result.volumeEvents.size();
+        for (int e = 0; e < maxEvents; e++) {
+            eventT[(size_t)i * maxEvents + e] = (!result.isOccluded && e < (int)result.volumeEvents.size()) ? result.volumeEvents[e].t : 0.f;
+        }
+    }
+}
+
+// Scene::testVolumetricIntersect (src/scene.cpp:225-353)
+void ref_volumetric_intersect(int n, const float *rays, int *hit, float *t, float *point, float *emit, int *nEvents, float *eventT, int maxEvents)
+{
+    #pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        const Ray ray(pnt(rays + 6 * i), vec(rays + 6 * i + 3));
+        const IntersectionResult result = s_scene->testVolumetricIntersect(ray);
+        const Intersection &isect = result.intersection;
+        hit[i] = isect.hit ? 1 : 0;
+        t[i] = isect.t;
+        put(point + 3 * i, isect.point);
+        if (isect.hit) { put(emit + 3 * i, isect.material->emit()); } else { emit[3 * i] = emit[3 * i + 1] = emit[3 * i + 2] = 0.f; }
+        nEvents[i] = (int)result.volumeEvents.size();
+        for (int e = 0; e < maxEvents; e++) { eventT[(size_t)i * maxEvents + e] = e < (int)result.volumeEvents.size() ? result.volumeEvents[e].t : 0.f; }
     }
 }
 
@@ -427,8 +467,8 @@ void ref_scene_environment(int n, const float *dir, float *rgb)
 
 // ------------------------------------------------------------------ whole paths
 // One radiance sample per primary ray, with the random stream replayed from xi[i*stride ...]:
-// the body of SampleIntegrator::samplePixel (src/sample_integrator.cpp:18-59, container
-// branch excluded: no config material is a container) followed by PathTracer::L.
+// the body of SampleIntegrator::samplePixel (src/sample_integrator.cpp:18-59, container branch included)
+// followed by PathTracer::L or VolumePathTracer::L (ref_set_integrator).
 void ref_radiance(int n, const float *rays, const float *xi, int stride, float *rgb, int *consumed)
 {
     #pragma omp parallel for
@@ -445,8 +485,16 @@ void ref_radiance(int n, const float *rays, const float *xi, int stride, float *
                 if (!emit.isBlack() && !IntersectionHelper::checkBacksideIntersection(isect)) {
                     color += emit;
                 }
+                if (isect.material->isContainer()) { // src/sample_integrator.cpp:35-51
+                    const IntersectionResult volumetricResult = s_scene->testVolumetricIntersect(ray);
+                    const Intersection &volumetricIntersection = volumetricResult.intersection;
+                    const Color transmittance = VolumeHelper::rayTransmission(ray, volumetricResult.volumeEvents, nullptr);
+                    if (volumetricIntersection.hit) { color += volumetricIntersection.material->emit() * transmittance; }
+                    else { color += s_scene->environmentL(ray.direction()) * transmittance; }
+                }
             }
-            color += s_pathTracer->L(isect, *s_scene, random, 0, sample);
+            if (s_integrator == 1) { color += s_volumeTracer->L(isect, *s_scene, random, 0, sample); }
+            else { color += s_pathTracer->L(isect, *s_scene, random, 0, sample); }
         } else {
             color += s_scene->environmentL(ray.direction());
         }

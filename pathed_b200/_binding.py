@@ -15,7 +15,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 
 PTC_INVALID_ID = 0xFFFFFFFF
-LAMBERTIAN, OREN_NAYAR, MIRROR, GLASS, MICROFACET, PLASTIC = range(6)
+LAMBERTIAN, OREN_NAYAR, MIRROR, GLASS, MICROFACET, PLASTIC, PASSTHROUGH = range(7)
+PATH_TRACER, VOLUME_PATH_TRACER = 0, 1
+NO_MEDIUM = 0xFFFFFFFF
+MAX_EVENTS = 8
 BECKMANN, GGX = 0, 1
 
 
@@ -52,7 +55,8 @@ assert RAY_DTYPE.itemsize == 24 and HIT_DTYPE.itemsize == 32 and ISECT_DTYPE.ite
 class SceneSink(ctypes.Structure):
     _fields_ = [("ctx", ctypes.c_void_p), ("add_material", ctypes.c_void_p), ("add_triangle_mesh", ctypes.c_void_p),
                 ("add_sphere", ctypes.c_void_p), ("set_environment", ctypes.c_void_p), ("set_camera", ctypes.c_void_p),
-                ("commit", ctypes.c_void_p), ("add_texture", ctypes.c_void_p)]
+                ("commit", ctypes.c_void_p), ("add_texture", ctypes.c_void_p), ("add_medium", ctypes.c_void_p),
+                ("set_internal_medium", ctypes.c_void_p)]
 
 
 class PathedError(RuntimeError):
@@ -112,7 +116,8 @@ class Api:
     def sink(self):
         addr = lambda name: ctypes.cast(self._fn(name), ctypes.c_void_p).value
         return SceneSink(self.ctx.value, addr("add_material"), addr("add_triangle_mesh"), addr("add_sphere"),
-                         addr("set_environment"), addr("set_camera"), addr("commit"), addr("add_texture"))
+                         addr("set_environment"), addr("set_camera"), addr("commit"), addr("add_texture"), addr("add_medium"),
+                         addr("set_internal_medium"))
 
     # ---- scene description
     def add_texture(self, rgb):
@@ -127,6 +132,18 @@ class Api:
         out = ctypes.c_uint32()
         self._call("add_material", ctypes.byref(desc), ctypes.byref(out))
         return out.value
+
+    def add_medium(self, sigma_t, sigma_s=(0.0, 0.0, 0.0)):
+        st = (ctypes.c_float * 3)(*[float(x) for x in sigma_t]); ss = (ctypes.c_float * 3)(*[float(x) for x in sigma_s])
+        out = ctypes.c_uint32()
+        self._call("add_medium", st, ss, ctypes.byref(out))
+        return out.value
+
+    def set_internal_medium(self, geom_id, medium_id):
+        self._call("set_internal_medium", ctypes.c_uint32(geom_id), ctypes.c_uint32(medium_id))
+
+    def set_integrator(self, integrator):
+        self._call("set_integrator", ctypes.c_int(integrator))
 
     def add_triangle_mesh(self, positions, normals, uvs, indices, material_of_tri):
         positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
@@ -208,6 +225,23 @@ class Api:
         out = np.zeros(len(rays), np.uint8)
         self._call("occluded", _ptr(rays), _ptr(max_t), ctypes.c_uint32(len(rays)), _ptr(out))
         return out
+
+    def occluded_volumetric(self, rays, max_t):
+        """Scene::testVolumetricOcclusion: (occluded, n_events, event_t[n, MAX_EVENTS], event_medium[n, MAX_EVENTS])"""
+        max_t = np.ascontiguousarray(max_t, np.float32)
+        n = len(rays)
+        occ = np.zeros(n, np.uint8); ne = np.zeros(n, np.uint32)
+        et = np.zeros((n, MAX_EVENTS), np.float32); em = np.zeros((n, MAX_EVENTS), np.uint32)
+        self._call("occluded_volumetric", _ptr(rays), _ptr(max_t), ctypes.c_uint32(n), _ptr(occ), _ptr(ne), _ptr(et), _ptr(em))
+        return occ, ne, et, em
+
+    def intersect_volumetric(self, rays):
+        """Scene::testVolumetricIntersect: (isects, n_events, event_t, event_medium)"""
+        n = len(rays)
+        out = np.zeros(n, ISECT_DTYPE); ne = np.zeros(n, np.uint32)
+        et = np.zeros((n, MAX_EVENTS), np.float32); em = np.zeros((n, MAX_EVENTS), np.uint32)
+        self._call("intersect_volumetric", _ptr(rays), ctypes.c_uint32(n), _ptr(out), _ptr(ne), _ptr(et), _ptr(em))
+        return out, ne, et, em
 
     def intersect_device(self, rays_ptr, n, hits_ptr, stream=0):
         self._call("intersect_device", ctypes.c_void_p(rays_ptr), ctypes.c_uint32(n), ctypes.c_void_p(hits_ptr), ctypes.c_void_p(stream))
@@ -435,11 +469,12 @@ def create_context(device=0):
     return Api(cuda_lib(), "ptc_", device)
 
 
-def load_scene(scene_json, width, height, device=0, root=REPO_ROOT, options=None):
+def load_scene(scene_json, width, height, device=0, root=REPO_ROOT, options=None, integrator=PATH_TRACER):
     """parseScene + upload: the Python spelling of what app/main.cpp does before Integrator::run.
     options: ptc_set_option pairs applied before the commit (e.g. {"bvh_builder": 0} for the host SAH builder)."""
     api = create_context(device)
     for name, value in (options or {}).items():
         api.set_option(name, value)
     SceneFile(scene_json, width, height, root).feed(api)
+    api.set_integrator(integrator)
     return api

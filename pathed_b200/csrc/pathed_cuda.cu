@@ -14,6 +14,7 @@
 // All queue sizes live on the device; a wave is a fixed launch sequence with no host synchronisation.
 #include "bvh.h"
 #include "shading.cuh"
+#include "volume.cuh"
 
 #include <cuda_runtime.h>
 
@@ -27,7 +28,7 @@
 using namespace ptc;
 
 // ================================================================================================ device state
-#define PTC_MATERIAL_CLASSES 6 /* PTC_LAMBERTIAN .. PTC_PLASTIC */
+#define PTC_MATERIAL_CLASSES 7 /* PTC_LAMBERTIAN .. PTC_PASSTHROUGH */
 struct PathBuffers {
     float4 *rayO, *rayD;   // current ray (origin = current vertex)
     float4 *hit;           // t, u, v, prim bits
@@ -61,7 +62,7 @@ struct BounceCounters {
     uint32_t extendCount, shadowCount;           // rays leaving vertex k / NEE shadow rays cast at vertex k
     uint32_t classCount[PTC_MATERIAL_CLASSES];   // survivors of logic(k) per material class
     uint32_t extendCursor, shadowCursor;         // work cursors of the two traversal launches (lane refill)
-    uint32_t pad[22];
+    uint32_t pad[21];
 };
 static_assert(sizeof(BounceCounters) == 128, "one cache line per bounce");
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
@@ -231,7 +232,8 @@ __device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState
     return done;
 }
 
-template <bool ANY, bool COUNT>
+// FILTER (shadow rays of a scene with container surfaces): Scene::testOcclusion's filter, src/scene.cpp:42-84, :369-370
+template <bool ANY, bool COUNT, bool FILTER = false>
 __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
                                                       unsigned long long *work)
 {
@@ -277,7 +279,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             // a ray whose triangle group is not finished yet (more triangles than PTC_TRI_ROUNDS) sits out this node phase
             if (busy && hasNodes && st.tgroup.y == 0u) { traversalNode<COUNT>(scene.bvh, st, &tc, fast); }
             bool done = false; // this ray needs no further BVH work
-            if (PTC_COOP_TRI && !COUNT) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
+            if (PTC_COOP_TRI && !COUNT && !FILTER) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
             else {
                 for (int round = 0; round < PTC_TRI_ROUNDS; round++) { // triangle rounds, warp-uniform control flow
                     bool pending = busy && !done && st.tgroup.y != 0u;
@@ -287,11 +289,11 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
                         if (pending && traversalPostpone(st, fast)) { pending = false; }
                         if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
                     }
-                    if (pending && traversalTriangle<COUNT>(scene.bvh, st, &tc) && ANY) { done = true; }
+                    if (pending && traversalTriangle<COUNT, FILTER>(scene.bvh, st, &tc) && ANY) { done = true; }
                 }
             }
             if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
-                const bool found = traversalSpheres<ANY>(scene.bvh, st);
+                const bool found = traversalSpheres<ANY, FILTER>(scene.bvh, st);
                 if (ANY) { pb.occluded[p] = found ? 1 : 0; }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
                 busy = false;
@@ -308,6 +310,43 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
 // BSDF samples.  Cheap per path (the Intersection is only built for emitter hits); survivors go to the class queues.
 // 78-86 registers -> 3 CTAs of 256 (logic) / 6 CTAs of 128 (material) per SM.  Forcing 64 registers (4 / 8 CTAs) spills and was
 // measured equal (shade 42.7 ms per 4 steps either way), so the compiler's allocation stands.
+// SampleIntegrator::samplePixel's container branch (src/sample_integrator.cpp:35-51): the camera ray hit a Passthrough surface;
+// adds what lies behind it, attenuated by the medium.
+__device__ __forceinline__ void cameraContainerTerm(const DScene &scene, float ox, float oy, float oz, float dx, float dy, float dz, float *rgb)
+{
+    const V3 O = mk(ox, oy, oz), D = mk(dx, dy, dz);
+    VolumeEvents ev; RayHit vh;
+    const bool vHit = traverseFiltered<false>(scene, O, D, PTC_TNEAR, PTC_TFAR, vh, ev);
+    const V3 tr = rayTransmission(scene, O, D, ev, -1);
+    V3 add;
+    if (vHit) {
+        Isect vi; makeIsect(scene, O, D, vh, vi);
+        const DMaterial &vm = scene.materials[vi.material];
+        add = mk(vm.emit[0], vm.emit[1], vm.emit[2]) * tr;
+    } else { add = envRadiance(scene, D) * tr; }
+    rgb[0] = add.x; rgb[1] = add.y; rgb[2] = add.z;
+}
+
+// Runs between logic(0) and the material kernels of vertex 1, only for scenes with container surfaces: the camera ray and its
+// hit are still in the path state, and out[p] holds the camera-hit emission (0 for a Passthrough surface).
+__global__ void __launch_bounds__(128) containerKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const BounceCounters *bc)
+{
+    const uint32_t n = bc->extendCount;
+    if (!checkCounts(wp.startBounce, wp.lastBounce, 0)) { return; }
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
+        const uint32_t p = queue[item];
+        const uint32_t prim = __float_as_uint(pb.hit[p].w);
+        if (prim == PTC_MISS) { continue; }
+        const uint32_t material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w);
+        if (__ldg(&scene.materials[material].type) != PTC_PASSTHROUGH) { continue; }
+        const float4 o4 = pb.rayO[p], d4 = pb.rayD[p];
+        float add[3];
+        cameraContainerTerm(scene, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, add);
+        const float4 c = pb.out[p];
+        pb.out[p] = make_float4(c.x + add[0], c.y + add[1], c.z + add[2], 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;
@@ -460,6 +499,41 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
     }
 }
 
+// ------------------------------------------------------------------------------------------------ VolumePathTracer
+// One thread follows one path from the camera to its end (volume.cuh: volumeRadiance); warps pull 32 paths at a time from a
+// global cursor, so a warp whose paths ended early does not wait for the rest of the wave.  First correct form of the
+// participating-media integrator; its rays are data-dependent in number (container probes, scatter shadow
+// rays), which is what the wavefront stages above would have to be widened for.
+__global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals)
+{
+    const uint32_t nPaths = wp.nPixels * wp.sppWave;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t closest = 0, shadow = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) { base = atomicAdd(cursor, 32u); }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= nPaths) { break; }
+        const uint32_t p = base + lane;
+        if (p < nPaths) {
+            const uint32_t pixel = slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), s = p / wp.nPixels;
+            Rng rng;
+            rng.initPhilox(wp.seed, pixel, wp.firstSample + s);
+            rng.beginVertex(0);
+            const float jitterX = rng.next() - 0.5f;
+            const float jitterY = rng.next() - 0.5f;
+            const int row = (int)(pixel / (uint32_t)scene.width), col = (int)(pixel % (uint32_t)scene.width);
+            V3 o, d;
+            cameraRay(scene, row + jitterY, col + jitterX, o, d);
+            const V3 L = volumeRadiance(scene, o, d, rng, wp.startBounce, wp.lastBounce, &closest, &shadow);
+            out[p] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { closest += __shfl_xor_sync(0xFFFFFFFFu, closest, o); shadow += __shfl_xor_sync(0xFFFFFFFFu, shadow, o); }
+    if (lane == 0) { atomicAdd(totals, (unsigned long long)closest); atomicAdd(totals + 1, (unsigned long long)shadow); }
+}
+
 __global__ void resolveKernel(const float *accum, float *out, uint32_t n, uint32_t spp) // src/integrator.cpp:74-85
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = accum[i] / (int)spp; }
@@ -548,14 +622,57 @@ __global__ void intersectFullKernel(DScene scene, const ptc_ray *rays, uint32_t 
     }
 }
 
+__device__ __forceinline__ void exportEvents(const VolumeEvents &ev, uint32_t i, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
+{
+    if (nEvents) { nEvents[i] = ev.count; }
+    for (uint32_t e = 0; e < PTC_MAX_EVENTS; e++) {
+        const bool have = e < ev.count;
+        if (eventT) { eventT[(size_t)i * PTC_MAX_EVENTS + e] = have ? ev.t[e] : 0.f; }
+        if (eventMedium) { eventMedium[(size_t)i * PTC_MAX_EVENTS + e] = have ? (uint32_t)ev.medium[e] : PTC_NO_MEDIUM; }
+    }
+}
+
+// Scene::testVolumetricIntersect, src/scene.cpp:225-353
+__global__ void intersectVolumetricKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        const V3 O = mk(r.origin[0], r.origin[1], r.origin[2]), D = mk(r.direction[0], r.direction[1], r.direction[2]);
+        RayHit h; VolumeEvents ev;
+        ptc_isect o;
+        memset(&o, 0, sizeof(o));
+        if (traverseFiltered<false>(scene, O, D, PTC_TNEAR, PTC_TFAR, h, ev)) {
+            Isect is;
+            makeIsect(scene, O, D, h, is);
+            exportIsect(is, h.t, o);
+        } else { o.t = 3.402823466e+38f; o.material = PTC_INVALID_ID; }
+        out[i] = o;
+        exportEvents(ev, i, nEvents, eventT, eventMedium);
+    }
+}
+
 __global__ void occludedKernel(DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
-        RayHit h;
-        occluded[i] = traverseBVH<true, false>(scene.bvh, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], PTC_TNEAR, maxT[i] - 1e-3f, h, nullptr) ? 1 : 0;
+        occluded[i] = sceneOccluded(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), maxT[i]) ? 1 : 0;
     }
 }
+
+// Scene::testVolumetricOcclusion, src/scene.cpp:383-424 (events are reported for unoccluded rays only)
+__global__ void occludedVolumetricKernel(DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, uint32_t *nEvents,
+                                         float *eventT, uint32_t *eventMedium)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        RayHit h; VolumeEvents ev;
+        const bool occ = traverseFiltered<true>(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), PTC_TNEAR, maxT[i] - 1e-3f, h, ev);
+        if (occ) { ev.count = 0; }
+        occluded[i] = occ ? 1 : 0;
+        exportEvents(ev, i, nEvents, eventT, eventMedium);
+    }
+}
+
 
 __global__ void cameraRaysKernel(DScene scene, const float *rowCol, uint32_t n, ptc_ray *rays)
 {
@@ -648,6 +765,11 @@ __global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const fl
             if (checkCounts(start, last, 0)) {
                 const DMaterial &m = scene.materials[isect.material];
                 if (m.emitter && !(dot(isect.n, isect.wo) < 0.f)) { color = mk(m.emit[0], m.emit[1], m.emit[2]); }
+                if (scene.hasFilter && m.type == PTC_PASSTHROUGH) {
+                    float add[3];
+                    cameraContainerTerm(scene, O.x, O.y, O.z, D.x, D.y, D.z, add);
+                    color = color + mk(add[0], add[1], add[2]);
+                }
             }
             BsdfSample bs;
             bsdfSample(scene.materials[isect.material], isect, rng, bs);
@@ -658,8 +780,7 @@ __global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const fl
                 if (wantDirect) {
                     V3 contribution, sd; float maxT;
                     if (directLightsSetup(scene, m, isect, bs, rng, contribution, sd, maxT)) {
-                        RayHit sh;
-                        if (!traverseBVH<true, false>(scene.bvh, isect.point.x, isect.point.y, isect.point.z, sd.x, sd.y, sd.z, PTC_TNEAR, maxT - 1e-3f, sh, nullptr)) { Ld = Ld + contribution; }
+                        if (!sceneOccluded(scene, isect.point, sd, maxT)) { Ld = Ld + contribution; }
                     }
                 }
                 const bool wantNext = !checkDone(last, bounce + 1);
@@ -686,8 +807,20 @@ __global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const fl
     }
 }
 
+__global__ void volumeReplayKernel(DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ptc_ray r = rays[i];
+        Rng rng; rng.initReplay(xi + (size_t)i * stride, stride);
+        uint32_t closest = 0, shadow = 0;
+        const V3 L = volumeRadiance(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), rng, start, last, &closest, &shadow);
+        rgb[3 * i] = L.x; rgb[3 * i + 1] = L.y; rgb[3 * i + 2] = L.z;
+    }
+}
+
 // ================================================================================================ host context
 struct HostGeometry {
+    int32_t medium = -1; // Surface::m_internalMedium of every surface of the geometry
     bool isSphere = false;
     uint32_t firstVertex = 0, firstPrim = 0, nPrims = 0;
     float centerRadius[4] = {0, 0, 0, 0};
@@ -705,6 +838,11 @@ struct ptc_ctx {
     std::vector<float> positions4, normals4, uvs2;
     std::vector<uint32_t> prims4, primIds2;
     std::vector<HostGeometry> geometries;
+    struct HostMedium { float sigmaT[3], sigmaS[3]; };
+    std::vector<HostMedium> media;
+    int integrator = PTC_INTEGRATOR_PATH_TRACER;
+    float4 *volumeOut = nullptr; uint32_t volumeCapacity = 0; uint32_t *volumeCursor = nullptr;
+    int gridVolume = 0;
     bool hasEnv = false, hasCamera = false;
     std::vector<float> envRgba; int envW = 0, envH = 0; float envScale = 1.f; float envM2W[16], envW2M[16];
     float camToWorld[12]; float vfov = 0.f; int width = 0, height = 0;
@@ -821,6 +959,8 @@ int ptc_create(int device, ptc_ctx **out)
     ctx->gridLogic = ctx->numSMs * std::max(perSM, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, materialKernel<PTC_PLASTIC>, 128, 0);
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumePathKernel, 128, 0);
+    ctx->gridVolume = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
     *out = ctx;
     return PTC_OK;
@@ -835,6 +975,7 @@ void ptc_destroy(ptc_ctx *ctx)
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
     cudaFree(ctx->framebuffer); cudaFree(ctx->gatherOut); cudaFree(ctx->gatherStage);
+    cudaFree(ctx->volumeOut); cudaFree(ctx->volumeCursor);
     if (ctx->framebufferReady) { cudaEventDestroy(ctx->framebufferReady); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
@@ -865,7 +1006,7 @@ int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *id)
 {
     if (!ctx || !desc) { return PTC_ERR_INVALID; }
     if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
-    if (desc->type < PTC_LAMBERTIAN || desc->type > PTC_PLASTIC) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented material type %d", desc->type); }
+    if (desc->type < PTC_LAMBERTIAN || desc->type > PTC_PASSTHROUGH) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented material type %d", desc->type); }
     if (desc->albedo_kind == PTC_ALBEDO_TEXTURE) {
         if (desc->type != PTC_LAMBERTIAN && desc->type != PTC_PLASTIC) { CTX_FAIL(ctx, PTC_ERR_INVALID, "only Lambertian and Plastic take a texture (src/scene_parser.cpp:625-647)"); }
         if (desc->texture >= ctx->textures.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "texture id %u out of range", desc->texture); }
@@ -877,6 +1018,35 @@ int ptc_add_material(ptc_ctx *ctx, const ptc_material_desc *desc, uint32_t *id)
     }
     ctx->materials.push_back(*desc);
     if (id) { *id = (uint32_t)ctx->materials.size() - 1; }
+    return PTC_OK;
+}
+
+int ptc_add_medium(ptc_ctx *ctx, const float sigmaT[3], const float sigmaS[3], uint32_t *id)
+{
+    if (!ctx || !sigmaT) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    ptc_ctx::HostMedium m;
+    for (int c = 0; c < 3; c++) { m.sigmaT[c] = sigmaT[c]; m.sigmaS[c] = sigmaS ? sigmaS[c] : 0.f; }
+    ctx->media.push_back(m);
+    if (id) { *id = (uint32_t)ctx->media.size() - 1; }
+    return PTC_OK;
+}
+
+int ptc_set_internal_medium(ptc_ctx *ctx, uint32_t geom, uint32_t medium)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (geom >= ctx->geometries.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "geometry id %u out of range", geom); }
+    if (medium != PTC_NO_MEDIUM && medium >= ctx->media.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "medium id %u out of range", medium); }
+    ctx->geometries[geom].medium = medium == PTC_NO_MEDIUM ? -1 : (int32_t)medium;
+    return PTC_OK;
+}
+
+int ptc_set_integrator(ptc_ctx *ctx, int integrator)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    if (integrator != PTC_INTEGRATOR_PATH_TRACER && integrator != PTC_INTEGRATOR_VOLUME_PATH_TRACER) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented integrator %d", integrator); }
+    ctx->integrator = integrator;
     return PTC_OK;
 }
 
@@ -1097,6 +1267,34 @@ int ptc_commit(ptc_ctx *ctx)
     if ((rc = upload(ctx, lights.data(), lights.size(), &s.lights, A))) { return rc; }
     s.nLights = ctx->nLights;
 
+    // participating media: sigma_t / sigma_s, the internal medium of every geometry, and the occlusion filter's table (a
+    // Passthrough surface that encloses a medium is not a hit for testOcclusion / the volumetric queries, src/scene.cpp:42-84)
+    s.nMedia = (int32_t)ctx->media.size(); s.hasFilter = 0;
+    s.media = nullptr; s.geomMedium = nullptr; s.bvh.primEvent = nullptr; s.bvh.sphereEvent = nullptr;
+    if (s.nMedia) {
+        std::vector<float> media4;
+        for (const ptc_ctx::HostMedium &m : ctx->media) { media4.insert(media4.end(), {m.sigmaT[0], m.sigmaT[1], m.sigmaT[2], 0.f, m.sigmaS[0], m.sigmaS[1], m.sigmaS[2], 0.f}); }
+        std::vector<int32_t> geomMedium(ctx->geometries.size()), primEvent(nPrims, -1), sphereEvent;
+        for (size_t g = 0; g < ctx->geometries.size(); g++) {
+            const HostGeometry &ge = ctx->geometries[g];
+            geomMedium[g] = ge.medium;
+            if (ge.isSphere) {
+                const bool filtered = ge.medium >= 0 && dm[ge.sphereMaterial].type == PTC_PASSTHROUGH;
+                sphereEvent.push_back(filtered ? ge.medium : -1);
+                if (filtered) { s.hasFilter = 1; }
+                continue;
+            }
+            if (ge.medium < 0) { continue; }
+            for (uint32_t p = ge.firstPrim; p < ge.firstPrim + ge.nPrims; p++) {
+                if (dm[ctx->prims4[4 * (size_t)p + 3]].type == PTC_PASSTHROUGH) { primEvent[p] = ge.medium; s.hasFilter = 1; }
+            }
+        }
+        if ((rc = upload(ctx, (const float4 *)media4.data(), media4.size() / 4, &s.media, A))) { return rc; }
+        if ((rc = upload(ctx, geomMedium.data(), geomMedium.size(), &s.geomMedium, A))) { return rc; }
+        if ((rc = upload(ctx, primEvent.data(), primEvent.size(), &s.bvh.primEvent, A))) { return rc; }
+        if ((rc = upload(ctx, sphereEvent.data(), sphereEvent.size(), &s.bvh.sphereEvent, A))) { return rc; }
+    }
+
     s.hasEnv = ctx->hasEnv ? 1 : 0;
     if (ctx->hasEnv) {
         // EnvironmentLight::EnvironmentLight, src/environment_light.cpp:29-53: weight = R+G+B, no sin(theta) (Q9)
@@ -1189,12 +1387,14 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         }
         if (k > 0) {
             StageTimer t(ctx, stream, STAGE_SHADOW);
-            if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
             else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
             logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, queue, bc, ctx->classMask);
+            if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, bc); ctx->launches++; }
             const int g = ctx->gridShade;
             if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
             if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
@@ -1202,6 +1402,7 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
             if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
             if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
             if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
         }
         ctx->launches += k > 0 ? 3 : 2;
     }
@@ -1216,6 +1417,40 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     return PTC_OK;
 }
 
+// VolumePathTracer waves: one volumePathKernel launch over pixels x sppWave paths, then the same in-order accumulation
+static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, uint32_t sppWave, int start, int last, float *accumDevice, cudaStream_t stream)
+{
+    const DScene &s = ctx->scene;
+    const uint32_t nPixels = (uint32_t)s.width * (uint32_t)s.height;
+    if (ctx->volumeCapacity < nPixels * sppWave) {
+        cudaFree(ctx->volumeOut); ctx->volumeOut = nullptr; ctx->volumeCapacity = 0;
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->volumeOut, (size_t)nPixels * sppWave * sizeof(float4)));
+        ctx->volumeCapacity = nPixels * sppWave;
+    }
+    if (!ctx->volumeCursor) { CUDA_TRY(ctx, cudaMalloc((void **)&ctx->volumeCursor, sizeof(uint32_t))); }
+    PathBuffers pb = ctx->paths;
+    pb.out = ctx->volumeOut;
+    for (uint32_t done = 0; done < nSpp; done += sppWave) {
+        WaveParams wp;
+        wp.seed = seed; wp.firstSample = firstSample + done; wp.sppWave = std::min(sppWave, nSpp - done); wp.nPixels = nPixels;
+        wp.startBounce = start; wp.lastBounce = last;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->volumeCursor, 0, sizeof(uint32_t), stream));
+        {
+            StageTimer t(ctx, stream, STAGE_SHADE);
+            volumePathKernel<<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals);
+        }
+        {
+            StageTimer t(ctx, stream, STAGE_OTHER);
+            accumulateKernel<<<std::min<uint32_t>((nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height);
+        }
+        ctx->launches += 2;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (ctx->pending.size() > 4096) { collectTimings(ctx); }
+    ctx->samples += (uint64_t)nPixels * nSpp;
+    return PTC_OK;
+}
+
 static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accumDevice, cudaStream_t stream)
 {
     if (start < 0 || (last != -1 && start > last)) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bad bounce window [%d, %d]", start, last); }
@@ -1223,6 +1458,7 @@ static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uin
     const uint32_t nPixels = (uint32_t)ctx->scene.width * (uint32_t)ctx->scene.height;
     uint32_t sppWave = (uint32_t)std::max<int64_t>(1, ctx->pathsPerWave / (int64_t)nPixels);
     sppWave = std::min(sppWave, std::max(nSpp, 1u));
+    if (ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { return renderVolume(ctx, seed, firstSample, nSpp, sppWave, start, last, accumDevice, stream); }
     int rc = ensurePathBuffers(ctx, nPixels * sppWave);
     if (rc) { return rc; }
     for (uint32_t done = 0; done < nSpp; done += sppWave) {
@@ -1412,6 +1648,48 @@ int ptc_occluded(ptc_ctx *ctx, const ptc_ray *rays, const float *maxT, uint32_t 
     cudaFree(dT);
     return rc;
 }
+// volumetric queries: the per-ray event lists come back through device scratch buffers
+static int volumetricQuery(ptc_ctx *ctx, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, ptc_isect *isects, uint32_t *nEvents,
+                           float *eventT, uint32_t *eventMedium)
+{
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ptc_ray *dRays = nullptr; float *dMaxT = nullptr, *dT = nullptr; uint8_t *dOcc = nullptr; ptc_isect *dIs = nullptr; uint32_t *dN = nullptr, *dM = nullptr;
+    const size_t m = std::max<size_t>(n, 1);
+    int rc = PTC_OK;
+    if (cudaMalloc((void **)&dRays, m * sizeof(ptc_ray)) != cudaSuccess || cudaMalloc((void **)&dMaxT, m * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&dOcc, m) != cudaSuccess || cudaMalloc((void **)&dIs, m * sizeof(ptc_isect)) != cudaSuccess ||
+        cudaMalloc((void **)&dN, m * sizeof(uint32_t)) != cudaSuccess || cudaMalloc((void **)&dT, m * PTC_MAX_EVENTS * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&dM, m * PTC_MAX_EVENTS * sizeof(uint32_t)) != cudaSuccess) { rc = PTC_ERR_NOMEM; ctx->error = "cudaMalloc failed"; }
+    if (!rc) {
+        cudaMemcpyAsync(dRays, rays, n * sizeof(ptc_ray), cudaMemcpyHostToDevice, ctx->stream);
+        if (maxT) { cudaMemcpyAsync(dMaxT, maxT, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream); }
+        if (occluded) { occludedVolumetricKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, dRays, dMaxT, n, dOcc, dN, dT, dM); }
+        else { intersectVolumetricKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, dRays, n, dIs, dN, dT, dM); }
+        ctx->launches++;
+        if (occluded) { cudaMemcpyAsync(occluded, dOcc, n, cudaMemcpyDeviceToHost, ctx->stream); }
+        if (isects) { cudaMemcpyAsync(isects, dIs, n * sizeof(ptc_isect), cudaMemcpyDeviceToHost, ctx->stream); }
+        if (nEvents) { cudaMemcpyAsync(nEvents, dN, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream); }
+        if (eventT) { cudaMemcpyAsync(eventT, dT, (size_t)n * PTC_MAX_EVENTS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream); }
+        if (eventMedium) { cudaMemcpyAsync(eventMedium, dM, (size_t)n * PTC_MAX_EVENTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream); }
+        const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        const cudaError_t e2 = cudaGetLastError();
+        if (e != cudaSuccess || e2 != cudaSuccess) { rc = PTC_ERR_CUDA; ctx->error = std::string("kernel failed: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); }
+    }
+    cudaFree(dRays); cudaFree(dMaxT); cudaFree(dT); cudaFree(dOcc); cudaFree(dIs); cudaFree(dN); cudaFree(dM);
+    return rc;
+}
+int ptc_occluded_volumetric(ptc_ctx *ctx, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !maxT || !occluded)) { return PTC_ERR_INVALID; }
+    return volumetricQuery(ctx, rays, maxT, n, occluded, nullptr, nEvents, eventT, eventMedium);
+}
+int ptc_intersect_volumetric(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !out)) { return PTC_ERR_INVALID; }
+    return volumetricQuery(ctx, rays, nullptr, n, nullptr, out, nEvents, eventT, eventMedium);
+}
 int ptc_intersect_device(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits, void *stream)
 {
     NEED_COMMIT(ctx);
@@ -1488,7 +1766,10 @@ int ptc_radiance_replay(ptc_ctx *ctx, const ptc_ray *rays, const float *xi, uint
     float *dXi = nullptr;
     CUDA_TRY(ctx, cudaMalloc((void **)&dXi, std::max<size_t>((size_t)n * stride, 1) * sizeof(float)));
     cudaMemcpyAsync(dXi, xi, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    const int rc = roundTrip(ctx, rays, n, rgb, (size_t)3 * n, [&](ptc_ray *d, float *o) { radianceReplayKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dXi, stride, n, start, last, o); });
+    const int rc = roundTrip(ctx, rays, n, rgb, (size_t)3 * n, [&](ptc_ray *d, float *o) {
+        if (ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { volumeReplayKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dXi, stride, n, start, last, o); }
+        else { radianceReplayKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, dXi, stride, n, start, last, o); }
+    });
     cudaFree(dXi);
     return rc;
 }

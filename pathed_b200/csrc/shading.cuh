@@ -78,6 +78,11 @@ struct DScene {
     float camToWorld[12];
     float vfov;
     int32_t width, height;
+    // participating media (volume.cuh): sigma_t rgb / sigma_s rgb per medium; internal medium per geometry (-1 none);
+    // hasFilter: some Passthrough surface encloses a medium, i.e. bvh.primEvent / bvh.sphereEvent are in use
+    const float4 *media;
+    const int32_t *geomMedium;
+    int32_t nMedia, hasFilter;
 };
 
 __device__ __forceinline__ V3 xfVec(const float *m, V3 v) // src/transform.cpp:89-100
@@ -462,6 +467,12 @@ __device__ __forceinline__ void bsdfSample(const DMaterial &m, const Isect &i, R
         return;
     }
     case PTC_MICROFACET: microfacetSample(m, i, r, s); return;
+    case PTC_PASSTHROUGH: { // src/passthrough.cpp:26-40: straight on, throughput 1 / |n_s . wo| (cancels the path's cosine)
+        const float cosTheta = fabsf(dot(-i.ns, -i.wo));
+        const float t = 1.f * (1.f / cosTheta); // Color(1.f) / cosTheta multiplies by the reciprocal (src/color.cpp:127-134)
+        s.wi = -i.wo; s.pdf = 1.f; s.thr = mk(t, t, t); s.delta = true;
+        return;
+    }
     default: { // PTC_PLASTIC, src/plastic.cpp:37-66: xi > 0.5 -> diffuse lobe
         const float xi = r.next();
         if (xi > 0.5f) {
@@ -681,12 +692,13 @@ __device__ __forceinline__ bool directLightsSetup(const DScene &s, const DMateri
 }
 
 // PathTracer::directSampleBSDF (src/path_tracer.cpp:167-216) given the already traced bounce hit
-__device__ V3 directBsdf(const DScene &s, V3 point, float cosTheta, V3 wi, float pdf, V3 thr, bool delta, bool hit, const Isect *bi)
+// frontOnly = false: DirectLightingHelper's copy (src/direct_lighting_helper.cpp:139-187), which has no front-side test
+__device__ V3 directBsdf(const DScene &s, V3 point, float cosTheta, V3 wi, float pdf, V3 thr, bool delta, bool hit, const Isect *bi, bool frontOnly = true)
 {
     V3 Le; float lightPDF;
     if (hit) {
         const DMaterial &bm = s.materials[bi->material];
-        if (!__ldg(&bm.emitter) || !(dot(bi->wo, bi->ns) >= 0.f)) { return mk(0.f, 0.f, 0.f); }
+        if (!__ldg(&bm.emitter) || (frontOnly && !(dot(bi->wo, bi->ns) >= 0.f))) { return mk(0.f, 0.f, 0.f); }
         Le = mk(__ldg(&bm.emit[0]), __ldg(&bm.emit[1]), __ldg(&bm.emit[2]));
         lightPDF = lightsPdf(s, point, *bi);
     } else {

@@ -126,6 +126,9 @@ struct BvhView {
     const float4 *spheres;   // center.xyz, radius
     uint32_t nSpheres;
     uint32_t nNodes;
+    // occlusion filter (src/scene.cpp:42-84): per triangle / per sphere the medium of a Passthrough surface that encloses one
+    // (such a hit is rejected and leaves a volume event), -1 for every other surface; null when the scene has no such surface
+    const int32_t *primEvent, *sphereEvent;
 };
 
 #define PTC_SPHERE_FLAG 0x80000000u
@@ -324,7 +327,8 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
 }
 
 // Tests one triangle of the pending group (precondition: st.tgroup.y != 0).  Returns true when a hit was accepted.
-template <bool COUNT>
+// FILTER: Scene::testOcclusion's shouldIntersectPassthroughs = false -- container surfaces are not hits.
+template <bool COUNT, bool FILTER = false>
 PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
 {
     const uint32_t bit = highestBit(st.tgroup.y);
@@ -336,6 +340,7 @@ PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCo
     if (!triangleTestRaw(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
     const float t = divIeee(T, absDen);
     const uint32_t prim = f2u(a.w);
+    if (FILTER && bvh.primEvent[prim] >= 0) { return false; }
     // equal depth (shared edges, coincident faces): keep the larger primitive index, as a linear scan would
     if (!(st.found && t == st.hit.t && prim < st.hit.prim)) { st.hit.t = t; st.hit.u = U; st.hit.v = V; st.hitDen = absDen; st.hit.prim = prim; }
     st.found = true;
@@ -361,7 +366,7 @@ PTC_HD bool traversalPop(TraversalState &st, uint2 *fast = nullptr)
 }
 
 // spheres: a handful per scene (mis-pbrt: 5), tested linearly after the mesh BVH; strict depth test
-template <bool ANY>
+template <bool ANY, bool FILTER = false>
 PTC_HD bool traversalSpheres(const BvhView &bvh, TraversalState &st)
 {
     if (ANY && st.found) { return true; }
@@ -369,6 +374,7 @@ PTC_HD bool traversalSpheres(const BvhView &bvh, TraversalState &st)
     for (uint32_t s = 0; s < bvh.nSpheres; s++) {
         float t, nx, ny, nz;
         if (sphereTest(loadNodeWord(bvh.spheres + s), st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, t, nx, ny, nz)) {
+            if (FILTER && bvh.sphereEvent[s] >= 0) { continue; }
             st.hit.t = t; st.hit.u = 0.f; st.hit.v = 0.f; st.hit.prim = PTC_SPHERE_FLAG | s;
             st.found = true;
             if (ANY) { return true; }

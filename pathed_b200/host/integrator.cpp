@@ -40,6 +40,8 @@ int sinkCamera(void *c, const float *o, const float *t, const float *u, float f,
 }
 int sinkCommit(void *c) { return ptc_commit((ptc_ctx *)c); }
 int sinkTexture(void *c, const uint8_t *rgb, int w, int h, uint32_t *id) { return ptc_add_texture((ptc_ctx *)c, rgb, w, h, id); }
+int sinkMedium(void *c, const float *st, const float *ss, uint32_t *id) { return ptc_add_medium((ptc_ctx *)c, st, ss, id); }
+int sinkInternalMedium(void *c, uint32_t geom, uint32_t medium) { return ptc_set_internal_medium((ptc_ctx *)c, geom, medium); }
 
 double now()
 {
@@ -58,7 +60,7 @@ Scene::Scene(const SceneDescription &description, int gpus) : m_width(descriptio
             throw std::runtime_error("Failed to create device " + std::to_string(device) + " (no CUDA device? there is no CPU path)");
         }
         m_contexts.push_back(ctx);
-        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture};
+        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium};
         const int status = feedScene(description, sink);
         if (status != PTC_OK) {
             const std::string message = ptc_last_error(ctx);
@@ -153,13 +155,18 @@ void Integrator::run(Image &image, Scene &scene, std::function<void(RenderStatus
 }
 
 // ------------------------------------------------------------------------------------------------ CudaPathTracer
-CudaPathTracer::CudaPathTracer(BounceController bounceController, uint64_t seed, int waveSpp)
-    : m_bounceController(bounceController), m_seed(seed), m_waveSpp(std::max(1, waveSpp))
+CudaPathTracer::CudaPathTracer(BounceController bounceController, uint64_t seed, int waveSpp, int integrator)
+    : m_bounceController(bounceController), m_seed(seed), m_waveSpp(std::max(1, waveSpp)), m_integrator(integrator)
+{}
+
+CudaVolumePathTracer::CudaVolumePathTracer(BounceController bounceController, uint64_t seed, int waveSpp)
+    : CudaPathTracer(bounceController, seed, waveSpp, PTC_INTEGRATOR_VOLUME_PATH_TRACER)
 {}
 
 void CudaPathTracer::sampleImage(std::vector<float> &radianceLookup, Scene &scene)
 {
     ptc_ctx *ctx = scene.context(0);
+    check(ctx, ptc_set_integrator(ctx, m_integrator), "integrator");
     check(ctx, ptc_render(ctx, m_seed, m_nextSample, 1, m_bounceController.startBounce(), m_bounceController.lastBounce(), radianceLookup.data()),
           "sampleImage");
     m_nextSample++;
@@ -181,7 +188,10 @@ void CudaPathTracer::run(Image &image, Scene &scene, std::function<void(RenderSt
 
     const int gpus = scene.gpus();
     const int start = m_bounceController.startBounce(), last = m_bounceController.lastBounce();
-    for (int g = 0; g < gpus; g++) { check(scene.context(g), ptc_framebuffer_clear(scene.context(g)), "framebuffer clear"); }
+    for (int g = 0; g < gpus; g++) {
+        check(scene.context(g), ptc_set_integrator(scene.context(g), m_integrator), "integrator");
+        check(scene.context(g), ptc_framebuffer_clear(scene.context(g)), "framebuffer clear");
+    }
     std::vector<ptc_ctx *> peers;
     for (int g = 1; g < gpus; g++) { peers.push_back(scene.context(g)); }
     std::vector<float> resolved((size_t)3 * width * height);

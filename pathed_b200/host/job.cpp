@@ -96,7 +96,8 @@ std::shared_ptr<Integrator> Job::integrator() const
 {
     const std::string name = (*m_json)["integrator"].asString();
     if (name == "PathTracer") { return std::make_shared<CudaPathTracer>(m_bounceController, seed(), waveSpp()); }
-    // the other twelve integrators of src/job.cpp:65-95 are research code outside the accelerated path
+    if (name == "VolumePathTracer") { return std::make_shared<CudaVolumePathTracer>(m_bounceController, seed(), waveSpp()); }
+    // the other eleven integrators of src/job.cpp:65-95 are research code outside the accelerated path
     throw "Unimplemented";
 }
 

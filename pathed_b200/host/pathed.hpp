@@ -170,7 +170,8 @@ public:
 // "PathTracer": the surface path tracer (src/path_tracer.cpp) on the GPU
 class CudaPathTracer : public Integrator {
 public:
-    explicit CudaPathTracer(BounceController bounceController, uint64_t seed = 0x5EED, int waveSpp = 64);
+    explicit CudaPathTracer(BounceController bounceController, uint64_t seed = 0x5EED, int waveSpp = 64,
+                            int integrator = 0 /* PTC_INTEGRATOR_PATH_TRACER */);
     // device-resident spp loop: framebuffers stay in HBM between checkpoints, spp split over scene.gpus() devices,
     // one peer-memory reduce + resolve per callback (replaces the per-wave host loop of src/integrator.cpp:42-105)
     void run(Image &image, Scene &scene, std::function<void(RenderStatus)> callback, bool *quit) override;
@@ -183,9 +184,16 @@ private:
     BounceController m_bounceController;
     uint64_t m_seed;
     int m_waveSpp;
+    int m_integrator; // which L() the device runs (ptc_set_integrator)
     uint32_t m_nextSample = 0;
     double m_renderSeconds = 0.0;
     uint64_t m_samples = 0;
+};
+
+// "VolumePathTracer" (src/volume_path_tracer.cpp): the same device-resident loop with the participating-media L()
+class CudaVolumePathTracer : public CudaPathTracer {
+public:
+    explicit CudaVolumePathTracer(BounceController bounceController, uint64_t seed = 0x5EED, int waveSpp = 64);
 };
 
 } // namespace pathed

@@ -19,6 +19,13 @@ struct GeometryDesc {
     // sphere
     float centerRadius[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t sphereMaterial = 0;
+    // "internal_medium" of the model (src/scene_parser.cpp:324-343, :370-381, :503-514): index into SceneDescription::media, -1 none
+    int internalMedium = -1;
+};
+
+struct MediumDesc { // HomogeneousMedium (include/homogeneous_medium.h), parseMedia src/scene_parser.cpp:202-229
+    std::string name;
+    float sigmaT[3], sigmaS[3];
 };
 
 struct CameraDesc {
@@ -46,6 +53,7 @@ struct TextureDesc { // Texture (include/texture.h): decoded at parse time like 
 struct SceneDescription {
     std::vector<TextureDesc> textures; // ptc_material_desc::texture indexes this list
     std::vector<ptc_material_desc> materials;
+    std::vector<MediumDesc> media;
     std::vector<GeometryDesc> geometries; // index == Embree geomID
     CameraDesc camera;
     EnvironmentDesc environment;
@@ -63,6 +71,8 @@ struct SceneSink {
     int (*set_camera)(void *, const float *, const float *, const float *, float, int, int, int);
     int (*commit)(void *);
     int (*add_texture)(void *, const uint8_t *, int, int, uint32_t *);
+    int (*add_medium)(void *, const float *, const float *, uint32_t *);
+    int (*set_internal_medium)(void *, uint32_t, uint32_t);
 };
 
 // returns the first non-zero status of the sink, 0 on success

@@ -146,8 +146,10 @@ int parseMaterial(const Json &j, const MaterialMap &lookup, SceneDescription &sc
             d.checker_resolution[0] = std::stof(albedo["resolution"]["u"].asString());
             d.checker_resolution[1] = std::stof(albedo["resolution"]["v"].asString());
         }
+    } else if (type == "passthrough") { // src/scene_parser.cpp:593-594: the container material of a participating medium
+        d.type = PTC_PASSTHROUGH;
     } else {
-        // phong / disney / ptex / passthrough / perfect-transmission exist in the reference but are outside
+        // phong / disney / ptex / perfect-transmission exist in the reference but are outside
         // the surface path-tracing hot path (SURVEY §2.1 "BSDFs (other)")
         throw std::runtime_error("Unimplemented material: " + type);
     }
@@ -205,22 +207,39 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
         if (id >= 0) { lookup[name] = (uint32_t)id; }
     }
 
-    if (sceneJson["media"].isArray() && sceneJson["media"].size() > 0) {
-        throw std::runtime_error("participating media are outside the surface path-tracing hot path (SURVEY N3)");
+    // parseMedia, src/scene_parser.cpp:202-229 (homogeneous media; the heterogeneous grid needs .vol assets and stays out)
+    std::map<std::string, int> mediaLookup;
+    if (sceneJson["media"].isArray()) {
+        for (const Json &mediumJson : sceneJson["media"].items()) {
+            const std::string type = parseString(mediumJson["type"], "");
+            if (type == "heterogeneous") { throw std::runtime_error("heterogeneous media are outside the accelerated path (SURVEY N3: HomogeneousMedium)"); }
+            if (type != "homogeneous") { continue; }
+            MediumDesc medium;
+            medium.name = mediumJson["name"].asString();
+            parseColor(mediumJson["sigma_t"], medium.sigmaT, 0.f);
+            parseColor(mediumJson["sigma_s"], medium.sigmaS, 0.f);
+            auto known = mediaLookup.find(medium.name);
+            if (known != mediaLookup.end()) { scene.media[(size_t)known->second] = medium; } // media[name] = ...: the last one wins
+            else { mediaLookup[medium.name] = (int)scene.media.size(); scene.media.push_back(medium); }
+        }
     }
+    // checkString(json["internal_medium"]) + media[key]: an unknown key default-constructs a null medium in the reference's map
+    auto internalMedium = [&](const Json &object) {
+        if (!object["internal_medium"].isString()) { return -1; }
+        auto it = mediaLookup.find(object["internal_medium"].asString());
+        return it == mediaLookup.end() ? -1 : it->second;
+    };
 
     // models, src/scene_parser.cpp:251-291; geometry ids follow attach order
     for (const Json &object : sceneJson["models"].items()) {
         if (parseBool(object["skip"], false)) { continue; }
         const std::string type = parseString(object["type"], "");
-        if (object["internal_medium"].isString()) {
-            throw std::runtime_error("participating media are outside the surface path-tracing hot path (SURVEY N3)");
-        }
         if (type == "obj") {
             const Transform transform = parseTransformOrIdentity(object["transform"]);
             const int material = parseMaterial(object["bsdf"], lookup, scene);
             scene.geometries.push_back(parseObj(resolve(root, object["filename"].asString()), root, transform, lookup,
                                                 parseString(object["materialPrefix"], ""), material, scene));
+            scene.geometries.back().internalMedium = internalMedium(object);
         } else if (type == "ply") {
             const Transform transform = parseTransformOrIdentity(object["transform"]);
             int material = parseMaterial(object["bsdf"], lookup, scene);
@@ -231,6 +250,7 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
                 material = (int)scene.materials.size() - 1;
             }
             scene.geometries.push_back(parsePly(resolve(root, object["filename"].asString()), transform, (uint32_t)material));
+            scene.geometries.back().internalMedium = internalMedium(object);
         } else if (type == "sphere") {
             const int material = parseMaterial(object["bsdf"], lookup, scene);
             if (material < 0) { throw std::runtime_error("sphere without bsdf"); }
@@ -243,6 +263,7 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
             g.centerRadius[0] = c.x; g.centerRadius[1] = c.y; g.centerRadius[2] = c.z;
             g.centerRadius[3] = parseFloat(object["radius"]);
             g.sphereMaterial = (uint32_t)material;
+            g.internalMedium = internalMedium(object);
             scene.geometries.push_back(g);
         } else if (type == "quad") {
             const int material = parseMaterial(object["bsdf"], lookup, scene);
@@ -285,14 +306,23 @@ int feedScene(const SceneDescription &scene, const SceneSink &sink)
     for (const ptc_material_desc &material : scene.materials) {
         if ((status = sink.add_material(sink.ctx, &material, nullptr))) { return status; }
     }
+    for (const MediumDesc &medium : scene.media) {
+        if (!sink.add_medium) { return PTC_ERR_INVALID; }
+        if ((status = sink.add_medium(sink.ctx, medium.sigmaT, medium.sigmaS, nullptr))) { return status; }
+    }
     for (const GeometryDesc &g : scene.geometries) {
-        if (g.isSphere) { status = sink.add_sphere(sink.ctx, g.centerRadius, g.sphereMaterial, nullptr); }
+        uint32_t geomId = 0;
+        if (g.isSphere) { status = sink.add_sphere(sink.ctx, g.centerRadius, g.sphereMaterial, &geomId); }
         else {
             status = sink.add_triangle_mesh(sink.ctx, g.positions.data(), g.normals.data(), g.uvs.data(),
                                             (uint32_t)(g.positions.size() / 3), g.indices.data(), g.materialOfTri.data(),
-                                            (uint32_t)g.materialOfTri.size(), nullptr);
+                                            (uint32_t)g.materialOfTri.size(), &geomId);
         }
         if (status) { return status; }
+        if (g.internalMedium >= 0) {
+            if (!sink.set_internal_medium) { return PTC_ERR_INVALID; }
+            if ((status = sink.set_internal_medium(sink.ctx, geomId, (uint32_t)g.internalMedium))) { return status; }
+        }
     }
     if (scene.environment.present) {
         const EnvironmentDesc &e = scene.environment;

@@ -259,7 +259,17 @@ SCENES = {
                      image_width=64, image_height=48, image_spp=2048),
     "env_sampling": dict(scene="test_scenes/environment_map_sampling.json", width=64, height=48, last_bounce=4, seed=16,
                          n_rays=2048, n_paths=1024, image_width=64, image_height=48, image_spp=1024),
+    # participating media.  integrator = 1: VolumePathTracer (paths and images); the ray fixtures add the
+    # volumetric queries (testVolumetricIntersect / testVolumetricOcclusion with their volume events)
+    "cornell_medium": dict(scene="scenes/cornell-medium.json", width=64, height=64, last_bounce=10, seed=18, n_rays=4096,
+                           n_paths=2048, image_width=64, image_height=64, image_spp=2048, integrator=1),
+    "medium_sphere": dict(scene="test_scenes/medium_sphere.json", width=64, height=48, last_bounce=8, seed=19, n_rays=4096,
+                          n_paths=2048, image_width=64, image_height=48, image_spp=2048, integrator=1),
+    # the same container scene under the plain PathTracer: Passthrough vertices + the occlusion filter in testOcclusion (A8f)
+    "cornell_medium_pt": dict(scene="scenes/cornell-medium.json", width=64, height=64, last_bounce=10, seed=20, n_rays=2048,
+                              n_paths=2048, image_width=64, image_height=64, image_spp=2048, integrator=0),
 }
+INTEGRATOR_NAMES = {0: "PathTracer", 1: "VolumePathTracer"}
 
 
 def ray_inputs(name, n):

@@ -26,9 +26,10 @@ def oracle_context():
     return Api(oracle_lib(), "orc_")
 
 
-def oracle_scene(scene_json, width, height, root=REPO_ROOT):
+def oracle_scene(scene_json, width, height, root=REPO_ROOT, integrator=0):
     api = oracle_context()
     SceneFile(scene_json, width, height, root).feed(api)
+    api.set_integrator(integrator)
     return api
 
 

@@ -5,7 +5,7 @@ import pytest
 
 from golden_inputs import BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, material_desc, ray_inputs, uniform_floats
 from oracle_binding import oracle_scene
-from parity import REL, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
+from parity import REL, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -18,7 +18,7 @@ def gpu_context():
 def gpu_scene(name, width=None, height=None):
     from pathed_b200 import load_scene
     cfg = SCENES[name]
-    return load_scene(cfg["scene"], width or cfg["width"], height or cfg["height"])
+    return load_scene(cfg["scene"], width or cfg["width"], height or cfg["height"], integrator=cfg.get("integrator", 0))
 
 
 def _tiny_scene(ctx, materials):
@@ -137,7 +137,14 @@ def test_paths_match_reference_with_replayed_stream(name):
     assert abs(rgb.mean() - g["path_rgb"].mean()) <= 0.02 * abs(g["path_rgb"].mean()) + 1e-6
 
 
-@pytest.mark.parametrize("name", ["cornell", "cornell_glass", "mis", "env_sampling", "teapot", "textured"])
+@pytest.mark.parametrize("name", sorted(n for n in SCENES if "integrator" in SCENES[n]))
+def test_volumetric_queries_match_reference(name):
+    """SURVEY N3: Scene::testVolumetricOcclusion / testVolumetricIntersect with their volume events against the reference"""
+    check_volumetric_queries(gpu_scene(name), golden("scene_" + name))
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell_glass", "mis", "env_sampling", "teapot", "textured", "cornell_medium",
+                                  "medium_sphere", "cornell_medium_pt"])
 def test_wavefront_render_matches_oracle_per_pixel(name):
     """same Philox streams (pixel, sample, bounce) on both sides: the wavefront stages must reproduce the oracle's
     per-pixel sums, up to the rare path whose branch flips on a last-bit difference in libm"""
@@ -146,7 +153,7 @@ def test_wavefront_render_matches_oracle_per_pixel(name):
     spp = 4
     ctx = gpu_scene(name, w, h)
     img = ctx.render(1234, 0, spp, 0, cfg["last_bounce"])
-    ref = oracle_scene(cfg["scene"], w, h).render(1234, 0, spp, 0, cfg["last_bounce"])
+    ref = oracle_scene(cfg["scene"], w, h, integrator=cfg.get("integrator", 0)).render(1234, 0, spp, 0, cfg["last_bounce"])
     assert np.isfinite(img).all()
     err = np.abs(img - ref) / (np.abs(ref) + 1e-3 * max(ref.mean(), 1e-3))
     frac = float((err.max(-1) < 1e-3).mean())

@@ -35,8 +35,10 @@ def test_job_accessors_and_defaults(tmp_path):
 
 def test_job_unknown_integrator_is_unimplemented(tmp_path):
     # src/job.cpp:96: throw "Unimplemented"; the research integrators are outside the accelerated path
-    for name in ("VolumePathTracer", "LightTracer", "NoSuchThing"):
+    for name in ("BDPT", "LightTracer", "NoSuchThing"):
         assert job_describe(_job(tmp_path, integrator=name))["integrator_status"] == "Unimplemented"
+    # "VolumePathTracer" (src/job.cpp:71-72) is built
+    assert job_describe(_job(tmp_path, integrator="VolumePathTracer"))["integrator_status"] == "ok"
 
 
 def test_job_missing_keys_raise(tmp_path):

@@ -5,7 +5,7 @@ import pytest
 
 from golden_inputs import BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, material_desc, ray_inputs, uniform_floats
 from oracle_binding import oracle_context, oracle_lib, oracle_scene
-from parity import REL, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
+from parity import REL, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
 
 import ctypes
 
@@ -122,11 +122,13 @@ def test_scene_queries_match_reference(name):
 
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_paths_match_reference_with_replayed_stream(name):
-    """PathTracer::L with the same random numbers in the same order: per-path radiance must agree"""
+    """PathTracer::L (VolumePathTracer::L for the scenes with media) with the same random numbers in the same order: per-path
+    radiance must agree"""
     cfg = SCENES[name]
     g = golden("scene_" + name)
     o = oracle_scene(cfg["scene"], cfg["width"], cfg["height"])
     o.set_option("brute_force", 0 if name in ("dragon", "teapot") else 1)
+    o.set_integrator(cfg.get("integrator", 0))
     m = cfg["n_paths"]
     xi = uniform_floats(cfg["seed"] + 101, (m, 96))
     rgb = o.radiance_replay(to_rays(g["cam_rays"][:m]), xi, 0, cfg["last_bounce"])
@@ -135,3 +137,13 @@ def test_paths_match_reference_with_replayed_stream(name):
     # a path that lands within float noise of an edge / a Fresnel threshold takes another branch; those are rare
     assert ok >= 0.99, (ok, np.sort(e)[-10:])
     assert abs(rgb.mean() - want.mean()) <= 0.01 * abs(want.mean()) + 1e-6
+
+
+MEDIA_SCENES = sorted(n for n in SCENES if "integrator" in SCENES[n])
+
+
+@pytest.mark.parametrize("name", MEDIA_SCENES)
+def test_volumetric_queries_match_reference(name):
+    """Scene::testVolumetricOcclusion / testVolumetricIntersect (src/scene.cpp:225-353, :383-424): container surfaces are
+    filtered out (src/scene.cpp:42-84) and leave volume events"""
+    check_volumetric_queries(oracle_scene(SCENES[name]["scene"], SCENES[name]["width"], SCENES[name]["height"]), golden("scene_" + name))

@@ -163,6 +163,20 @@ sh[~ok] = cam[~ok]; dist = np.where(ok, dist, 50.0).astype(np.float32)
 occ = np.zeros(n, np.uint8)
 lib.ref_occluded(n, fptr(sh), fptr(dist), fptr(occ))
 out['shadow_rays'] = sh.astype(np.float32); out['shadow_max_t'] = dist; out['shadow_occluded'] = occ
+if 'integrator' in cfg:
+    # volumetric queries (participating media): containers are filtered out and leave volume events
+    ME = 8
+    sh32 = np.ascontiguousarray(sh.astype(np.float32))
+    vocc = np.zeros(n, np.uint8); vne = np.zeros(n, np.int32); vet = np.zeros((n, ME), np.float32)
+    lib.ref_volumetric_occluded(n, fptr(sh32), fptr(dist), fptr(vocc), fptr(vne), fptr(vet), ME)
+    out['vshadow_occluded'] = vocc; out['vshadow_n_events'] = vne; out['vshadow_event_t'] = vet
+    for tag, rays in (('vcam', cam), ('vsec', sec)):
+        vh = np.zeros(n, np.int32); vt = np.zeros(n, np.float32); vp = np.zeros((n, 3), np.float32); ve = np.zeros((n, 3), np.float32)
+        ne = np.zeros(n, np.int32); et = np.zeros((n, ME), np.float32)
+        lib.ref_volumetric_intersect(n, fptr(rays), fptr(vh), fptr(vt), fptr(vp), fptr(ve), fptr(ne), fptr(et), ME)
+        out[tag + '_hit'] = vh; out[tag + '_t'] = vt; out[tag + '_point'] = vp; out[tag + '_emit'] = ve
+        out[tag + '_n_events'] = ne; out[tag + '_event_t'] = et
+    lib.ref_set_integrator(cfg['integrator'])
 # light sampling from the hit points
 nl = int(out['num_lights'])
 if nl > 0:
@@ -207,7 +221,8 @@ def gen_images(names):
             continue
         w, h, spp = cfg["image_width"], cfg["image_height"], cfg["image_spp"]
         with tempfile.TemporaryDirectory() as tmp:
-            job = {"spp": spp, "integrator": "PathTracer", "scene": cfg["scene"], "startBounce": 0,
+            from golden_inputs import INTEGRATOR_NAMES
+            job = {"spp": spp, "integrator": INTEGRATOR_NAMES[cfg.get("integrator", 0)], "scene": cfg["scene"], "startBounce": 0,
                    "lastBounce": cfg["last_bounce"], "output_directory": os.path.join(tmp, "out"), "showUI": False,
                    "force": True, "width": w, "height": h, "output_name": "golden"}
             job_path = os.path.join(tmp, "job.json")
