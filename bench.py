@@ -44,6 +44,8 @@ WORKLOADS = {
     "cornell-glass": dict(scene="scenes/cornell-glass.json", width=512, height=512, last_bounce=10),
     "mis-pbrt": dict(scene="scenes/mis-pbrt.json", width=768, height=512, last_bounce=10),
     "teapot": dict(scene="scenes/teapot.json", width=1920, height=1080, last_bounce=10),
+    # participating medium in a Passthrough container, VolumePathTracer (one-thread-per-path kernel)
+    "cornell-medium": dict(scene="scenes/cornell-medium.json", width=512, height=512, last_bounce=10, integrator="VolumePathTracer"),
 }
 SPP_PER_STEP = 16
 REF_SPP_PER_STEP = 1  # the CPU reference does ~0.5 Msamples/s: one spp of 1024^2 is ~2 s
@@ -95,7 +97,7 @@ def run_reference(workload, steps, warmup, spp_per_step=REF_SPP_PER_STEP):
     with tempfile.TemporaryDirectory() as tmp:
         def job(name, spp):
             path = os.path.join(tmp, name + ".json")
-            json.dump({"spp": spp, "integrator": "PathTracer", "scene": w["scene"], "startBounce": 0, "lastBounce": w["last_bounce"],
+            json.dump({"spp": spp, "integrator": w.get("integrator", "PathTracer"), "scene": w["scene"], "startBounce": 0, "lastBounce": w["last_bounce"],
                        "output_directory": os.path.join(tmp, name), "showUI": False, "force": True,
                        "width": w["width"], "height": w["height"], "output_name": name}, open(path, "w"))
             return path
@@ -126,7 +128,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["render_wall_s"] * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], w["width"], w["height"], w["last_bounce"]),
+        "config": {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], w["width"], w["height"], w.get("integrator", "PathTracer"), w["last_bounce"]),
                    "spp_per_step": r["spp_per_step"]},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": r["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,7 +176,8 @@ def main():
     width, height, last = w["width"], w["height"], w["last_bounce"]
     spp = args.spp_per_step
     t0 = time.time()
-    ctx = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder})
+    ctx = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder},
+                     integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
     build_s = time.time() - t0
     tst0 = ctx.stats()
     if args.paths_per_wave:
@@ -262,7 +265,11 @@ def main():
 
     # ---- roofline of the dominant kernel (extend), rank 0 only: stage-timed pass, then counted pass (same seed)
     roofline, stages = None, None
-    if rank == 0:
+    if rank == 0 and w.get("integrator") == "VolumePathTracer":
+        # no wavefront stages here: one kernel follows whole paths (volumePathKernel); the roofline line is the extend kernel's
+        roofline = {"bound": "hbm", "kernel": "volumePathKernel (one thread per path)", "achieved": None, "peak": measured_peak()[0], "unit": "GB/s",
+                    "frac": None, "traffic": None, "note": "first correct form of SURVEY N3; not a bench headline"}
+    elif rank == 0:
         peak, peak_note = measured_peak()
         ctx.set_option("stage_timing", 1)
         ctx.reset_stats()
@@ -316,7 +323,7 @@ def main():
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "%s %dx%d PathTracer lastBounce %d" % (w["scene"], width, height, last), "spp_per_step": spp,
+            "config": {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], width, height, w.get("integrator", "PathTracer"), last), "spp_per_step": spp,
                        "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 148 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
                        "scene_build_s": build_s,

@@ -266,8 +266,10 @@ SCENES = {
     "medium_sphere": dict(scene="test_scenes/medium_sphere.json", width=64, height=48, last_bounce=8, seed=19, n_rays=4096,
                           n_paths=2048, image_width=64, image_height=48, image_spp=2048, integrator=1),
     # the same container scene under the plain PathTracer: Passthrough vertices + the occlusion filter in testOcclusion (A8f)
+    # image_noise: two independent 1024-spp oracle renders of this scene differ by relMSE 2.1e-2 (light is only found through
+    # BSDF hits behind the delta Passthrough vertices), i.e. 2.6e-3 at 4096 spp against the 1e-3 the north-star gate assumes
     "cornell_medium_pt": dict(scene="scenes/cornell-medium.json", width=64, height=64, last_bounce=10, seed=20, n_rays=2048,
-                              n_paths=2048, image_width=64, image_height=64, image_spp=2048, integrator=0),
+                              n_paths=2048, image_width=64, image_height=64, image_spp=2048, integrator=0, image_noise=3.0),
 }
 INTEGRATOR_NAMES = {0: "PathTracer", 1: "VolumePathTracer"}
 

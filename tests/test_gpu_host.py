@@ -53,10 +53,22 @@ def test_cli_wave_size_and_seed_keys(tmp_path):
 
 
 def test_cli_rejects_what_the_reference_rejects(tmp_path):
-    _, r = _run_job(tmp_path, integrator="VolumePathTracer")
+    _, r = _run_job(tmp_path, integrator="BDPT")
     assert r.returncode == 1 and "Unimplemented" in r.stdout
     _, r = _run_job(tmp_path, scene="scenes/does-not-exist.json")
     assert r.returncode == 1
+
+
+def test_cli_volume_path_tracer_job(tmp_path):
+    """job.json with "integrator": "VolumePathTracer" on the medium scene = ptc_set_integrator + ptc_render"""
+    from pathed_b200._binding import VOLUME_PATH_TRACER
+    job, r = _run_job(tmp_path, integrator="VolumePathTracer", scene="scenes/cornell-medium.json", spp=4)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = read_exr(str(tmp_path / "out" / "final.exr"))[..., :3]
+    ctx = load_scene(job["scene"], job["width"], job["height"], integrator=VOLUME_PATH_TRACER)
+    want = (ctx.render(0x5EED, 0, 4, 0, 10) / np.float32(4))[::-1].astype(np.float16).astype(np.float32)
+    assert np.array_equal(got, want)
+    assert want.mean() > 0.01
 
 
 def test_scene_queries_through_the_host_api():
