@@ -504,11 +504,11 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
 // global cursor, so a warp whose paths ended early does not wait for the rest of the wave.  First correct form of the
 // participating-media integrator; its rays are data-dependent in number (container probes, scatter shadow
 // rays), which is what the wavefront stages above would have to be widened for.
-__global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals)
+__global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals, bool countWork)
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t closest = 0, shadow = 0;
+    VolumeWork work = {0, 0, {0, 0}, {0, 0}};
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) { base = atomicAdd(cursor, 32u); }
@@ -525,13 +525,18 @@ __global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *ou
             const int row = (int)(pixel / (uint32_t)scene.width), col = (int)(pixel % (uint32_t)scene.width);
             V3 o, d;
             cameraRay(scene, row + jitterY, col + jitterX, o, d);
-            const V3 L = volumeRadiance(scene, o, d, rng, wp.startBounce, wp.lastBounce, &closest, &shadow);
+            const V3 L = volumeRadiance(scene, o, d, rng, wp.startBounce, wp.lastBounce, &work);
             out[p] = make_float4(L.x, L.y, L.z, 0.f);
         }
     }
+    // totals: [0] closest rays, [1] shadow rays, [2..3] inner visits / triangle tests of the closest-hit rays, [4..5] of the shadow rays
+    uint32_t v[6] = {work.closestRays, work.shadowRays, work.closest.inner, work.closest.tris, work.shadow.inner, work.shadow.tris};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { closest += __shfl_xor_sync(0xFFFFFFFFu, closest, o); shadow += __shfl_xor_sync(0xFFFFFFFFu, shadow, o); }
-    if (lane == 0) { atomicAdd(totals, (unsigned long long)closest); atomicAdd(totals + 1, (unsigned long long)shadow); }
+    for (int k = 0; k < 6; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o); }
+        if (lane == 0 && (k < 2 || countWork)) { atomicAdd(totals + k, (unsigned long long)v[k]); }
+    }
 }
 
 __global__ void resolveKernel(const float *accum, float *out, uint32_t n, uint32_t spp) // src/integrator.cpp:74-85
@@ -812,8 +817,8 @@ __global__ void volumeReplayKernel(DScene scene, const ptc_ray *rays, const floa
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
         Rng rng; rng.initReplay(xi + (size_t)i * stride, stride);
-        uint32_t closest = 0, shadow = 0;
-        const V3 L = volumeRadiance(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), rng, start, last, &closest, &shadow);
+        VolumeWork work = {0, 0, {0, 0}, {0, 0}};
+        const V3 L = volumeRadiance(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), rng, start, last, &work);
         rgb[3 * i] = L.x; rgb[3 * i + 1] = L.y; rgb[3 * i + 2] = L.z;
     }
 }
@@ -1437,7 +1442,7 @@ static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint3
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->volumeCursor, 0, sizeof(uint32_t), stream));
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
-            volumePathKernel<<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals);
+            volumePathKernel<<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals, ctx->countTraversal);
         }
         {
             StageTimer t(ctx, stream, STAGE_OTHER);
