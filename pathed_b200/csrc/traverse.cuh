@@ -88,6 +88,15 @@ PTC_HD float byteToMagic(uint32_t x, int j)
     return u2f(0x47000000u | (((x >> (8 * j)) & 0xFFu) << 8));
 #endif
 }
+// byte j of x, zero-extended (one PRMT on the device)
+PTC_HD uint32_t byteOf(uint32_t x, int j)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0u, 0x4440u | (uint32_t)j);
+#else
+    return (x >> (8 * j)) & 0xFFu;
+#endif
+}
 // a * b + c rounded towards -inf / +inf
 PTC_HD float fmaDown(float a, float b, float c)
 {
@@ -202,6 +211,11 @@ PTC_HD bool sphereTest(const float4 s, float ox, float oy, float oz, float dx, f
 
 struct TraverseCounters { uint32_t inner, tris; };
 
+// 1: assemble the traversal mask in a loop over the hit children (measured slower: the loop runs at 8 of 32 lanes)
+#ifndef PTC_HITMASK_LOOP
+#define PTC_HITMASK_LOOP 0
+#endif
+
 #define PTC_STACK_SIZE 40
 
 // Per-ray traversal state: lets a kernel interleave the phases of many rays (persistent warps that refill idle lanes).
@@ -290,7 +304,15 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
         const float bx1 = fmaUp(-32768.f, ax, bx), by1 = fmaUp(-32768.f, ay, by), bz1 = fmaUp(-32768.f, az, bz);
         ngroup.x = f2u(n1.x);
         tgroup.x = f2u(n1.y);
+#if PTC_HITMASK_LOOP
         uint32_t hits8 = 0;
+#else
+        // octant-ordered traversal mask: the per-child meta byte is 0b cccxxxxx (ccc = child bits to set, xxxxx = first bit;
+        // inner children, xxxxx >= 24, have their slot xor-ed with the ray octant).  The four children of a meta word are decoded
+        // at once with byte-parallel integer operations, so that the slab loop below only extracts two bytes per hit child.
+        uint32_t hitmask = 0;
+        const uint32_t octInv4 = st.octInv * 0x01010101u;
+#endif
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const uint32_t qlox = f2u(half ? n2.y : n2.x), qloy = f2u(half ? n2.w : n2.z), qloz = f2u(half ? n3.y : n3.x);
@@ -298,6 +320,12 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
             const uint32_t xmin = st.dx < 0.f ? qhix : qlox, xmax = st.dx < 0.f ? qlox : qhix;
             const uint32_t ymin = st.dy < 0.f ? qhiy : qloy, ymax = st.dy < 0.f ? qloy : qhiy;
             const uint32_t zmin = st.dz < 0.f ? qhiz : qloz, zmax = st.dz < 0.f ? qloz : qhiz;
+#if !PTC_HITMASK_LOOP
+            const uint32_t meta4 = f2u(half ? n1.w : n1.z);
+            const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4; // 1 in every byte of an inner child
+            const uint32_t index4 = (meta4 ^ (octInv4 & (inner4 * 0xFFu))) & 0x1F1F1F1Fu;
+            const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
+#endif
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float t0x = fmaf(byteToMagic(xmin, j), ax, bx0), t1x = fmaf(byteToMagic(xmax, j), ax, bx1);
@@ -305,9 +333,14 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
                 const float t0z = fmaf(byteToMagic(zmin, j), az, bz0), t1z = fmaf(byteToMagic(zmax, j), az, bz1);
                 const float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, st.tnear));
                 const float tmax = fminf(fminf(t1x, t1y), fminf(t1z, st.hit.t)) * 1.0000004f;
+#if PTC_HITMASK_LOOP
                 if (tmin <= tmax) { hits8 |= 1u << (4 * half + j); }
+#else
+                if (tmin <= tmax) { hitmask |= byteOf(bits4, j) << byteOf(index4, j); }
+#endif
             }
         }
+#if PTC_HITMASK_LOOP
         // octant-ordered traversal mask, assembled for the children that were hit only
         uint32_t hitmask = 0;
         const uint32_t metaLo = f2u(n1.z), metaHi = f2u(n1.w);
@@ -319,6 +352,7 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
             const uint32_t bitIndex = (meta ^ (isInner ? st.octInv : 0u)) & 0x1Fu;
             hitmask |= (meta >> 5) << bitIndex;
         }
+#endif
         ngroup.y = (hitmask & 0xFF000000u) | (e >> 24);
         tgroup.y = hitmask & 0x00FFFFFFu;
     }
