@@ -216,8 +216,8 @@ int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);
 int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out);  /* Scene::testIntersect */
 int ptc_occluded(ptc_ctx *ctx, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded); /* Scene::testOcclusion */
 /* Scene::testVolumetricOcclusion (src/scene.cpp:383-424): occlusion with container surfaces filtered out; n_events[i] = number
- * of distinct volume events on an unoccluded ray, event_t / event_medium[PTC_MAX_EVENTS * i ...] = the first PTC_MAX_EVENTS of
- * them sorted by t (either may be NULL) */
+ * of distinct volume events on an unoccluded ray, event_t / event_medium[PTC_MAX_EVENTS * i ...] = those events sorted by t
+ * (when there are more than PTC_MAX_EVENTS, the ones the traversal met first); either array may be NULL */
 int ptc_occluded_volumetric(ptc_ctx *ctx, const ptc_ray *rays, const float *max_t, uint32_t n, uint8_t *occluded,
                             uint32_t *n_events, float *event_t, uint32_t *event_medium);
 /* Scene::testVolumetricIntersect (src/scene.cpp:225-353): closest hit that is not a container-with-medium surface, plus the

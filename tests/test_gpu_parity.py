@@ -238,6 +238,54 @@ def test_error_statuses():
         ctx.commit()  # no camera
 
 
+def test_media_edge_cases():
+    """SURVEY N3 edge cases: status codes of the medium calls, empty query batches, a Passthrough surface WITHOUT a medium (an
+    ordinary occluder: the filter only skips containers that enclose a medium, src/scene.cpp:59-63), the VolumePathTracer on a
+    scene without media (= no events anywhere), unbounded event lists."""
+    from pathed_b200 import PathedError
+    from pathed_b200._binding import NO_MEDIUM, PASSTHROUGH, VOLUME_PATH_TRACER, rays_array
+    ctx = gpu_context()
+    with pytest.raises(PathedError):
+        ctx.set_internal_medium(0, 0)  # no such geometry
+    with pytest.raises(PathedError):
+        ctx.set_integrator(7)
+    gas = ctx.add_medium((1.0, 1.0, 1.0), (0.5, 0.5, 0.5))
+    wall = ctx.add_material(material_desc(dict(type=0, diffuse=(0.5, 0.5, 0.5))))
+    glass = ctx.add_material(material_desc(dict(type=PASSTHROUGH)))
+    quad = lambda z: [[-1, -1, z], [1, -1, z], [1, 1, z], [-1, 1, z]]
+    far = ctx.add_triangle_mesh(quad(-5.0), None, None, [[0, 1, 2], [0, 2, 3]], wall)
+    layers = [ctx.add_triangle_mesh(quad(-1.0 - 0.25 * i), None, None, [[0, 1, 2], [0, 2, 3]], glass) for i in range(12)]
+    bare = ctx.add_triangle_mesh(quad(-4.5), None, None, [[0, 1, 2], [0, 2, 3]], glass)  # container material, no medium
+    for g in layers:
+        ctx.set_internal_medium(g, gas)
+    with pytest.raises(PathedError):
+        ctx.set_internal_medium(far, 5)  # no such medium
+    ctx.set_internal_medium(far, NO_MEDIUM)
+    ctx.set_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 0.5, 8, 8)
+    ctx.commit()
+    rays = rays_array([[0.1, 0.2, 0.0]], [[0, 0, -1]])
+    isects, ne, et, em = ctx.intersect_volumetric(rays)
+    assert isects["hit"][0] == 1 and abs(isects["t"][0] - 4.5) < 1e-5  # the bare Passthrough quad is a hit
+    # 12 events counted; 8 of them stored (whichever the traversal met first), sorted by t
+    assert ne[0] == 12 and (em[0] == gas).all() and (np.diff(et[0]) > 0).all()
+    assert all(np.isclose(1.0 + 0.25 * np.arange(12), t).any() for t in et[0])
+    occ, ne, et, em = ctx.occluded_volumetric(rays, np.array([4.0], np.float32))
+    assert occ[0] == 0 and ne[0] == 12
+    occ, ne, et, em = ctx.occluded_volumetric(rays, np.array([4.75], np.float32))
+    assert occ[0] == 1 and ne[0] == 0  # the bare quad occludes; events of occluded rays are not reported
+    assert ctx.occluded(rays, np.array([4.0], np.float32))[0] == 0 and ctx.occluded(rays, np.array([4.75], np.float32))[0] == 1
+    assert ctx.intersect_full(rays)["t"][0] == np.float32(1.0)  # Scene::testIntersect hits containers
+    empty = rays_array(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert len(ctx.intersect_volumetric(empty)[0]) == 0 and len(ctx.occluded_volumetric(empty, np.zeros(0, np.float32))[0]) == 0
+    # no media at all: the volume integrator must agree with the oracle running the same integrator
+    cfg = SCENES["cornell_glass"]
+    from pathed_b200 import load_scene
+    img = load_scene(cfg["scene"], 32, 32, integrator=VOLUME_PATH_TRACER).render(3, 0, 4, 0, 6)
+    ref = oracle_scene(cfg["scene"], 32, 32, integrator=VOLUME_PATH_TRACER).render(3, 0, 4, 0, 6)
+    err = np.abs(img - ref) / (np.abs(ref) + 1e-3 * ref.mean())
+    assert (err.max(-1) < 1e-3).mean() >= 0.97
+
+
 def test_empty_scene_renders_environment_only():
     ctx = gpu_context()
     env = np.zeros((8, 16, 4), np.float32)
