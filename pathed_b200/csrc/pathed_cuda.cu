@@ -504,7 +504,13 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
 // global cursor, so a warp whose paths ended early does not wait for the rest of the wave.  First correct form of the
 // participating-media integrator; its rays are data-dependent in number (container probes, scatter shadow
 // rays), which is what the wavefront stages above would have to be widened for.
-__global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals, bool countWork)
+// 16 resident CTAs per SM (32 registers, the rest spills to L1): measured 2.1x faster than the compiler's own allocation
+// (186 registers, 2 CTAs) -- the kernel waits on dependent loads, not on issue slots (profiles/r01_sweep_volume_occupancy.txt)
+#ifndef PTC_VOLUME_MIN_BLOCKS
+#define PTC_VOLUME_MIN_BLOCKS 16
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(128, PTC_VOLUME_MIN_BLOCKS) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals)
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     const uint32_t lane = threadIdx.x & 31u;
@@ -525,7 +531,7 @@ __global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *ou
             const int row = (int)(pixel / (uint32_t)scene.width), col = (int)(pixel % (uint32_t)scene.width);
             V3 o, d;
             cameraRay(scene, row + jitterY, col + jitterX, o, d);
-            const V3 L = volumeRadiance(scene, o, d, rng, wp.startBounce, wp.lastBounce, &work);
+            const V3 L = volumeRadiance<COUNT>(scene, o, d, rng, wp.startBounce, wp.lastBounce, &work);
             out[p] = make_float4(L.x, L.y, L.z, 0.f);
         }
     }
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(128) volumePathKernel(DScene scene, float4 *ou
     for (int k = 0; k < 6; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o); }
-        if (lane == 0 && (k < 2 || countWork)) { atomicAdd(totals + k, (unsigned long long)v[k]); }
+        if (lane == 0 && (k < 2 || COUNT)) { atomicAdd(totals + k, (unsigned long long)v[k]); }
     }
 }
 
@@ -818,7 +824,7 @@ __global__ void volumeReplayKernel(DScene scene, const ptc_ray *rays, const floa
         const ptc_ray r = rays[i];
         Rng rng; rng.initReplay(xi + (size_t)i * stride, stride);
         VolumeWork work = {0, 0, {0, 0}, {0, 0}};
-        const V3 L = volumeRadiance(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), rng, start, last, &work);
+        const V3 L = volumeRadiance<false>(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), rng, start, last, &work);
         rgb[3 * i] = L.x; rgb[3 * i + 1] = L.y; rgb[3 * i + 2] = L.z;
     }
 }
@@ -964,7 +970,7 @@ int ptc_create(int device, ptc_ctx **out)
     ctx->gridLogic = ctx->numSMs * std::max(perSM, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, materialKernel<PTC_PLASTIC>, 128, 0);
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumePathKernel, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumePathKernel<false>, 128, 0);
     ctx->gridVolume = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
     *out = ctx;
@@ -1442,7 +1448,8 @@ static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint3
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->volumeCursor, 0, sizeof(uint32_t), stream));
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
-            volumePathKernel<<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals, ctx->countTraversal);
+            if (ctx->countTraversal) { volumePathKernel<true><<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals); }
+            else { volumePathKernel<false><<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals); }
         }
         {
             StageTimer t(ctx, stream, STAGE_OTHER);

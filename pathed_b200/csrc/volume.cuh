@@ -35,13 +35,14 @@ __device__ __forceinline__ void eventsSort(VolumeEvents &ev) // std::sort by t, 
 }
 
 // One triangle of the pending group with the filter applied before a hit is accepted (traversalTriangle + occlusionFilter)
+template <bool COUNT>
 __device__ __forceinline__ bool filteredTriangle(const DScene &s, TraversalState &st, VolumeEvents &ev, TraverseCounters &tc)
 {
     const uint32_t bit = highestBit(st.tgroup.y);
     st.tgroup.y &= ~(1u << bit);
     const float4 *tri = s.bvh.triangles + (size_t)(st.tgroup.x + bit) * 3;
     const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
-    tc.tris++;
+    if (COUNT) { tc.tris++; }
     float T, U, V, absDen;
     if (!triangleTestRaw(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
     const float t = divIeee(T, absDen);
@@ -60,7 +61,7 @@ __device__ __forceinline__ bool filteredTriangle(const DScene &s, TraversalState
 // the sphere points, as in Embree's per-type acceleration structures).  Any hit: every container surface in the interval when
 // the ray is unoccluded -- order-independent.
 // counters (optional): inner-node visits and triangle tests, the same quantities the wavefront traversal counts
-template <bool ANY>
+template <bool ANY, bool COUNT = false>
 __device__ bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float tfar, RayHit &hit, VolumeEvents &ev, TraverseCounters *counters = nullptr)
 {
     TraverseCounters tc = {0, 0};
@@ -70,8 +71,8 @@ __device__ bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float
     bool stop = false;
     if (s.bvh.nNodes) {
         for (;;) {
-            traversalNode<true>(s.bvh, st, &tc);
-            while (st.tgroup.y) { if (filteredTriangle(s, st, ev, tc) && ANY) { stop = true; break; } }
+            traversalNode<COUNT>(s.bvh, st, &tc);
+            while (st.tgroup.y) { if (filteredTriangle<COUNT>(s, st, ev, tc) && ANY) { stop = true; break; } }
             if (stop || traversalPop(st)) { break; }
         }
     }
@@ -98,17 +99,18 @@ __device__ bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float
     }
     eventsSort(ev);
     hit = st.hit;
-    if (counters) { counters->inner += tc.inner; counters->tris += tc.tris; }
+    if (COUNT && counters) { counters->inner += tc.inner; counters->tris += tc.tris; }
     return st.found;
 }
 
 // Closest hit / any hit of the plain queries on a scene that may hold containers: Scene::testIntersect passes
 // shouldIntersectPassthroughs = true (containers are ordinary hits), Scene::testOcclusion passes false (src/scene.cpp:369-370)
+template <bool COUNT = false>
 __device__ __forceinline__ bool sceneIntersect(const DScene &s, V3 O, V3 D, RayHit &h, TraverseCounters *counters = nullptr)
 {
     TraverseCounters tc = {0, 0};
-    const bool found = traverseBVH<false, true>(s.bvh, O.x, O.y, O.z, D.x, D.y, D.z, PTC_TNEAR, PTC_TFAR, h, &tc);
-    if (counters) { counters->inner += tc.inner; counters->tris += tc.tris; }
+    const bool found = traverseBVH<false, COUNT>(s.bvh, O.x, O.y, O.z, D.x, D.y, D.z, PTC_TNEAR, PTC_TFAR, h, &tc);
+    if (COUNT && counters) { counters->inner += tc.inner; counters->tris += tc.tris; }
     return found;
 }
 __device__ __forceinline__ bool sceneOccluded(const DScene &s, V3 O, V3 D, float maxT)
@@ -155,6 +157,7 @@ struct VolumeWork { uint32_t closestRays, shadowRays; TraverseCounters closest, 
 
 // VolumeHelper::directSampleLights, src/volume_helper.cpp:12-70: single scattering from a point inside `medium`
 // (isotropic phase function 1 / 4 pi, no sigma_s factor)
+template <bool COUNT>
 __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng &r, VolumeWork *work)
 {
     SurfSample ls;
@@ -165,7 +168,7 @@ __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng 
     const float dist = length(sd);
     RayHit h; VolumeEvents ev;
     work->shadowRays++;
-    if (traverseFiltered<true>(s, point, wi, PTC_TNEAR, dist - 1e-3f, h, ev, &work->shadow)) { return mk(0.f, 0.f, 0.f); }
+    if (traverseFiltered<true, COUNT>(s, point, wi, PTC_TNEAR, dist - 1e-3f, h, ev, &work->shadow)) { return mk(0.f, 0.f, 0.f); }
     const float pdf = solidAnglePdf(ls, point);
     const V3 lwo = -normalize(sd);
     V3 tr = mk(0.f, 0.f, 0.f);
@@ -176,6 +179,7 @@ __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng 
 }
 
 // VolumePathTracer::scatter -> HomogeneousMedium::integrate, src/volume_path_tracer.cpp:112-131, src/homogeneous_medium.cpp:36-66
+template <bool COUNT>
 __device__ V3 mediumScatter(const DScene &s, int32_t medium, V3 entry, V3 exit, Rng &r, VolumeWork *work)
 {
     if (medium < 0) { return mk(0.f, 0.f, 0.f); }
@@ -186,10 +190,11 @@ __device__ V3 mediumScatter(const DScene &s, int32_t medium, V3 entry, V3 exit, 
     const float sampleT = -logf(1 - xi) / sigmaT;
     if (sampleT >= distance) { return mk(0.f, 0.f, 0.f); }
     const V3 samplePoint = entry + normalize(travel) * sampleT;
-    return volumeDirectLights(s, medium, samplePoint, r, work);
+    return volumeDirectLights<COUNT>(s, medium, samplePoint, r, work);
 }
 
 // DirectLightingHelper::Ld, src/direct_lighting_helper.cpp:37-187
+template <bool COUNT>
 __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const BsdfSample &bs, Rng &r, VolumeWork *work)
 {
     const DMaterial &m = s.materials[i.material];
@@ -205,7 +210,7 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
             const float dist = length(ld);
             RayHit h; VolumeEvents ev;
             work->shadowRays++;
-            if (!traverseFiltered<true>(s, i.point, wi, PTC_TNEAR, dist - 1e-3f, h, ev, &work->shadow)) {
+            if (!traverseFiltered<true, COUNT>(s, i.point, wi, PTC_TNEAR, dist - 1e-3f, h, ev, &work->shadow)) {
                 const V3 tr = rayTransmission(s, i.point, wi, ev, medium);
                 const float pdf = solidAnglePdf(ls, i.point);
                 float brdfPDF;
@@ -220,7 +225,7 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
     { // directSampleBSDF, :139-187: the probe ray skips containers; an emitter counts from either side, no transmittance
         RayHit h; VolumeEvents ev; Isect bi;
         work->closestRays++;
-        const bool isHit = traverseFiltered<false>(s, i.point, bs.wi, PTC_TNEAR, PTC_TFAR, h, ev, &work->closest);
+        const bool isHit = traverseFiltered<false, COUNT>(s, i.point, bs.wi, PTC_TNEAR, PTC_TFAR, h, ev, &work->closest);
         if (isHit) { makeIsect(s, i.point, bs.wi, h, bi); }
         result = result + directBsdf(s, i.point, fabsf(dot(i.ns, bs.wi)), bs.wi, bs.pdf, bs.thr, bs.delta, isHit, &bi, false);
     }
@@ -229,12 +234,13 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
 
 // SampleIntegrator::samplePixel's body (src/sample_integrator.cpp:18-59, container branch included) + VolumePathTracer::L
 // (src/volume_path_tracer.cpp:14-95) for one primary ray; the caller has positioned `r` (Philox: vertex 0 consumed the jitter)
+template <bool COUNT>
 __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int last, VolumeWork *work)
 {
     V3 color = mk(0.f, 0.f, 0.f);
     RayHit h;
     work->closestRays++;
-    if (!sceneIntersect(s, O, D, h, &work->closest)) { return envRadiance(s, D); }
+    if (!sceneIntersect<COUNT>(s, O, D, h, &work->closest)) { return envRadiance(s, D); }
     Isect lastI;
     makeIsect(s, O, D, h, lastI);
     if (checkCounts(start, last, 0)) {
@@ -243,7 +249,7 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
         if (m.type == PTC_PASSTHROUGH) { // what lies behind the container, attenuated (src/sample_integrator.cpp:35-51)
             VolumeEvents ev; RayHit vh;
             work->closestRays++;
-            const bool vHit = traverseFiltered<false>(s, O, D, PTC_TNEAR, PTC_TFAR, vh, ev, &work->closest);
+            const bool vHit = traverseFiltered<false, COUNT>(s, O, D, PTC_TNEAR, PTC_TFAR, vh, ev, &work->closest);
             const V3 tr = rayTransmission(s, O, D, ev, -1);
             if (vHit) {
                 Isect vi; makeIsect(s, O, D, vh, vi);
@@ -257,7 +263,7 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
     BsdfSample bs;
     bsdfSample(s.materials[lastI.material], lastI, r, bs);
     V3 result = mk(0.f, 0.f, 0.f);
-    if (checkCounts(start, last, 1)) { result = volumeLd(s, lastI, medium, bs, r, work); }
+    if (checkCounts(start, last, 1)) { result = volumeLd<COUNT>(s, lastI, medium, bs, r, work); }
     V3 modulation = mk(1.f, 1.f, 1.f);
     for (int bounce = 2; !checkDone(last, bounce); bounce++) {
         if (dot(lastI.wo, bs.wi) < 0.f) { // refraction: the medium changes (:42-50)
@@ -265,21 +271,21 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
             else { medium = -1; }
         }
         work->closestRays++;
-        if (!sceneIntersect(s, lastI.point, bs.wi, h, &work->closest)) { break; }
+        if (!sceneIntersect<COUNT>(s, lastI.point, bs.wi, h, &work->closest)) { break; }
         Isect bi;
         makeIsect(s, lastI.point, bs.wi, h, bi);
         const float invPDF = 1.f / bs.pdf;
         const float cosT = fabsf(dot(lastI.ns, bs.wi));
         modulation = modulation * ((bs.thr * cosT) * invPDF);
         r.beginVertex((uint32_t)bounce);
-        const V3 Ls = mediumScatter(s, medium, lastI.point, bi.point, r, work);
+        const V3 Ls = mediumScatter<COUNT>(s, medium, lastI.point, bi.point, r, work);
         result = result + Ls * modulation;
         if (medium >= 0) { modulation = modulation * mediumTransmittance(s, medium, lastI.point, bi.point); }
         if (isBlack(modulation)) { break; }
         bsdfSample(s.materials[bi.material], bi, r, bs);
         lastI = bi;
         if (checkCounts(start, last, bounce)) {
-            const V3 Ld = volumeLd(s, bi, medium, bs, r, work);
+            const V3 Ld = volumeLd<COUNT>(s, bi, medium, bs, r, work);
             result = result + Ld * modulation;
         }
     }

@@ -9,7 +9,8 @@ for defs in "$@"; do
   PTC_NVCC_DEFINES="$defs" python -c "from pathed_b200 import build as b; b.build_cuda(force=True); b.build_host(force=True)" >/dev/null 2>&1
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline ${SWEEP_BENCH_ARGS:-} 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.readlines()[-1]); s=d['stages']; r=d['roofline']
-print('%-60s value %7.1f  extend %7.2f shadow %7.2f shade %7.2f  inner/ray %.2f tri/ray %.2f' % ('$defs', d['value'], s['extend_ms'], s['shadow_ms'], s['shade_ms'], r['inner_visits_per_ray'], r['triangle_tests_per_ray']))" | tee -a gpurun_out/sweep.txt
+d=json.loads(sys.stdin.readlines()[-1]); s=d['stages'] or {}; r=d['roofline'] or {}
+stage=' '.join('%s %8.2f' % (k[:-3], s[k]) for k in ('extend_ms', 'shadow_ms', 'shade_ms', 'volume_kernel_ms') if k in s)
+print('%-60s value %7.1f  %s  inner/ray %.2f tri/ray %.2f' % ('$defs', d['value'], stage, r.get('inner_visits_per_ray', 0), r.get('triangle_tests_per_ray', 0)))" | tee -a gpurun_out/sweep.txt
 done
 python -c "from pathed_b200 import build as b; b.build_cuda(force=True); b.build_host(force=True)" >/dev/null 2>&1
