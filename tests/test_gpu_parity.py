@@ -332,6 +332,33 @@ def test_full_size_dragon_properties():
     assert np.array_equal(half, img)
 
 
+@pytest.mark.parametrize("name,width,height,spp", [("cornell", 512, 512, 64), ("cornell_glass", 512, 512, 64), ("mis", 768, 512, 64),
+                                                   ("teapot", 1920, 1080, 16), ("cornell_medium", 512, 512, 64)])
+def test_full_size_configs_block_average_to_the_reference_images(name, width, height, spp):
+    """The other BASELINE configurations at their full resolutions, through the same size-independent property as the dragon
+    test: with the box pixel filter a b x b block average of the full-size render estimates the same integral as one pixel of
+    the reference's small converged image (b^2 * spp samples per block)."""
+    import os
+    from parity import GOLDEN
+    cfg = SCENES[name]
+    g = np.load(os.path.join(GOLDEN, "image_%s.npz" % name))
+    ref = g["image"].astype(np.float32)
+    rh, rw = ref.shape[:2]
+    b = width // rw
+    assert b * rw == width and b * rh == height
+    ctx = gpu_scene(name, width, height)
+    ctx.reset_stats()
+    img = ctx.render(77, 0, spp, 0, cfg["last_bounce"])
+    st = ctx.stats()
+    assert np.isfinite(img).all() and st.samples == width * height * spp
+    blocks = img.reshape(rh, b, rw, b, 3).sum((1, 3)) / np.float32(b * b * spp)
+    e = rel_mse(blocks, ref)
+    per_block = b * b * spp
+    print(name, "%dx%d, %d spp: block-averaged (%d samples per block) vs reference render (%d spp): relMSE" % (width, height, spp, per_block, int(g["spp"])), e)
+    assert e <= 1e-3 * cfg.get("image_noise", 1.0) * (4096.0 / per_block + 4096.0 / float(g["spp"])), e
+    assert abs(blocks.mean() - ref.mean()) <= 0.02 * ref.mean()
+
+
 @pytest.mark.parametrize("name", ["cornell_glass", "dragon", "mis"])
 def test_device_bvh_builder_matches_host_builder(name):
     """the BVH built on the device (Morton sort + PLOC + wide collapse kernels, the default) and the host
