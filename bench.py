@@ -6,7 +6,7 @@
 Workload (config.workload): scenes/dragon.json, 1024 x 1024, PathTracer, startBounce 0, lastBounce 10 — the
 configuration the north-star target is quoted on (">= 100x the reference CPU Msamples/s on dragon.json on 1 B200").
 One step = one pass of the hot path over one batch = SPP_PER_STEP samples per pixel over the whole image
-(16 spp -> 16.8 M samples; 16 steps = the config's 256 spp).  Synthetic data: the dragon mesh and the environment
+(64 spp -> 67.1 M samples = one wave of the wavefront; 4 steps = the config's 256 spp).  Synthetic data: the dragon mesh and the environment
 map are seeded procedural stand-ins (tools/make_assets.py) because the reference's assets/ are not in its repo.
 
 Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + synchronize on both sides):
@@ -17,7 +17,7 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
             triangle tests (SURVEY 8(d)) / mean launch duration measured live with CUDA events on the launch stream;
             `traffic` = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
-L2: every wave streams its path state (16.8 M paths x 157 B = 2.6 GB, plus queues) through each stage, far more than the
+L2: every wave streams its path state (67.1 M paths x 157 B = 10.5 GB, plus queues) through each stage, far more than the
 126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~55 MB) is meant to be L2-resident.
 
 Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
@@ -47,7 +47,7 @@ WORKLOADS = {
     # participating medium in a Passthrough container, VolumePathTracer (one-thread-per-path kernel)
     "cornell-medium": dict(scene="scenes/cornell-medium.json", width=512, height=512, last_bounce=10, integrator="VolumePathTracer"),
 }
-SPP_PER_STEP = 16
+SPP_PER_STEP = 64  # one wave of 2^26 paths at 1024^2: the late bounces' queues stay long enough to fill 148 SMs (profiles/README.md)
 REF_SPP_PER_STEP = 1  # the CPU reference does ~0.5 Msamples/s: one spp of 1024^2 is ~2 s
 
 
@@ -182,7 +182,7 @@ def main():
     tst0 = ctx.stats()
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
-    ppw = args.paths_per_wave or (1 << 24)
+    ppw = args.paths_per_wave or (1 << 26)
     n_pix = width * height
     accum = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream

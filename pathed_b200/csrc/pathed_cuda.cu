@@ -875,7 +875,8 @@ struct ptc_ctx {
     int numSMs = 148;
     int gridTraverse = 0, gridShade = 0, gridLogic = 0, gridSimple = 0;
     // options / stats
-    int64_t pathsPerWave = 1 << 24; // 16.8 M paths x 157 B = 2.6 GB of path state per wave: long queues keep 148 SMs busy through the late bounces
+    int64_t pathsPerWave = 1 << 26; // 67 M paths x 157 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
+                                    // keep 148 SMs busy; measured 648 vs 613 Msamples/s against 2^24 on the dragon workload, 653 with 2^27
     bool stageTiming = false, countTraversal = false;
     int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
     float bvhBuildMs = 0.f; uint32_t bvhPlocIterations = 0;
