@@ -4,7 +4,8 @@ any library exporting the ABI (the CPU oracle in the CPU suite, the CUDA library
   test/transform_test.cpp:6-14   normalToWorldSpace(n, dir) maps (0,1,0) to n exactly          -> tangent_frame_maps_y_to_normal
   test/vector_test.cpp:6-14      Vector3::reflect                                              -> reflect_follows_the_source
   test_scenes/1_pixel_test.exr   one non-zero texel (row 239, col 753) in a 1000x500 map       -> one_pixel_environment_map
-test/camera_test.cpp pins Camera::calculatePixel, the light tracer's world->pixel mapping, which is not on the path;
+test/camera_test.cpp pins Camera::calculatePixel, the light tracer's world->pixel mapping, which is not on the path (and its
+"Cornell light" case, pixel x 57 / y 92, disagrees with src/camera.cpp:57-93 at this commit, which mirrors the film: x 42, y 7);
 Camera::generateRay is pinned by the compiled reference instead (tests/golden/scene_*.npz: cam_rays).
 """
 import numpy as np

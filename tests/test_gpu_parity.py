@@ -286,6 +286,35 @@ def test_media_edge_cases():
     assert (err.max(-1) < 1e-3).mean() >= 0.97
 
 
+def test_ragged_inputs_and_limits_match_oracle():
+    """Edge cases of the render call: a resolution that is not a multiple of the 8 x 4 path tiles (row-major slot order), one
+    sample, a window that starts after the first bounces, lastBounce = -1 (unbounded in the reference, src/bounce_controller.cpp:
+    20-25; capped at PTC_MAX_BOUNCES on both sides), zero samples, empty query batches, a mesh with no triangles."""
+    from pathed_b200 import PathedError, load_scene
+    from pathed_b200._binding import rays_array
+    cfg = SCENES["cornell_glass"]
+    for (w, h, spp, start, last) in [(37, 23, 3, 0, 10), (40, 22, 1, 2, 5), (16, 12, 2, 0, -1)]:
+        img = load_scene(cfg["scene"], w, h).render(9, 0, spp, start, last)
+        ref = oracle_scene(cfg["scene"], w, h).render(9, 0, spp, start, last)
+        err = np.abs(img - ref) / (np.abs(ref) + 1e-3 * max(ref.mean(), 1e-3))
+        assert (err.max(-1) < 1e-3).mean() >= 0.97, (w, h, spp, start, last)
+    ctx = load_scene(cfg["scene"], 16, 12)
+    before = np.full((12, 16, 3), 0.25, np.float32)
+    assert np.array_equal(ctx.render(1, 0, 0, 0, 10, accum=before.copy()), before)  # zero samples: radianceLookup untouched
+    with pytest.raises(PathedError):
+        ctx.render(1, 0, 1, 5, 2)  # startBounce > lastBounce
+    empty = rays_array(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert len(ctx.intersect(empty)) == 0 and len(ctx.occluded(empty, np.zeros(0, np.float32))) == 0 and len(ctx.intersect_full(empty)) == 0
+    bare = gpu_context()
+    m = bare.add_material(material_desc(dict(type=0, diffuse=(1, 1, 1))))
+    bare.add_triangle_mesh(np.zeros((0, 3), np.float32), None, None, np.zeros((0, 3), np.uint32), m)  # a geometry with no faces
+    bare.add_sphere((0, 0, 0), 1.0, m)
+    bare.set_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 0.5, 8, 8)
+    bare.commit()
+    hit = bare.intersect(rays_array([[0, 0, 5]], [[0, 0, -1]]))
+    assert hit["geom_id"][0] == 1 and abs(hit["t"][0] - 4.0) < 1e-5  # geometry ids follow the attach order, empty mesh included
+
+
 def test_empty_scene_renders_environment_only():
     ctx = gpu_context()
     env = np.zeros((8, 16, 4), np.float32)
