@@ -133,7 +133,7 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 #define PTC_POSTPONE_DIV 1000 /* off: measured slower on B200 (profiles/r01_sweep_postpone.txt) */
 #endif
 
-// 48 registers -> 10 resident CTAs per SM; forcing 12 or 16 CTAs (40 / 32 registers) spills and was measured slower
+// 64 registers -> 8 resident CTAs per SM (48 / 10 before the phase split); forcing 12 or 16 CTAs (40 / 32 registers) spills and was measured slower
 // (profiles/r01_sweep_occupancy.txt)
 #ifdef PTC_TRAVERSE_MIN_BLOCKS
 #define PTC_TRAVERSE_BOUNDS __launch_bounds__(128, PTC_TRAVERSE_MIN_BLOCKS)
