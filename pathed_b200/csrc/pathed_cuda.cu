@@ -329,7 +329,7 @@ __device__ __forceinline__ void cameraContainerTerm(const DScene &scene, float o
 
 // Runs between logic(0) and the material kernels of vertex 1, only for scenes with container surfaces: the camera ray and its
 // hit are still in the path state, and out[p] holds the camera-hit emission (0 for a Passthrough surface).
-__global__ void __launch_bounds__(128) containerKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const BounceCounters *bc)
+__global__ void __launch_bounds__(128) containerKernel(const __grid_constant__ DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const BounceCounters *bc)
 {
     const uint32_t n = bc->extendCount;
     if (!checkCounts(wp.startBounce, wp.lastBounce, 0)) { return; }
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
 #define PTC_VOLUME_MIN_BLOCKS 16
 #endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128, PTC_VOLUME_MIN_BLOCKS) volumePathKernel(DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals)
+__global__ void __launch_bounds__(128, PTC_VOLUME_MIN_BLOCKS) volumePathKernel(const __grid_constant__ DScene scene, float4 *out, WaveParams wp, uint32_t *cursor, unsigned long long *totals)
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     const uint32_t lane = threadIdx.x & 31u;
@@ -644,7 +644,7 @@ __device__ __forceinline__ void exportEvents(const VolumeEvents &ev, uint32_t i,
 }
 
 // Scene::testVolumetricIntersect, src/scene.cpp:225-353
-__global__ void intersectVolumetricKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
+__global__ void intersectVolumetricKernel(const __grid_constant__ DScene scene, const ptc_ray *rays, uint32_t n, ptc_isect *out, uint32_t *nEvents, float *eventT, uint32_t *eventMedium)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
@@ -662,7 +662,7 @@ __global__ void intersectVolumetricKernel(DScene scene, const ptc_ray *rays, uin
     }
 }
 
-__global__ void occludedKernel(DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded)
+__global__ void occludedKernel(const __grid_constant__ DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
@@ -671,7 +671,7 @@ __global__ void occludedKernel(DScene scene, const ptc_ray *rays, const float *m
 }
 
 // Scene::testVolumetricOcclusion, src/scene.cpp:383-424 (events are reported for unoccluded rays only)
-__global__ void occludedVolumetricKernel(DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, uint32_t *nEvents,
+__global__ void occludedVolumetricKernel(const __grid_constant__ DScene scene, const ptc_ray *rays, const float *maxT, uint32_t n, uint8_t *occluded, uint32_t *nEvents,
                                          float *eventT, uint32_t *eventMedium)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -760,7 +760,7 @@ __global__ void envRadianceKernel(DScene scene, const float *dirs, uint32_t n, f
 
 // samplePixel body + PathTracer::L as one sequential loop per path (test hook for the replayed random stream);
 // uses the same device functions as the wavefront stages
-__global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
+__global__ void radianceReplayKernel(const __grid_constant__ DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
@@ -818,7 +818,7 @@ __global__ void radianceReplayKernel(DScene scene, const ptc_ray *rays, const fl
     }
 }
 
-__global__ void volumeReplayKernel(DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
+__global__ void volumeReplayKernel(const __grid_constant__ DScene scene, const ptc_ray *rays, const float *xi, uint32_t stride, uint32_t n, int start, int last, float *rgb)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];

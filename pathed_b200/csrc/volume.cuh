@@ -61,8 +61,12 @@ __device__ __forceinline__ bool filteredTriangle(const DScene &s, TraversalState
 // the sphere points, as in Embree's per-type acceleration structures).  Any hit: every container surface in the interval when
 // the ray is unoccluded -- order-independent.
 // counters (optional): inner-node visits and triangle tests, the same quantities the wavefront traversal counts
+// Kept out of line on purpose (like the other building blocks marked PTC_VOLUME_CALL below): the one-thread-per-path kernel
+// reaches them from several places, and one copy of each keeps its code inside the instruction cache -- with everything inlined
+// the kernel stalled on instruction fetch (no_instruction: 68 warps per issue) and spilled 470 GB per launch.
+#define PTC_VOLUME_CALL __device__ __noinline__
 template <bool ANY, bool COUNT = false>
-__device__ bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float tfar, RayHit &hit, VolumeEvents &ev, TraverseCounters *counters = nullptr)
+PTC_VOLUME_CALL bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float tfar, RayHit &hit, VolumeEvents &ev, TraverseCounters *counters = nullptr)
 {
     TraverseCounters tc = {0, 0};
     TraversalState st;
@@ -106,7 +110,7 @@ __device__ bool traverseFiltered(const DScene &s, V3 O, V3 D, float tnear, float
 // Closest hit / any hit of the plain queries on a scene that may hold containers: Scene::testIntersect passes
 // shouldIntersectPassthroughs = true (containers are ordinary hits), Scene::testOcclusion passes false (src/scene.cpp:369-370)
 template <bool COUNT = false>
-__device__ __forceinline__ bool sceneIntersect(const DScene &s, V3 O, V3 D, RayHit &h, TraverseCounters *counters = nullptr)
+PTC_VOLUME_CALL bool sceneIntersect(const DScene &s, V3 O, V3 D, RayHit &h, TraverseCounters *counters = nullptr)
 {
     TraverseCounters tc = {0, 0};
     const bool found = traverseBVH<false, COUNT>(s.bvh, O.x, O.y, O.z, D.x, D.y, D.z, PTC_TNEAR, PTC_TFAR, h, &tc);
@@ -126,6 +130,20 @@ __device__ __forceinline__ int32_t internalMedium(const DScene &s, uint32_t prim
     if (!s.nMedia) { return -1; }
     const uint32_t geom = (prim & PTC_SPHERE_FLAG) ? __ldg(s.sphereIds + (prim & ~PTC_SPHERE_FLAG)).x : __ldg(s.primIds + prim).x;
     return __ldg(s.geomMedium + geom);
+}
+
+// out-of-line copies of the shading library's building blocks for the volume integrator
+PTC_VOLUME_CALL void volIsect(const DScene &s, V3 O, V3 D, const RayHit &h, Isect &out) { makeIsect(s, O, D, h, out); }
+PTC_VOLUME_CALL void volBsdfSample(const DScene &s, const Isect &i, Rng &r, BsdfSample &out) { bsdfSample(s.materials[i.material], i, r, out); }
+PTC_VOLUME_CALL V3 volBsdfEval(const DScene &s, const Isect &i, V3 wi, float &pdf) { return bsdfEval(s.materials[i.material], i, wi, pdf); }
+PTC_VOLUME_CALL const DLight *volSampleLights(const DScene &s, V3 ref, Rng &r, SurfSample &out) { return sampleDirectLights(s, ref, r, out); }
+PTC_VOLUME_CALL V3 volLightRadiance(const DScene &s, const DLight *light, V3 towardsLight)
+{
+    return __ldg(&light->kind) == 2 ? envRadiance(s, towardsLight) : mk(__ldg(&light->emit[0]), __ldg(&light->emit[1]), __ldg(&light->emit[2]));
+}
+PTC_VOLUME_CALL V3 volDirectBsdf(const DScene &s, V3 point, float cosTheta, V3 wi, float pdf, V3 thr, bool delta, bool hit, const Isect *bi)
+{
+    return directBsdf(s, point, cosTheta, wi, pdf, thr, delta, hit, bi, false);
 }
 
 // HomogeneousMedium::transmittance, src/homogeneous_medium.cpp:13-17: util::exp(-sigmaT * |b - a|)
@@ -161,7 +179,7 @@ template <bool COUNT>
 __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng &r, VolumeWork *work)
 {
     SurfSample ls;
-    const DLight *light = sampleDirectLights(s, point, r, ls);
+    const DLight *light = volSampleLights(s, point, r, ls);
     const V3 sd = ls.point - point;
     const V3 wi = normalize(sd);
     if (dot(ls.normal, wi) >= 0.f) { return mk(0.f, 0.f, 0.f); }
@@ -174,7 +192,7 @@ __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng 
     V3 tr = mk(0.f, 0.f, 0.f);
     if (ev.count == 1) { tr = mediumTransmittance(s, medium, point, point + wi * ev.t[0]); }
     else if (ev.count == 2) { tr = mediumTransmittance(s, medium, point + wi * ev.t[0], point + wi * ev.t[1]); }
-    const V3 Le = __ldg(&light->kind) == 2 ? envRadiance(s, -lwo) : mk(__ldg(&light->emit[0]), __ldg(&light->emit[1]), __ldg(&light->emit[2]));
+    const V3 Le = volLightRadiance(s, light, -lwo);
     return (((Le * tr) * 1.f) / (float)(4.f * PTC_PI_D)) / pdf;
 }
 
@@ -203,7 +221,7 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
     V3 result = mk(0.f, 0.f, 0.f);
     if (!bs.delta) { // directSampleLights, :75-137
         SurfSample ls;
-        const DLight *light = sampleDirectLights(s, i.point, r, ls);
+        const DLight *light = volSampleLights(s, i.point, r, ls);
         const V3 ld = ls.point - i.point;
         const V3 wi = normalize(ld);
         if (!(dot(ls.normal, wi) >= 0.f)) {
@@ -214,10 +232,10 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
                 const V3 tr = rayTransmission(s, i.point, wi, ev, medium);
                 const float pdf = solidAnglePdf(ls, i.point);
                 float brdfPDF;
-                const V3 f = bsdfEval(m, i, wi, brdfPDF);
+                const V3 f = volBsdfEval(s, i, wi, brdfPDF);
                 const float w = (1 * pdf) / (1 * pdf + 1 * brdfPDF);
                 const V3 lwo = -normalize(ld);
-                const V3 Le = __ldg(&light->kind) == 2 ? envRadiance(s, -lwo) : mk(__ldg(&light->emit[0]), __ldg(&light->emit[1]), __ldg(&light->emit[2]));
+                const V3 Le = volLightRadiance(s, light, -lwo);
                 result = result + ((((Le * tr) * w) * f) * fabsf(dot(i.ns, wi))) / pdf;
             }
         }
@@ -226,8 +244,8 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
         RayHit h; VolumeEvents ev; Isect bi;
         work->closestRays++;
         const bool isHit = traverseFiltered<false, COUNT>(s, i.point, bs.wi, PTC_TNEAR, PTC_TFAR, h, ev, &work->closest);
-        if (isHit) { makeIsect(s, i.point, bs.wi, h, bi); }
-        result = result + directBsdf(s, i.point, fabsf(dot(i.ns, bs.wi)), bs.wi, bs.pdf, bs.thr, bs.delta, isHit, &bi, false);
+        if (isHit) { volIsect(s, i.point, bs.wi, h, bi); }
+        result = result + volDirectBsdf(s, i.point, fabsf(dot(i.ns, bs.wi)), bs.wi, bs.pdf, bs.thr, bs.delta, isHit, &bi);
     }
     return result;
 }
@@ -242,7 +260,7 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
     work->closestRays++;
     if (!sceneIntersect<COUNT>(s, O, D, h, &work->closest)) { return envRadiance(s, D); }
     Isect lastI;
-    makeIsect(s, O, D, h, lastI);
+    volIsect(s, O, D, h, lastI);
     if (checkCounts(start, last, 0)) {
         const DMaterial &m = s.materials[lastI.material];
         if (m.emitter && !(dot(lastI.n, lastI.wo) < 0.f)) { color = mk(m.emit[0], m.emit[1], m.emit[2]); }
@@ -252,20 +270,26 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
             const bool vHit = traverseFiltered<false, COUNT>(s, O, D, PTC_TNEAR, PTC_TFAR, vh, ev, &work->closest);
             const V3 tr = rayTransmission(s, O, D, ev, -1);
             if (vHit) {
-                Isect vi; makeIsect(s, O, D, vh, vi);
+                Isect vi; volIsect(s, O, D, vh, vi);
                 const DMaterial &vm = s.materials[vi.material];
                 color = color + mk(vm.emit[0], vm.emit[1], vm.emit[2]) * tr;
             } else { color = color + envRadiance(s, D) * tr; }
         }
     }
+    // VolumePathTracer::L as ONE loop (the reference peels the first vertex, src/volume_path_tracer.cpp:21-31; with modulation = 1
+    // there `result += Ld * modulation` is the same value), so that every building block has a single call site
     int32_t medium = -1;
+    V3 result = mk(0.f, 0.f, 0.f), modulation = mk(1.f, 1.f, 1.f);
     r.beginVertex(1);
-    BsdfSample bs;
-    bsdfSample(s.materials[lastI.material], lastI, r, bs);
-    V3 result = mk(0.f, 0.f, 0.f);
-    if (checkCounts(start, last, 1)) { result = volumeLd<COUNT>(s, lastI, medium, bs, r, work); }
-    V3 modulation = mk(1.f, 1.f, 1.f);
-    for (int bounce = 2; !checkDone(last, bounce); bounce++) {
+    for (int bounce = 1;;) {
+        BsdfSample bs;
+        volBsdfSample(s, lastI, r, bs);
+        if (checkCounts(start, last, bounce)) {
+            const V3 Ld = volumeLd<COUNT>(s, lastI, medium, bs, r, work);
+            result = result + Ld * modulation;
+        }
+        bounce++;
+        if (checkDone(last, bounce)) { break; }
         if (dot(lastI.wo, bs.wi) < 0.f) { // refraction: the medium changes (:42-50)
             if (dot(lastI.n, bs.wi) < 0.f) { medium = internalMedium(s, lastI.prim); }
             else { medium = -1; }
@@ -273,7 +297,7 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
         work->closestRays++;
         if (!sceneIntersect<COUNT>(s, lastI.point, bs.wi, h, &work->closest)) { break; }
         Isect bi;
-        makeIsect(s, lastI.point, bs.wi, h, bi);
+        volIsect(s, lastI.point, bs.wi, h, bi);
         const float invPDF = 1.f / bs.pdf;
         const float cosT = fabsf(dot(lastI.ns, bs.wi));
         modulation = modulation * ((bs.thr * cosT) * invPDF);
@@ -282,12 +306,7 @@ __device__ V3 volumeRadiance(const DScene &s, V3 O, V3 D, Rng &r, int start, int
         result = result + Ls * modulation;
         if (medium >= 0) { modulation = modulation * mediumTransmittance(s, medium, lastI.point, bi.point); }
         if (isBlack(modulation)) { break; }
-        bsdfSample(s.materials[bi.material], bi, r, bs);
         lastI = bi;
-        if (checkCounts(start, last, bounce)) {
-            const V3 Ld = volumeLd<COUNT>(s, bi, medium, bs, r, work);
-            result = result + Ld * modulation;
-        }
     }
     return color + result;
 }
