@@ -1839,7 +1839,10 @@ int ptc_reset_stats(ptc_ctx *ctx)
 int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) { return PTC_ERR_INVALID; }
-    if (!strcmp(name, "paths_per_wave")) { if (value < 1024) { CTX_FAIL(ctx, PTC_ERR_INVALID, "paths_per_wave must be >= 1024"); } ctx->pathsPerWave = value; return PTC_OK; }
+    if (!strcmp(name, "paths_per_wave")) { // path indices are 32-bit
+        if (value < 1024 || value > (int64_t)1 << 30) { CTX_FAIL(ctx, PTC_ERR_INVALID, "paths_per_wave must be in [1024, 2^30]"); }
+        ctx->pathsPerWave = value; return PTC_OK;
+    }
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
     if (!strcmp(name, "bvh_builder")) { // before ptc_commit; 1 = device (default), 0 = host binned SAH
