@@ -17,7 +17,7 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
             triangle tests (SURVEY 8(d)) / mean launch duration measured live with CUDA events on the launch stream;
             `traffic` = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
-L2: every wave streams its path state (67.1 M paths x 157 B = 10.5 GB, plus queues) through each stage, far more than the
+L2: every wave streams its path state (67.1 M paths x 156 B = 10.5 GB incl. queues) through each stage, far more than the
 126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~55 MB) is meant to be L2-resident.
 
 Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
@@ -352,7 +352,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], width, height, w.get("integrator", "PathTracer"), last), "spp_per_step": spp,
                        "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 148 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
+                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 156 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
                        "scene_build_s": build_s,
                        "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
                                      "ms": tst0.bvh_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},

@@ -29,16 +29,27 @@ using namespace ptc;
 
 // ================================================================================================ device state
 #define PTC_MATERIAL_CLASSES 7 /* PTC_LAMBERTIAN .. PTC_PASSTHROUGH */
+// Fields that the stages always touch together share one 32-byte record (PTC_PAIRED_STATE): after the first bounces the
+// surviving paths are sparse in slot space, so every 16-byte field access costs a whole 32-byte sector -- pairing (origin,
+// direction), (hit, result) and (modulation, throughput) makes both halves of those sectors useful.  The accessors keep the
+// `pb.field[p]` spelling of a plain array.
+#ifndef PTC_PAIRED_STATE
+#define PTC_PAIRED_STATE 1
+#endif
+struct PairedField {
+    float4 *base;
+    __device__ __forceinline__ float4 &operator[](uint32_t p) const { return base[(PTC_PAIRED_STATE ? 2 : 1) * (size_t)p]; }
+};
 struct PathBuffers {
-    float4 *rayO, *rayD;   // current ray (origin = current vertex)
-    float4 *hit;           // t, u, v, prim bits
-    float4 *modPdf;        // modulation rgb, pdf of the BSDF sample that produced the ray
-    float4 *thrCos;        // BSDF sample throughput rgb, |n_s . wi|
-    float4 *result;        // L() accumulator rgb, w = flags
-    float4 *nee;           // pending light-sampling contribution (valid when the shadow ray is unoccluded)
+    PairedField rayO, rayD;   // current ray (origin = current vertex)
+    PairedField hit;          // t, u, v, prim bits
+    PairedField modPdf;       // modulation rgb, pdf of the BSDF sample that produced the ray
+    PairedField thrCos;       // BSDF sample throughput rgb, |n_s . wi|
+    PairedField result;       // L() accumulator rgb, w = flags
+    float4 *nee;           // pending light-sampling contribution rgb; w = 0 until the shadow stage finds the ray occluded (then 1):
+                           // the flag travels in the record the logic stage reads anyway instead of a separate sparse byte array
     float4 *shadowD;       // shadow ray direction, w = distance to the light sample
     float4 *out;           // per-sample radiance: camera-hit emission / environment, plus result at termination
-    uint8_t *occluded;
     uint32_t *extendQueue[2];
     uint32_t *shadowQueue;
     uint32_t *classQueue[PTC_MATERIAL_CLASSES]; // survivors of the logic stage, binned by material class (null: class absent from the scene)
@@ -294,7 +305,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             }
             if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
                 const bool found = traversalSpheres<ANY, FILTER>(scene.bvh, st);
-                if (ANY) { pb.occluded[p] = found ? 1 : 0; }
+                if (ANY) { if (found) { reinterpret_cast<float *>(pb.nee + p)[3] = 1.f; } }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
                 busy = false;
             }
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                 const V3 thr = mk(tc.x, tc.y, tc.z);
                 if (flags & FLAG_DIRECT) { // direct() of vertex k, src/path_tracer.cpp:79-111
                     V3 Ld = mk(0.f, 0.f, 0.f);
-                    if ((flags & FLAG_NEE) && !pb.occluded[p]) { const float4 ne = pb.nee[p]; Ld = Ld + mk(ne.x, ne.y, ne.z); }
+                    if (flags & FLAG_NEE) { const float4 ne = pb.nee[p]; if (ne.w == 0.f) { Ld = Ld + mk(ne.x, ne.y, ne.z); } }
                     if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
                         const float4 o4 = pb.rayO[p];
                         const V3 O = mk(o4.x, o4.y, o4.z);
@@ -875,7 +886,7 @@ struct ptc_ctx {
     int numSMs = 148;
     int gridTraverse = 0, gridShade = 0, gridLogic = 0, gridSimple = 0;
     // options / stats
-    int64_t pathsPerWave = 1 << 26; // 67 M paths x 157 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
+    int64_t pathsPerWave = 1 << 26; // 67 M paths x 156 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
                                     // keep 148 SMs busy; measured 648 vs 613 Msamples/s against 2^24 on the dragon workload, 653 with 2^27
     bool stageTiming = false, countTraversal = false;
     int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
@@ -1352,12 +1363,19 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
     PathBuffers &pb = ctx->paths;
-    float4 **f4[] = {&pb.rayO, &pb.rayD, &pb.hit, &pb.modPdf, &pb.thrCos, &pb.result, &pb.nee, &pb.shadowD, &pb.out};
+    float4 **f4[] = {&pb.nee, &pb.shadowD, &pb.out};
     for (float4 **slot : f4) {
         CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(float4)));
         ctx->pathAllocations.push_back(*slot);
     }
-    CUDA_TRY(ctx, cudaMalloc((void **)&pb.occluded, capacity)); ctx->pathAllocations.push_back(pb.occluded);
+    PairedField *pairs[3][2] = {{&pb.rayO, &pb.rayD}, {&pb.hit, &pb.result}, {&pb.modPdf, &pb.thrCos}};
+    for (auto &pair : pairs) { // one buffer per pair: interleaved records, or two plain arrays back to back
+        float4 *buffer = nullptr;
+        CUDA_TRY(ctx, cudaMalloc((void **)&buffer, (size_t)capacity * 2 * sizeof(float4)));
+        ctx->pathAllocations.push_back(buffer);
+        pair[0]->base = buffer;
+        pair[1]->base = PTC_PAIRED_STATE ? buffer + 1 : buffer + capacity;
+    }
     uint32_t **u32[] = {&pb.extendQueue[0], &pb.extendQueue[1], &pb.shadowQueue};
     for (uint32_t **slot : u32) {
         CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(uint32_t)));
