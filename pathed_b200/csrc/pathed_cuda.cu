@@ -1284,6 +1284,25 @@ int ptc_commit(ptc_ctx *ctx)
     s.bvh.nSpheres = (uint32_t)(spheres4.size() / 4);
     if ((rc = upload(ctx, (const float4 *)ctx->normals4.data(), ctx->normals4.size() / 4, &s.normals, A))) { return rc; }
     if ((rc = upload(ctx, (const float2 *)ctx->uvs2.data(), ctx->uvs2.size() / 2, &s.uvs, A))) { return rc; }
+    { // per-triangle shading records (shading.cuh: DScene::triShade); Ng = e2 x e1 with the fused multiply-subtracts of triangleNg
+        std::vector<float> rec((size_t)nPrims * 20, 0.f);
+        for (uint32_t p = 0; p < nPrims; p++) {
+            const uint32_t *ix = &ctx->prims4[4 * (size_t)p];
+            const float *v0 = &ctx->positions4[4 * (size_t)ix[0]], *v1 = &ctx->positions4[4 * (size_t)ix[1]], *v2 = &ctx->positions4[4 * (size_t)ix[2]];
+            const float e1x = v0[0] - v1[0], e1y = v0[1] - v1[1], e1z = v0[2] - v1[2];
+            const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+            float *r = &rec[(size_t)p * 20];
+            r[0] = fmaf(e2y, e1z, -(e2z * e1y)); r[1] = fmaf(e2z, e1x, -(e2x * e1z)); r[2] = fmaf(e2x, e1y, -(e2y * e1x));
+            memcpy(&r[3], &ix[3], sizeof(float));
+            for (int k = 0; k < 3; k++) {
+                const float *n = &ctx->normals4[4 * (size_t)ix[k]];
+                const float *t = &ctx->uvs2[2 * (size_t)ix[k]];
+                r[4 + 3 * k] = n[0]; r[5 + 3 * k] = n[1]; r[6 + 3 * k] = n[2];
+                r[13 + 2 * k] = t[0]; r[14 + 2 * k] = t[1];
+            }
+        }
+        if ((rc = upload(ctx, (const float4 *)rec.data(), rec.size() / 4, &s.triShade, A))) { return rc; }
+    }
     if ((rc = upload(ctx, (const uint2 *)ctx->primIds2.data(), ctx->primIds2.size() / 2, &s.primIds, A))) { return rc; }
     if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
     if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }

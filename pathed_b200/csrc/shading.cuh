@@ -62,6 +62,10 @@ struct DScene {
     const uint4 *prims;      // per triangle: i0, i1, i2, material
     const uint2 *primIds;    // per triangle: geomID, primID
     const uint2 *sphereIds;  // per sphere: geomID, material
+    // per triangle, everything Scene::testIntersect's post-processing needs in one 80-byte record (5 float4): unnormalised Ng as the
+    // traversal computes it + material | n0.xyz n1.x | n1.yz n2.xy | n2.z uv0.xy uv1.x | uv1.y uv2.xy.  Ten scattered sectors
+    // (index record, 3 positions, 3 normals, 3 uvs) become three contiguous ones; built at ptc_commit with the same arithmetic.
+    const float4 *triShade;
     const DMaterial *materials;
     const DLight *lights;
     uint32_t nLights;
@@ -168,6 +172,9 @@ __device__ __forceinline__ V3 toLocal(const Isect &i, V3 w)
     return mk(i.tx.x * w.x + i.tx.y * w.y + i.tx.z * w.z, i.ns.x * w.x + i.ns.y * w.y + i.ns.z * w.z, i.tz.x * w.x + i.tz.y * w.y + i.tz.z * w.z);
 }
 
+#ifndef PTC_FAT_TRIANGLES
+#define PTC_FAT_TRIANGLES 1
+#endif
 // geometric normal exactly as the traversal computed it (Embree returns Ng = e2 x e1 with fused msub)
 __device__ __forceinline__ V3 triangleNg(const DScene &s, uint32_t prim, uint4 &ix)
 {
@@ -191,12 +198,21 @@ __device__ __forceinline__ void makeIsect(const DScene &s, V3 O, V3 D, const Ray
         ngU = mk(nx, ny, nz);
         r.material = __ldg(s.sphereIds + slot).y;
     } else {
+#if PTC_FAT_TRIANGLES
+        const float4 *rec = s.triShade + (size_t)h.prim * 5;
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3), r4 = __ldg(rec + 4);
+        ngU = mk(r0.x, r0.y, r0.z);
+        uint4 ix; ix.w = __float_as_uint(r0.w);
+        const float4 n0 = make_float4(r1.x, r1.y, r1.z, 0.f), n1 = make_float4(r1.w, r2.x, r2.y, 0.f), n2 = make_float4(r2.z, r2.w, r3.x, 0.f);
+        const float2 t0 = make_float2(r3.y, r3.z), t1 = make_float2(r3.w, r4.x), t2 = make_float2(r4.y, r4.z);
+#else
         uint4 ix;
         ngU = triangleNg(s, h.prim, ix);
-        // rtcInterpolate0, ext/embree/kernels/common/scene_triangle_mesh.cpp:248-253: madd(w, p0, madd(u, p1, v * p2))
-        const float w = 1.0f - h.u - h.v;
         const float4 n0 = __ldg(s.normals + ix.x), n1 = __ldg(s.normals + ix.y), n2 = __ldg(s.normals + ix.z);
         const float2 t0 = __ldg(s.uvs + ix.x), t1 = __ldg(s.uvs + ix.y), t2 = __ldg(s.uvs + ix.z);
+#endif
+        // rtcInterpolate0, ext/embree/kernels/common/scene_triangle_mesh.cpp:248-253: madd(w, p0, madd(u, p1, v * p2))
+        const float w = 1.0f - h.u - h.v;
         ns = mk(fmaf(w, n0.x, fmaf(h.u, n1.x, h.v * n2.x)), fmaf(w, n0.y, fmaf(h.u, n1.y, h.v * n2.y)), fmaf(w, n0.z, fmaf(h.u, n1.z, h.v * n2.z)));
         r.u = fmaf(w, t0.x, fmaf(h.u, t1.x, h.v * t2.x));
         r.v = fmaf(w, t0.y, fmaf(h.u, t1.y, h.v * t2.y));
