@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(128) containerKernel(const __grid_constant__ D
     }
 }
 
+#ifndef PTC_LAZY_DIRECTION
+#define PTC_LAZY_DIRECTION 1
+#endif
 __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;
@@ -368,11 +371,18 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
         uint32_t p = 0;
         if (item < n) {
             p = queue[item];
+#if PTC_LAZY_DIRECTION
+            // the ray direction is only needed for environment misses and emitter hits: a surviving ordinary hit never reads it
+            const float4 h4 = pb.hit[p];
+#else
             const float4 d4 = pb.rayD[p], h4 = pb.hit[p];
+#endif
             float4 res4 = pb.result[p];
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
+#if !PTC_LAZY_DIRECTION
             const V3 D = mk(d4.x, d4.y, d4.z);
+#endif
             const uint32_t prim = __float_as_uint(h4.w);
             const bool isHit = prim != PTC_MISS;
             uint32_t material = 0;
@@ -386,6 +396,10 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
             if (k == 0) {
                 // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59
                 V3 color = mk(0.f, 0.f, 0.f);
+#if PTC_LAZY_DIRECTION
+                V3 D = mk(0.f, 0.f, 0.f);
+                if (!isHit || emitter) { const float4 d4 = pb.rayD[p]; D = mk(d4.x, d4.y, d4.z); }
+#endif
                 if (!isHit) { color = envRadiance(scene, D); alive = false; }
                 else if (emitter && checkCounts(wp.startBounce, wp.lastBounce, 0)) {
                     const float4 o4 = pb.rayO[p];
@@ -404,6 +418,10 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                     V3 Ld = mk(0.f, 0.f, 0.f);
                     if (flags & FLAG_NEE) { const float4 ne = pb.nee[p]; if (ne.w == 0.f) { Ld = Ld + mk(ne.x, ne.y, ne.z); } }
                     if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
+#if PTC_LAZY_DIRECTION
+                        const float4 d4 = pb.rayD[p];
+                        const V3 D = mk(d4.x, d4.y, d4.z);
+#endif
                         const float4 o4 = pb.rayO[p];
                         const V3 O = mk(o4.x, o4.y, o4.z);
                         Isect bi;
