@@ -46,9 +46,9 @@ struct PathBuffers {
     PairedField modPdf;       // modulation rgb, pdf of the BSDF sample that produced the ray
     PairedField thrCos;       // BSDF sample throughput rgb, |n_s . wi|
     PairedField result;       // L() accumulator rgb, w = flags
-    float4 *nee;           // pending light-sampling contribution rgb; w = 0 until the shadow stage finds the ray occluded (then 1):
+    PairedField nee;       // pending light-sampling contribution rgb; w = 0 until the shadow stage finds the ray occluded (then 1):
                            // the flag travels in the record the logic stage reads anyway instead of a separate sparse byte array
-    float4 *shadowD;       // shadow ray direction, w = distance to the light sample
+    PairedField shadowD;   // shadow ray direction, w = distance to the light sample (one record with nee: written together)
     float4 *out;           // per-sample radiance: camera-hit emission / environment, plus result at termination
     uint32_t *extendQueue[2];
     uint32_t *shadowQueue;
@@ -305,7 +305,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             }
             if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
                 const bool found = traversalSpheres<ANY, FILTER>(scene.bvh, st);
-                if (ANY) { if (found) { reinterpret_cast<float *>(pb.nee + p)[3] = 1.f; } }
+                if (ANY) { if (found) { reinterpret_cast<float *>(&pb.nee[p])[3] = 1.f; } }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
                 busy = false;
             }
@@ -1400,12 +1400,12 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
     PathBuffers &pb = ctx->paths;
-    float4 **f4[] = {&pb.nee, &pb.shadowD, &pb.out};
+    float4 **f4[] = {&pb.out};
     for (float4 **slot : f4) {
         CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(float4)));
         ctx->pathAllocations.push_back(*slot);
     }
-    PairedField *pairs[3][2] = {{&pb.rayO, &pb.rayD}, {&pb.hit, &pb.result}, {&pb.modPdf, &pb.thrCos}};
+    PairedField *pairs[4][2] = {{&pb.rayO, &pb.rayD}, {&pb.hit, &pb.result}, {&pb.modPdf, &pb.thrCos}, {&pb.nee, &pb.shadowD}};
     for (auto &pair : pairs) { // one buffer per pair: interleaved records, or two plain arrays back to back
         float4 *buffer = nullptr;
         CUDA_TRY(ctx, cudaMalloc((void **)&buffer, (size_t)capacity * 2 * sizeof(float4)));
