@@ -77,3 +77,20 @@ def check_volumetric_queries(o, g):
             k = min(int(g[tag + "_n_events"][i]), want.shape[1])
             want[i, :k] = np.sort(want[i, :k])
         assert frac_within(et[both], want[both], floor=1e-4)[0] >= 0.999
+
+
+def check_container_known_answer(api):
+    """scenes/cornell-medium.json, the ray down the view axis from the camera: the container box (z = +-0.9, Passthrough + medium)
+    is an ordinary hit for Scene::testIntersect (t = 5.9) and is skipped by the volumetric queries, which report the glass sphere
+    (radius 0.3 at the origin of the xz plane: t = 6.5) and the two container faces as volume events (t = 5.9 and 7.7: both lie in
+    front of the back wall, the closest TRIANGLE hit, which is all Embree's per-type traversal knows when it meets them)."""
+    rays = rays_array([[0.0, 1.0, 6.8]], [[0.0, 0.0, -1.0]])
+    assert abs(float(api.intersect_full(rays)["t"][0]) - 5.9) < 1e-5
+    isects, ne, et, em = api.intersect_volumetric(rays)
+    assert isects["hit"][0] == 1 and abs(float(isects["t"][0]) - 6.5) < 1e-5
+    assert ne[0] == 2 and abs(float(et[0, 0]) - 5.9) < 1e-5 and abs(float(et[0, 1]) - 7.7) < 1e-5 and (em[0, :2] == 0).all()
+    occ, ne, et, em = api.occluded_volumetric(rays, np.array([6.0], np.float32))
+    assert occ[0] == 0 and ne[0] == 1 and abs(float(et[0, 0]) - 5.9) < 1e-5      # up to just before the sphere: one event
+    occ, ne, et, em = api.occluded_volumetric(rays, np.array([7.0], np.float32))
+    assert occ[0] == 1 and ne[0] == 0                                              # the glass sphere occludes
+    assert api.occluded(rays, np.array([6.0], np.float32))[0] == 0               # Scene::testOcclusion skips the container too

@@ -5,7 +5,7 @@ import pytest
 
 from golden_inputs import BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, material_desc, ray_inputs, uniform_floats
 from oracle_binding import oracle_scene
-from parity import REL, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
+from parity import REL, check_container_known_answer, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -236,6 +236,11 @@ def test_error_statuses():
         ctx.add_material(textured)  # only Lambertian / Plastic take a texture
     with pytest.raises(PathedError):
         ctx.commit()  # no camera
+
+
+def test_container_known_answer():
+    from pathed_b200 import load_scene
+    check_container_known_answer(load_scene("scenes/cornell-medium.json", 32, 32))
 
 
 def test_media_edge_cases():

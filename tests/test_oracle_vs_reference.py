@@ -5,7 +5,7 @@ import pytest
 
 from golden_inputs import BSDF_CONFIGS, SCENES, bsdf_inputs, light_inputs, material_desc, ray_inputs, uniform_floats
 from oracle_binding import oracle_context, oracle_lib, oracle_scene
-from parity import REL, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
+from parity import REL, check_container_known_answer, check_volumetric_queries, frac_within, golden, make_isects, rel_err, rel_mse, to_rays
 
 import ctypes
 
@@ -147,3 +147,7 @@ def test_volumetric_queries_match_reference(name):
     """Scene::testVolumetricOcclusion / testVolumetricIntersect (src/scene.cpp:225-353, :383-424): container surfaces are
     filtered out (src/scene.cpp:42-84) and leave volume events"""
     check_volumetric_queries(oracle_scene(SCENES[name]["scene"], SCENES[name]["width"], SCENES[name]["height"]), golden("scene_" + name))
+
+
+def test_container_known_answer():
+    check_container_known_answer(oracle_scene("scenes/cornell-medium.json", 32, 32))
