@@ -93,3 +93,43 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([os.path.join(PKG_DIR, "pathed"), _job(tmp_path), "--root", REPO_ROOT], capture_output=True, text=True)
     assert r.returncode == 1 and "Failed to create device" in r.stdout
     assert os.path.exists(str(tmp_path / "out" / "report.json"))  # Job::init ran first, as in app/main.cpp:66-73
+
+
+def _scene(tmp_path, models, media=None):
+    scene = {"sensor": {"lookAt": {"origin": ["0", "0", "5"], "target": ["0", "0", "0"], "up": ["0", "1", "0"]}, "fov": "40"},
+             "models": models}
+    if media is not None:
+        scene["media"] = media
+    path = str(tmp_path / "scene.json")
+    json.dump(scene, open(path, "w"))
+    return path
+
+
+def test_parser_media_and_internal_medium(tmp_path):
+    """parseMedia + `internal_medium` + the passthrough bsdf (src/scene_parser.cpp:202-229, :324-343, :503-514, :593-594) through
+    the C++ host parser, fed to the CPU checker: a Passthrough sphere that encloses a medium is skipped by Scene::testOcclusion and
+    leaves a volume event; the same sphere with an UNKNOWN medium name gets no medium (the reference's map default-constructs a
+    null pointer) and is an ordinary occluder; a later medium with the same name replaces the earlier one."""
+    from oracle_binding import oracle_context
+    from pathed_b200 import SceneFile
+    from pathed_b200._binding import PASSTHROUGH, rays_array
+    media = [{"name": "gas", "type": "homogeneous", "sigma_t": ["9", "9", "9"]},
+             {"name": "gas", "type": "homogeneous", "sigma_t": ["0.5", "0.5", "0.5"], "sigma_s": ["0.25", "0.25", "0.25"]}]
+    ball = lambda medium: {"type": "sphere", "center": ["0", "0", "0"], "radius": "1", "internal_medium": medium, "bsdf": {"type": "passthrough"}}
+    rays = rays_array([[0, 0, 5]], [[0, 0, -1]])
+    far = np.array([20.0], np.float32)
+
+    sf = SceneFile(_scene(tmp_path, [ball("gas")], media), 8, 8, root=str(tmp_path))
+    assert sf.counts() == {"geometries": 1, "triangles": 0, "spheres": 1, "materials": 1} and sf.material(0).type == PASSTHROUGH
+    o = sf.feed(oracle_context())
+    assert o.occluded(rays, far)[0] == 0                      # the container is not an occluder ...
+    occ, ne, et, em = o.occluded_volumetric(rays, far)
+    assert occ[0] == 0 and ne[0] == 1 and abs(et[0, 0] - 4.0) < 1e-5 and em[0, 0] == 0   # ... it leaves one event (near side only)
+    assert abs(float(o.intersect_full(rays)["t"][0]) - 4.0) < 1e-5                      # Scene::testIntersect does hit it
+
+    o = SceneFile(_scene(tmp_path, [ball("no-such-medium")], media), 8, 8, root=str(tmp_path)).feed(oracle_context())
+    assert o.occluded(rays, far)[0] == 1                      # no medium: the filter lets the hit stand
+    assert o.occluded_volumetric(rays, far)[1][0] == 0
+
+    with pytest.raises(PathedError):
+        SceneFile(_scene(tmp_path, [ball("fog")], [{"name": "fog", "type": "heterogeneous", "filename": "x.vol", "albedo": "1"}]), 8, 8, root=str(tmp_path))
