@@ -15,14 +15,17 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
             framebuffer inside the timed region), i.e. what Integrator::run's sampleImage loop would call
   roofline  the extend (closest-hit traversal) kernel: algorithmic bytes per launch from counted node visits and
             triangle tests (SURVEY 8(d)) / mean launch duration measured live with CUDA events on the launch stream;
-            `traffic` = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
+            `traffic` = DRAM bytes per launch of the same kernel from the ncu capture of THIS build (profiles/traffic.json carries
+            the hash of the CUDA sources it was taken from; a capture of another build is reported as null, never scaled)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
 L2: every wave streams its path state (67.1 M paths x 156 B = 10.5 GB incl. queues) through each stage, far more than the
 126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~55 MB) is meant to be L2-resident.
 
 Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
-indices of every pixel, Philox-keyed by (pixel, sample, bounce)); per step one NCCL reduce of the fp32 framebuffer to
-rank 0.  Per-GPU work is fixed as N grows ("weak").
+indices of every pixel, Philox-keyed by (pixel, sample, bounce)); every rank's framebuffer stays in its HBM and keeps
+accumulating, per step one NCCL reduce of a staging copy to rank 0 (pathed_b200.distributed.reduce_cumulative).
+Default "weak": per-GPU work is fixed as N grows (spp_per_step samples per pixel per rank and step).  `--scaling strong`:
+the step is the whole BASELINE job (dragon: 256 spp, teapot: 1024 spp) split over the ranks.
 """
 import argparse
 import json
@@ -49,6 +52,7 @@ WORKLOADS = {
 }
 SPP_PER_STEP = 64  # one wave of 2^26 paths at 1024^2: the late bounces' queues stay long enough to fill 148 SMs (profiles/README.md)
 REF_SPP_PER_STEP = 1  # the CPU reference does ~0.5 Msamples/s: one spp of 1024^2 is ~2 s
+STRONG_JOB_SPP = {"dragon": 256, "teapot": 1024}  # --scaling strong: one step = the whole job BASELINE.json names for the scene
 
 
 def measured_peak():
@@ -106,34 +110,104 @@ def run_reference(workload, steps, warmup, spp_per_step=REF_SPP_PER_STEP):
             cmd += ["--warmup", job("warmup", warmup * spp_per_step)]
         # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core
         env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
-        out = subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stderr[-4000:])
+            raise RuntimeError("pathed_ref_headless exited with %d (stderr above)" % proc.returncode)
+        out = proc.stdout
     line = [l for l in out.splitlines() if l.startswith("REF_RESULT")][-1]
     r = json.loads(line[len("REF_RESULT "):])
     r["spp_per_step"] = spp_per_step
     return r
 
 
+def ensure_reference_inputs():
+    """scenes/, assets/ and test_scenes/ are generated (git- and gpurun-ignored): a fresh box has none until
+    tools/make_assets.py ran.  Where /root/reference is mounted the compiled reference is (re)built as well."""
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_assets.py")], stdout=sys.stderr)
+    binary = os.path.join(ROOT, "oracle", "_ref", "pathed_ref_headless")
+    if not os.path.exists(binary) and os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "ref", "build_ref.sh")], stdout=sys.stderr)
+
+
+def workload_config(args, world):
+    """`config` of the JSON line: a pure function of the command line, so that both arms print the same object"""
+    w = WORKLOADS[args.workload]
+    n_pix = w["width"] * w["height"]
+    ppw = args.paths_per_wave or (1 << 26)
+    spp_rank = rank_spp(args, world)
+    waves = max(1, -(-spp_rank // max(1, ppw // n_pix)))
+    if world > 1:
+        parallelism = "spp-split x%d (%s) + one NCCL reduce of the fp32 framebuffer per step" % (world, args.scaling)
+    else:
+        parallelism = "single GPU"
+    return {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], w["width"], w["height"], w.get("integrator", "PathTracer"), w["last_bounce"]),
+            "spp_per_step": step_spp(args, world), "spp_per_rank_and_step": spp_rank, "scaling": args.scaling, "parallelism": parallelism,
+            "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d wave(s) per step" % (min(n_pix * spp_rank, ppw) * 156 / 1e6, waves)}
+
+
+def rank_spp(args, world):
+    if args.scaling == "strong":
+        return max(1, step_spp(args, world) // world)
+    return args.spp_per_step
+
+
+def step_spp(args, world):
+    """samples per pixel one step adds to the image, over all ranks"""
+    if args.scaling == "strong":
+        return args.spp_per_step if args.spp_per_step_given else STRONG_JOB_SPP.get(args.workload, 256)
+    return args.spp_per_step * world
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     w = WORKLOADS[args.workload]
+    ensure_reference_inputs()
     r = run_reference(args.workload, args.steps, args.warmup)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pathed_ref_headless is not built"}))
         return 0
     value = r["msamples_per_s"]
-    sample = "%d spp of %dx%d (%d steps x %d spp), %d OpenMP threads" % (r["spp"], w["width"], w["height"], args.steps, r["spp_per_step"], r["threads"])
+    sample = "each step = %d spp of %dx%d (a bounded sample of the workload; throughput per sample does not depend on spp): %d spp in %d steps, " \
+             "unmodified reference + Embree 3.6.0, %d OpenMP threads" % (r["spp_per_step"], w["width"], w["height"], r["spp"], args.steps, r["threads"])
     print(json.dumps({
         "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["render_wall_s"] * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r["render_wall_s"] * 1e3 / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], w["width"], w["height"], w.get("integrator", "PathTracer"), w["last_bounce"]),
-                   "spp_per_step": r["spp_per_step"]},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": r["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
+
+
+def source_hash():
+    """identifies the build a profile was taken from: sha256 over the CUDA sources"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "pathed_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def profile_facts(workload):
+    """ncu-derived per-ray facts of the extend kernel (profiles/traffic.json, written by tools/ncu_traffic.py from a capture of the
+    bench command).  Only a capture of THIS build counts; anything else is reported as stale instead of being scaled."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed"
+    t = json.load(open(path))
+    if t.get("workload") != workload:
+        return None, "the committed ncu capture is of workload %s" % t.get("workload")
+    if t.get("source_hash") != source_hash():
+        return None, "the committed ncu capture is of another build (%s, this build %s)" % (t.get("source_hash"), source_hash())
+    return t, t.get("source")
 
 
 def main():
@@ -143,11 +217,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dragon", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
+    ap.add_argument("--spp-per-step", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: spp-per-step samples per pixel per rank and step; strong: one step = the whole BASELINE job split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--paths-per-wave", type=int, default=0, help="override the library's wave size (paths resident per wave)")
     ap.add_argument("--bvh-builder", type=int, default=1, choices=[0, 1], help="1: device builder (default), 0: host binned-SAH builder")
     args = ap.parse_args()
+    args.spp_per_step_given = args.spp_per_step is not None
+    if args.spp_per_step is None:
+        args.spp_per_step = SPP_PER_STEP
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
@@ -174,7 +253,8 @@ def main():
     from pathed_b200 import load_scene
     w = WORKLOADS[args.workload]
     width, height, last = w["width"], w["height"], w["last_bounce"]
-    spp = args.spp_per_step
+    spp = rank_spp(args, world)          # samples per pixel THIS rank renders per step
+    total_spp = spp * world              # samples per pixel one step adds to the image
     t0 = time.time()
     ctx = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder},
                      integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
@@ -182,19 +262,20 @@ def main():
     tst0 = ctx.stats()
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
-    ppw = args.paths_per_wave or (1 << 26)
     n_pix = width * height
-    accum = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")
+    local = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")    # this rank's cumulative radianceLookup
+    staging = torch.zeros_like(local) if distributed else None                     # what the per-step reduce works on
     stream = torch.cuda.current_stream().cuda_stream
     seed = 0x5EED
 
-    from pathed_b200.distributed import reduce_framebuffer, sample_block
+    from pathed_b200.distributed import reduce_cumulative, reduce_framebuffer, sample_block
 
     def step_device(i):
         # global sample indices of this step: [i*world*spp, (i+1)*world*spp); this rank takes its contiguous block
         first, count = sample_block(i, rank, world, spp)
-        ctx.render_device(seed, first, count, 0, last, accum.data_ptr(), stream)
-        reduce_framebuffer(accum, dst=0)
+        ctx.render_device(seed, first, count, 0, last, local.data_ptr(), stream)
+        if distributed:
+            reduce_cumulative(local, staging, dst=0)  # rank 0's staging = the image of every sample rendered so far
 
     def timed(fn, steps):
         if distributed:
@@ -220,41 +301,59 @@ def main():
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = timed(step_device, args.steps)
+    ms = timed(lambda i: step_device(i + args.warmup), args.steps)
     st = ctx.stats()
     launches = int(st.kernel_launches)
     rays = int(st.closest_rays + st.shadow_rays)
-    samples_total = float(n_pix) * spp * args.steps * world
+    samples_total = float(n_pix) * total_spp * args.steps
     value = samples_total / (ms * 1e-3) * 1e-6
+    # the multi-rank image is checked, not only timed: rank 0's reduced image = mean radiance of every rank's samples
+    image_check = None
+    if distributed:
+        mean_local = torch.tensor([float(local.double().mean())], device="cuda", dtype=torch.float64)
+        dist.all_reduce(mean_local, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            got, want = float(staging.double().mean()), float(mean_local.item())
+            image_check = {"reduced_mean": got, "sum_of_rank_means": want, "spp": (args.steps + args.warmup) * total_spp}
+            assert abs(got - want) <= 1e-4 * abs(want) + 1e-9, image_check
 
-    # ---- e2e: host radianceLookup through ptc_render (H2D + D2H of the framebuffer inside the timed region)
-    # N > 1: every rank makes the same host-buffer call, then the per-rank host framebuffers are summed on rank 0:
-    # pinned host -> device, NCCL reduce, device -> pinned host (all inside the timed region)
+    # ---- e2e: the reference-facing call with a HOST radianceLookup (accumulated, not overwritten: upload, add, download).
+    # N = 1: ptc_render.  N > 1: every rank renders its sample block into a cleared device buffer, one NCCL reduce brings the step's
+    # sum to rank 0, which uploads the host accumulator from pinned memory, adds and downloads -- one H2D + one D2H of the
+    # framebuffer per step on rank 0, nothing through the host on the other ranks
     host_accum = np.zeros((height, width, 3), np.float32)
-    pinned = torch.zeros(height * width * 3, dtype=torch.float32).pin_memory() if distributed else None
-    staged = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda") if distributed else None
+    fb_bytes = n_pix * 3 * 4
+    if distributed:
+        stepbuf = torch.zeros_like(local)
+        pinned = torch.zeros(height * width * 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+        total = torch.zeros_like(local) if rank == 0 else None
 
     def step_host(i):
-        if distributed:
-            host_accum.fill(0.0)
-        ctx.render(seed, sample_block(i, rank, world, spp)[0], spp, 0, last, accum=host_accum)
-        if distributed:
-            pinned.copy_(torch.from_numpy(host_accum.reshape(-1)))
-            staged.copy_(pinned, non_blocking=True)
-            reduce_framebuffer(staged, dst=0)
-            if rank == 0:
-                pinned.copy_(staged)
-            torch.cuda.synchronize()
+        if not distributed:
+            ctx.render(seed, sample_block(i, rank, world, spp)[0], spp, 0, last, accum=host_accum)
+            return
+        stepbuf.zero_()
+        first, count = sample_block(i, rank, world, spp)
+        ctx.render_device(seed, first, count, 0, last, stepbuf.data_ptr(), stream)
+        reduce_framebuffer(stepbuf, dst=0)
+        if rank == 0:
+            total.copy_(pinned, non_blocking=True)
+            total.add_(stepbuf)
+            pinned.copy_(total, non_blocking=True)
+        torch.cuda.synchronize()
 
     for i in range(3):
         step_host(i)
     if distributed:
         dist.barrier()
+    torch.cuda.synchronize()
     t_start = time.perf_counter()
     e2e_device_ms = 0.0
     for i in range(args.steps):
-        step_host(i)
-        e2e_device_ms += ctx.stats().last_render_ms
+        step_host(i + 3)
+        if not distributed:
+            e2e_device_ms += ctx.stats().last_render_ms
+    torch.cuda.synchronize()
     e2e_wall_ms = (time.perf_counter() - t_start) * 1e3
     e2e_ms = torch.tensor([max(e2e_wall_ms, e2e_device_ms)], device="cuda")
     if distributed:
@@ -273,13 +372,13 @@ def main():
         ctx.set_option("stage_timing", 1)
         ctx.reset_stats()
         for i in range(args.steps):
-            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+            ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         tst = ctx.stats()
         ctx.set_option("stage_timing", 0)
         ctx.set_option("count_traversal", 1)
         ctx.reset_stats()
         for i in range(args.steps):
-            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+            ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         cst = ctx.stats()
         ctx.set_option("count_traversal", 0)
         total_bytes = 48.0 * cst.closest_rays + 33.0 * cst.shadow_rays + 80.0 * (cst.extend_inner_visits + cst.shadow_inner_visits) + \
@@ -301,14 +400,14 @@ def main():
         ctx.set_option("stage_timing", 1)
         ctx.reset_stats()
         for i in range(args.steps):
-            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+            ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         tst = ctx.stats()
         ctx.set_option("stage_timing", 0)
         ctx.set_option("count_traversal", 1)
         ctx.reset_stats()
         count_steps = min(args.steps, 2)
         for i in range(count_steps):
-            ctx.render_device(seed, i * world * spp, spp, 0, last, accum.data_ptr(), stream)
+            ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         cst = ctx.stats()
         ctx.set_option("count_traversal", 0)
         # algorithmic bytes per extend ray: 32 B ray + 16 B hit record + 80 B per inner node + 48 B per triangle test
@@ -317,20 +416,29 @@ def main():
         bytes_per_launch = per_ray * extend_rays_per_launch
         ms_per_launch = tst.extend_ms / max(tst.extend_launches, 1)
         achieved = bytes_per_launch / (ms_per_launch * 1e-3) * 1e-9
-        traffic, traffic_source = None, None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and args.workload == "dragon":
-            t = json.load(open(tpath))
-            # measured per ray under ncu on this workload; scaled to the rays one launch processes here
-            traffic = t["extend_dram_bytes_per_ray"] * extend_rays_per_launch
-            traffic_source = t["source"]
+        facts, facts_source = profile_facts(args.workload)
+        traffic = facts["extend_dram_bytes_per_ray"] * extend_rays_per_launch if facts else None
+        l2_peak = None
+        lpath = os.path.join(ROOT, "profiles", "l2_peak.json")
+        if os.path.exists(lpath):
+            l2_peak = json.load(open(lpath))
         total_stage = tst.extend_ms + tst.shadow_ms + tst.shade_ms + tst.other_ms
         roofline = {"bound": "hbm", "kernel": "traverseKernel<false> (extend: closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_note,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": facts_source, "peak_source": peak_note,
                     "bytes_per_ray": per_ray, "inner_visits_per_ray": cst.extend_inner_visits / max(cst.closest_rays, 1),
                     "triangle_tests_per_ray": cst.extend_triangle_tests / max(cst.closest_rays, 1),
                     "rays_per_launch": extend_rays_per_launch, "ms_per_launch": ms_per_launch,
-                    "note": "algorithmic bytes: the BVH (%.1f MB) is L2-resident, so this exceeds DRAM traffic" % (tst.bvh_bytes / 1e6)}
+                    "limiter": "instruction issue, then L2->L1 bandwidth: the BVH (%.1f MB) is L2-resident, so `achieved` (algorithmic bytes, the contract's "
+                               "definition) exceeds the DRAM traffic and the HBM ceiling is not the wall this kernel runs into" % (tst.bvh_bytes / 1e6)}
+        if facts:
+            roofline["issue_active"] = facts.get("extend_issue_active")
+            roofline["lanes_per_instruction"] = facts.get("extend_lanes_per_instruction")
+            if l2_peak and facts.get("extend_l2_bytes_per_ray"):
+                l2_rate = facts["extend_l2_bytes_per_ray"] * extend_rays_per_launch / (ms_per_launch * 1e-3) * 1e-9
+                roofline["l2_gbs"] = l2_rate
+                roofline["l2_peak_gbs"] = l2_peak["l2_read_gbs"]
+                roofline["l2_frac"] = l2_rate / l2_peak["l2_read_gbs"]
+                roofline["l2_peak_source"] = l2_peak.get("source")
         ext_counts, sh_counts = ctx.wave_counts(last + 2)
         stages = {"last_wave_extend_rays": ext_counts, "last_wave_shadow_rays": sh_counts, "extend_ms": tst.extend_ms, "shadow_ms": tst.shadow_ms, "shade_ms": tst.shade_ms, "other_ms": tst.other_ms,
                   "extend_share": tst.extend_ms / max(total_stage, 1e-9), "extend_grays_per_s": tst.closest_rays / max(tst.extend_ms, 1e-9) * 1e-6,
@@ -345,21 +453,19 @@ def main():
                              % (r["spp"], width, height, r["threads"], r["render_wall_s"])}
 
     if rank == 0:
-        fb_bytes = n_pix * 3 * 4
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], width, height, w.get("integrator", "PathTracer"), last), "spp_per_step": spp,
-                       "parallelism": "spp-split x%d + NCCL reduce of the fp32 framebuffer" % world if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d waves per step" % (min(n_pix * spp, ppw) * 156 / 1e6, max(1, -(-spp // max(1, ppw // n_pix)))),
-                       "scene_build_s": build_s,
-                       "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
-                                     "ms": tst0.bvh_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world),
+            "setup": {"scene_build_s": build_s,
+                      "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
+                                    "ms": tst0.bvh_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},
             "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
         }
+        if image_check:
+            line["multi_gpu_image_check"] = image_check
         print(json.dumps(line))
     if distributed:
         dist.barrier()

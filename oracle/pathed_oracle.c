@@ -1117,7 +1117,8 @@ typedef struct { uint64_t closest, shadow; } counts_t;
 /* PathTracer::directSampleLights, src/path_tracer.cpp:113-165 */
 static v3 direct_lights(orc_ctx *c, const isect_t *i, const bsdf_sample_t *bs, rng_t *r, counts_t *n)
 {
-    if (bs->delta) { return V(0, 0, 0); }
+    /* no light at all: m_lights[0] of an empty vector in the reference (undefined, Q18); defined as "no direct lighting", as on the device */
+    if (bs->delta || c->n_lights == 0) { return V(0, 0, 0); }
     const material_t *m = &c->materials[i->material];
     const light_sample_t ls = sample_direct_lights(c, i->point, r);
     const v3 ld = vsub(ls.s.point, i->point);
@@ -1207,6 +1208,7 @@ static v3 ray_transmission(const orc_ctx *c, v3 O, v3 D, const events_t *ev, int
 /* VolumeHelper::directSampleLights, src/volume_helper.cpp:12-70 */
 static v3 volume_direct_lights(orc_ctx *c, int medium, v3 point, rng_t *r, counts_t *n)
 {
+    if (c->n_lights == 0) { return V(0, 0, 0); }
     const light_sample_t ls = sample_direct_lights(c, point, r);
     const v3 sd = vsub(ls.s.point, point);
     const v3 wi = vnorm(sd);
@@ -1246,7 +1248,7 @@ static v3 volume_ld(orc_ctx *c, const isect_t *i, int medium, const bsdf_sample_
     if (m->d.type == PTC_PASSTHROUGH) { return V(0, 0, 0); }
     if (!black(V(m->d.emit[0], m->d.emit[1], m->d.emit[2]))) { return V(0, 0, 0); }
     v3 result = V(0, 0, 0);
-    if (!bs->delta) { /* directSampleLights, :75-137 */
+    if (!bs->delta && c->n_lights != 0) { /* directSampleLights, :75-137 */
         const light_sample_t ls = sample_direct_lights(c, i->point, r);
         const v3 ld = vsub(ls.s.point, i->point);
         const v3 wi = vnorm(ld);

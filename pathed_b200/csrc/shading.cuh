@@ -35,6 +35,31 @@ __device__ __forceinline__ bool isBlack(V3 c) { return c.x == 0.f && c.y == 0.f 
 __device__ __forceinline__ bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(v, lo)); }      // include/util.h:39-41
 
+// ------------------------------------------------------------------------------------------------ host-matched libm
+// Directions go through the host's libm in the reference (sinf / cosf of an azimuth, logf / atanf of a random number), and several
+// quantities downstream are ill-conditioned in the direction: D(wh) of a narrow lobe (tan^2 = (1 - y^2) / y^2 moves by 1e-7 / theta^2 per
+// ulp of y), the triangle a bounce ray lands on.  glibc's float sinf / cosf / logf return the correctly rounded value for 98.7 - 99.3 %
+// of their inputs (measured against the rounded double result; they are evaluated in double), expf for 99.94 %; libdevice's float
+// versions are only within 1 - 2 ulp.  So the sampling code calls the double-precision functions and rounds once (PTC_HOST_TRIG 1):
+// sampled directions are then bit-identical to the reference's for ~97 % of the samples instead of about half.  atanf, acosf, atan2f
+// and tanf of glibc are not correctly rounded often enough (84 - 96 %) for this to pin them; atanf still gains, the rest stay float.
+#ifndef PTC_HOST_TRIG
+#define PTC_HOST_TRIG 1
+#endif
+#if PTC_HOST_TRIG
+__device__ __forceinline__ float sinHost(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float cosHost(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float logHost(float x) { return (float)log((double)x); }
+__device__ __forceinline__ float atanHost(float x) { return (float)atan((double)x); }
+__device__ __forceinline__ float expHost(float x) { return (float)exp((double)x); }
+#else
+__device__ __forceinline__ float sinHost(float x) { return sinf(x); }
+__device__ __forceinline__ float cosHost(float x) { return cosf(x); }
+__device__ __forceinline__ float logHost(float x) { return logf(x); }
+__device__ __forceinline__ float atanHost(float x) { return atanf(x); }
+__device__ __forceinline__ float expHost(float x) { return expf(x); }
+#endif
+
 // ------------------------------------------------------------------------------------------------ scene
 struct DMaterial {
     int32_t type, distribution, albedoKind, emitter;
@@ -266,7 +291,7 @@ __device__ __forceinline__ void cartToSph(V3 c, float &phi, float &theta) // src
 }
 __device__ __forceinline__ V3 sphToCart(float phi, float cosTheta, float sinTheta) // :26-32
 {
-    return mk(sinTheta * cosf(phi), cosTheta, sinTheta * sinf(phi));
+    return mk(sinTheta * cosHost(phi), cosTheta, sinTheta * sinHost(phi));
 }
 
 __device__ __forceinline__ V3 cosineSample(Rng &r) // src/monte_carlo.cpp:24-41
@@ -274,7 +299,7 @@ __device__ __forceinline__ V3 cosineSample(Rng &r) // src/monte_carlo.cpp:24-41
     const float xi1 = r.next();
     const float rad = sqrtf(xi1);
     const float phi = (float)(2 * PTC_PI_D * (double)r.next());
-    return mk(rad * cosf(phi), sqrtf(1.f - xi1), rad * sinf(phi));
+    return mk(rad * cosHost(phi), sqrtf(1.f - xi1), rad * sinHost(phi));
 }
 
 // pow(c / 255.f, 2.2f) for the 256 byte values, tabulated by the host's powf at ptc_commit (bit-identical to the reference's
@@ -318,7 +343,7 @@ __device__ __forceinline__ float mfD(const DMaterial &m, V3 wh) // src/beckmann.
     const float cos4 = cos2 * cos2;
     if (m.distribution == PTC_BECKMANN) {
         const float cp = tfCosPhi(wh), sp = tfSinPhi(wh);
-        const float num = expf(-tan2 * (divIeee(cp * cp, alpha2) + divIeee(sp * sp, alpha2)));
+        const float num = expHost(-tan2 * (divIeee(cp * cp, alpha2) + divIeee(sp * sp, alpha2)));
         const float den = (float)(PTC_PI_D * (double)alpha2 * (double)cos4);
         return num / den;
     }
@@ -354,7 +379,7 @@ __device__ __forceinline__ V3 mfSampleWh(const DMaterial &m, Rng &r) // src/beck
     if (m.distribution == PTC_BECKMANN) {
         const float phi = (float)((double)r.next() * PTC_PI_D * (double)2.f); // phi is drawn first
         const float xi = r.next();
-        float logXi = logf(xi);
+        float logXi = logHost(xi);
         if (isinf(logXi)) { logXi = 0.f; }
         const float tan2 = -m.alpha * m.alpha * logXi;
         const float cosT = 1.f / sqrtf(1.f + tan2);
@@ -362,9 +387,9 @@ __device__ __forceinline__ V3 mfSampleWh(const DMaterial &m, Rng &r) // src/beck
         return sphToCart(phi, cosT, sinT);
     }
     const float xi1 = r.next(), xi2 = r.next();
-    const float theta = atanf((m.alpha * sqrtf(xi1)) / sqrtf(1.f - xi1));
+    const float theta = atanHost((m.alpha * sqrtf(xi1)) / sqrtf(1.f - xi1));
     const float phi = PTC_TWO_PI_F * xi2;
-    return sphToCart(phi, cosf(theta), sinf(theta));
+    return sphToCart(phi, cosHost(theta), sinHost(theta));
 }
 
 __device__ __forceinline__ V3 lambertF(const DMaterial &m, const Isect &i, V3 wiW, float &pdf) // src/lambertian.cpp:16-41
@@ -407,7 +432,7 @@ __device__ __forceinline__ V3 bsdfEval(const DMaterial &m, const Isect &i, V3 wi
         cartToSph(lwi, phiI, thetaI); cartToSph(lwo, phiO, thetaO);
         const float alpha = fmaxf(thetaI, thetaO), beta = fminf(thetaI, thetaO);
         pdf = lwi.y * PTC_INV_PI;
-        const float thr = PTC_INV_PI * (m.sigmaA + m.sigmaB * fmaxf(0.f, cosf(phiI - phiO)) * sinf(alpha) * tanf(beta));
+        const float thr = PTC_INV_PI * (m.sigmaA + m.sigmaB * fmaxf(0.f, cosHost(phiI - phiO)) * sinHost(alpha) * tanf(beta));
         return mk(m.diffuse[0] * thr, m.diffuse[1] * thr, m.diffuse[2] * thr);
     }
     case PTC_MICROFACET: return microfacetF(m, i, wiW, pdf);
@@ -533,7 +558,7 @@ __device__ void sphereSample(const DLight &l, V3 ref, Rng &r, SurfSample &s) // 
         const float z = 1 - 2 * r.next();
         const float rr = sqrtf(fmaxf(0.f, 1 - z * z));
         const float phi = (float)(2 * PTC_PI_D * (double)r.next());
-        const V3 v = mk(rr * cosf(phi), rr * sinf(phi), z);
+        const V3 v = mk(rr * cosHost(phi), rr * sinHost(phi), z);
         s.point = center + v * radius; s.normal = normalize(v);
         s.invPDF = (float)(4 * PTC_PI_D * (double)radius * (double)radius); s.measure = 1;
         return;
@@ -611,7 +636,7 @@ __device__ float envPdf(const DScene &s, V3 dir) // EnvironmentLight::emitPDF, s
     const int ts = min((int)floorf(thetaC * s.envH), s.envH - 1);
     const float tp = cdfPdf(s.envThetaCdf, s.envThetaEmpty != 0, ts);
     const float pp = cdfPdf(s.envPhiCdf + (size_t)ts * s.envW, __ldg(s.envPhiEmpty + ts) != 0, ps);
-    return (float)((double)(tp * pp * s.envW * s.envH) / ((double)(sinf(theta) * PTC_TWO_PI_F) * PTC_PI_D));
+    return (float)((double)(tp * pp * s.envW * s.envH) / ((double)(sinHost(theta) * PTC_TWO_PI_F) * PTC_PI_D));
 }
 __device__ void envSample(const DScene &s, V3 ref, Rng &r, SurfSample &out) // src/environment_light.cpp:82-105
 {
@@ -622,8 +647,8 @@ __device__ void envSample(const DScene &s, V3 ref, Rng &r, SurfSample &out) // s
     const float thetaC = (ts + 0.5f) / s.envH;
     const float phi = phiC * PTC_TWO_PI_F;
     const float theta = (float)((double)thetaC * PTC_PI_D);
-    const float pdf = (float)((double)(tp * pp * s.envW * s.envH) / ((double)(sinf(theta) * PTC_TWO_PI_F) * PTC_PI_D));
-    const V3 dir = xfVec(s.envM2W, sphToCart(phi, cosf(theta), sinf(theta)));
+    const float pdf = (float)((double)(tp * pp * s.envW * s.envH) / ((double)(sinHost(theta) * PTC_TWO_PI_F) * PTC_PI_D));
+    const V3 dir = xfVec(s.envM2W, sphToCart(phi, cosHost(theta), sinHost(theta)));
     out.point = ref + dir * 10000.f; out.normal = dir * -1.f; out.invPDF = 1.f / pdf; out.measure = 0;
 }
 
@@ -690,7 +715,9 @@ template <int TYPE = -1>
 __device__ __forceinline__ bool directLightsSetup(const DScene &s, const DMaterial &m, const Isect &i, const BsdfSample &bs, Rng &r,
                                                   V3 &contribution, V3 &shadowDir, float &shadowMaxT)
 {
-    if (bs.delta) { return false; }
+    // a scene without any light: Scene::sampleDirectLights indexes m_lights[0] of an empty vector in the reference (undefined, Q18);
+    // defined here as "no direct lighting"
+    if (bs.delta || s.nLights == 0u) { return false; }
     SurfSample ls;
     const DLight *light = sampleDirectLights(s, i.point, r, ls);
     const V3 ld = ls.point - i.point;

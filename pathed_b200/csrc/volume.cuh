@@ -151,7 +151,7 @@ __device__ __forceinline__ V3 mediumTransmittance(const DScene &s, int32_t mediu
 {
     const float4 st = __ldg(s.media + 2 * medium);
     const float d = length(b - a);
-    return mk(expf(-st.x * d), expf(-st.y * d), expf(-st.z * d));
+    return mk(expHost(-st.x * d), expHost(-st.y * d), expHost(-st.z * d));
 }
 
 // VolumeHelper::rayTransmission, src/volume_helper.cpp:72-123 (current = the medium the path is in, -1 = none)
@@ -178,6 +178,7 @@ struct VolumeWork { uint32_t closestRays, shadowRays; TraverseCounters closest, 
 template <bool COUNT>
 __device__ V3 volumeDirectLights(const DScene &s, int32_t medium, V3 point, Rng &r, VolumeWork *work)
 {
+    if (s.nLights == 0u) { return mk(0.f, 0.f, 0.f); } // no light to sample (undefined in the reference, Q18): no in-scattered light
     SurfSample ls;
     const DLight *light = volSampleLights(s, point, r, ls);
     const V3 sd = ls.point - point;
@@ -205,7 +206,7 @@ __device__ V3 mediumScatter(const DScene &s, int32_t medium, V3 entry, V3 exit, 
     const V3 travel = exit - entry;
     const float distance = length(travel);
     const float xi = r.next();
-    const float sampleT = -logf(1 - xi) / sigmaT;
+    const float sampleT = -logHost(1 - xi) / sigmaT;
     if (sampleT >= distance) { return mk(0.f, 0.f, 0.f); }
     const V3 samplePoint = entry + normalize(travel) * sampleT;
     return volumeDirectLights<COUNT>(s, medium, samplePoint, r, work);
@@ -219,7 +220,7 @@ __device__ V3 volumeLd(const DScene &s, const Isect &i, int32_t medium, const Bs
     if (__ldg(&m.type) == PTC_PASSTHROUGH) { return mk(0.f, 0.f, 0.f); } // isContainer
     if (__ldg(&m.emitter)) { return mk(0.f, 0.f, 0.f); }
     V3 result = mk(0.f, 0.f, 0.f);
-    if (!bs.delta) { // directSampleLights, :75-137
+    if (!bs.delta && s.nLights != 0u) { // directSampleLights, :75-137 (no light at all: undefined in the reference, skipped here)
         SurfSample ls;
         const DLight *light = volSampleLights(s, i.point, r, ls);
         const V3 ld = ls.point - i.point;

@@ -38,8 +38,18 @@ def init_from_env(backend):
 
 
 def reduce_framebuffer(framebuffer, dst=0):
-    """Sum the per-rank framebuffers into rank `dst` (in place there; other ranks' buffers are left unspecified)."""
+    """Sum the per-rank framebuffers into rank `dst` (in place there; other ranks' buffers are left unspecified).
+    A buffer that went through this call must not be accumulated into again: rank `dst` now holds every rank's samples
+    (use reduce_cumulative for a framebuffer that keeps accumulating across steps)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(framebuffer, dst=dst, op=dist.ReduceOp.SUM)
     return framebuffer
+
+
+def reduce_cumulative(local, staging, dst=0):
+    """Per-step reduce of framebuffers that keep accumulating (radianceLookup +=, src/sample_integrator.cpp:61-63): every rank's
+    cumulative sum `local` is left untouched; its copy in `staging` is sum-reduced, so after the call `staging` on rank `dst` is the
+    image of ALL samples rendered so far by all ranks (a sum of cumulative sums = the cumulative sum of the per-step sums)."""
+    staging.copy_(local)
+    return reduce_framebuffer(staging, dst)

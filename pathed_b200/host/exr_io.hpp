@@ -1,7 +1,8 @@
 // OpenEXR scanline reader/writer covering what the reference does through tinyexr:
 //   LoadEXR  -> RGBA fp32           /root/reference/src/environment_light.cpp:23
 //   SaveEXRImageToFile, 3 x HALF, channel order B,G,R, no compression   src/image.cpp:80-154
-// Reads uncompressed / ZIPS / ZIP files with HALF or FLOAT channels; writes uncompressed files.
+// Reads uncompressed / RLE / ZIPS / ZIP / PIZ scanline files with HALF or FLOAT channels (every block header is range-checked);
+// writes uncompressed files.
 #pragma once
 
 #include <string>

@@ -42,6 +42,16 @@ def _worker(rank, world, port, out_dir):
         first, n = sample_block(step, r, w, 2)
         local = scene.render(77, first, n, 0, 4)
         fb += torch.from_numpy(local)
+    # the per-step pattern of bench.py: the cumulative framebuffer keeps accumulating, a staging copy is reduced every step
+    from pathed_b200.distributed import reduce_cumulative
+    cumulative = torch.zeros(24, 24, 3, dtype=torch.float32)
+    staging = torch.zeros_like(cumulative)
+    for step in range(2):
+        first, n = sample_block(step, r, w, 2)
+        cumulative += torch.from_numpy(scene.render(77, first, n, 0, 4))
+        reduce_cumulative(cumulative, staging, dst=0)
+        if r == 0:
+            np.save(os.path.join(out_dir, "per_step_%d.npy" % step), staging.numpy())
     reduce_framebuffer(fb, dst=0)
     if r == 0:
         np.save(os.path.join(out_dir, "reduced.npy"), fb.numpy())
@@ -62,3 +72,7 @@ def test_spp_split_and_reduce_match_single_rank(tmp_path):
     # same samples, different fp32 summation order
     assert np.allclose(reduced, single, rtol=1e-5, atol=1e-6)
     assert reduced.sum() > 0
+    # reduced every step without double counting (the N-rank image after k steps = the 1-rank image of the same samples)
+    orc = oracle_scene("scenes/cornell.json", 24, 24)
+    assert np.allclose(np.load(str(tmp_path / "per_step_0.npy")), orc.render(77, 0, 4, 0, 4), rtol=1e-5, atol=1e-6)
+    assert np.allclose(np.load(str(tmp_path / "per_step_1.npy")), single, rtol=1e-5, atol=1e-6)

@@ -416,3 +416,20 @@ def test_device_bvh_builder_matches_host_builder(name):
     shadow = to_rays(g["shadow_rays"])
     assert np.array_equal(dev.occluded(shadow, g["shadow_max_t"]), host.occluded(shadow, g["shadow_max_t"]))
     assert np.array_equal(dev.render(11, 0, 4, 0, cfg["last_bounce"]), host.render(11, 0, 4, 0, cfg["last_bounce"]))
+
+
+def test_scene_without_lights_renders_black():
+    """no emitter and no environment map: Scene::sampleDirectLights is undefined in the reference (m_lights[0] of an empty vector,
+    SURVEY Q18); the device path is defined -- no direct lighting, a finite black image -- and agrees with the oracle"""
+    from oracle_binding import oracle_context
+    imgs = []
+    for ctx in (gpu_context(), oracle_context()):
+        m = ctx.add_material(material_desc(dict(type=0, diffuse=(0.5, 0.5, 0.5))))
+        p = ctx.add_material(material_desc(dict(type=5, diffuse=(0.5, 0.5, 0.5), distribution=0, alpha=0.1)))
+        ctx.add_triangle_mesh([[-2, -2, 0], [2, -2, 0], [0, 2, 0]], None, None, [[0, 1, 2]], m)
+        ctx.add_triangle_mesh([[-2, -2, -1], [2, -2, -1], [0, 2, -1]], None, None, [[0, 1, 2]], p)
+        ctx.set_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 0.6, 16, 16)
+        ctx.commit()
+        assert ctx.num_lights() == 0
+        imgs.append(ctx.render(3, 0, 4, 0, 5))
+    assert np.isfinite(imgs[0]).all() and (imgs[0] == 0).all() and np.array_equal(imgs[0], imgs[1])

@@ -133,3 +133,70 @@ def test_parser_media_and_internal_medium(tmp_path):
 
     with pytest.raises(PathedError):
         SceneFile(_scene(tmp_path, [ball("fog")], [{"name": "fog", "type": "heterogeneous", "filename": "x.vol", "albedo": "1"}]), 8, 8, root=str(tmp_path))
+
+
+# ---- EXR reader (environment maps): every scanline codec the reference reads through tinyexr for its own assets
+EXR_DIR = os.path.join(REPO_ROOT, "tests", "golden", "exr")
+
+
+@pytest.mark.parametrize("codec", ["none", "rle", "zips", "zip", "piz"])
+@pytest.mark.parametrize("kind", ["f32", "f16"])
+def test_exr_reader_decodes_every_codec(codec, kind):
+    """files written by OpenEXR itself (cv2.imwrite, tests/golden/exr); PIZ is what the reference's test_scenes/1_pixel_test.exr uses"""
+    want = np.load(os.path.join(EXR_DIR, "pixels_rgb_f32.npy"))
+    if kind == "f16":
+        want = want.astype(np.float16).astype(np.float32)
+    got = read_exr(os.path.join(EXR_DIR, "%s_%s.exr" % (codec, kind)))
+    assert got.shape == want.shape[:2] + (4,)
+    assert np.array_equal(got[..., :3], want) and (got[..., 3] == 1).all()
+
+
+def test_exr_reader_reads_the_reference_one_pixel_fixture():
+    """known answer: 1000 x 500 fp32 PIZ, exactly one non-zero texel = 10000 at row 239, column 753"""
+    path = "/root/reference/test_scenes/1_pixel_test.exr"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not mounted here")
+    img = read_exr(path)
+    assert img.shape == (500, 1000, 4)
+    lit = np.argwhere(img[..., :3].sum(-1) != 0)
+    assert lit.tolist() == [[239, 753]] and img[239, 753, :3].tolist() == [10000.0, 10000.0, 10000.0]
+
+
+def test_exr_reader_rejects_malformed_blocks(tmp_path):
+    """a block header is untrusted input: scanline outside the data window, block sizes beyond the file or the scanlines, negative
+    attribute sizes and truncated files raise instead of writing out of bounds"""
+    import struct
+    data = bytearray(open(os.path.join(EXR_DIR, "none_f32.exr"), "rb").read())
+    # locate the offset table: it follows the header's terminating zero byte; block 0 starts at its first entry
+    pos = 8
+    while data[pos] != 0:
+        pos = data.index(0, pos) + 1           # attribute name
+        pos = data.index(0, pos) + 1           # attribute type
+        size = struct.unpack_from("<i", data, pos)[0]
+        pos += 4 + size
+    table = pos + 1
+    block0 = struct.unpack_from("<Q", data, table)[0]
+
+    def expect_failure(mutated, what):
+        path = str(tmp_path / (what + ".exr"))
+        open(path, "wb").write(bytes(mutated))
+        with pytest.raises(PathedError):
+            read_exr(path)
+
+    bad = bytearray(data); struct.pack_into("<i", bad, block0, -30000000); expect_failure(bad, "negative_y")
+    bad = bytearray(data); struct.pack_into("<i", bad, block0, 1 << 20); expect_failure(bad, "y_beyond_window")
+    bad = bytearray(data); struct.pack_into("<i", bad, block0 + 4, 1 << 30); expect_failure(bad, "huge_block")
+    bad = bytearray(data); struct.pack_into("<i", bad, block0 + 4, -5); expect_failure(bad, "negative_block")
+    bad = bytearray(data); struct.pack_into("<Q", bad, table, 1 << 40); expect_failure(bad, "offset_outside")
+    expect_failure(data[:block0 + 40], "truncated")
+    zipped = bytearray(open(os.path.join(EXR_DIR, "zip_f32.exr"), "rb").read())
+    expect_failure(zipped[:len(zipped) - 100], "truncated_zip")
+    piz = bytearray(open(os.path.join(EXR_DIR, "piz_f32.exr"), "rb").read())
+    for k in range(len(piz) - 400, len(piz) - 300):
+        piz[k] ^= 0x5A
+    path = str(tmp_path / "corrupt_piz.exr")
+    open(path, "wb").write(bytes(piz))
+    try:  # a corrupted Huffman stream either fails a check or decodes to other pixels; it must not crash
+        read_exr(path)
+    except PathedError:
+        pass
