@@ -151,6 +151,23 @@ int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *positions, const float *nor
                           uint32_t n_triangles, uint32_t *geom_id_out);
 /* replaces Sphere::create (src/sphere.cpp:16-48): RTC_GEOMETRY_TYPE_SPHERE_POINT, one item */
 int ptc_add_sphere(ptc_ctx *ctx, const float center_radius[4], uint32_t material, uint32_t *geom_id_out);
+/* ---- hierarchical instancing, up to RTC_MAX_INSTANCE_LEVEL_COUNT = 2 levels.
+ * ptc_begin_instance .. ptc_end_instance replace parseInstance (src/scene_parser.cpp:231-249: rtcNewScene + parseObjects into it +
+ * rtcCommitScene): triangle meshes added in between belong to the new instance scene, with geometry ids counting from 0 inside it
+ * (the reference's quads, spheres and PLY meshes attach to the global scene even there -- src/quad.cpp:149, src/sphere.cpp:46,
+ * src/ply_parser.cpp:143 -- and leave its surface tables inconsistent, so anything but a triangle mesh is refused).  Definitions
+ * nest like the parser's recursion does; ptc_end_instance returns to the enclosing scene.
+ * ptc_add_instance replaces parseInstanced (:449-492: rtcNewGeometry(RTC_GEOMETRY_TYPE_INSTANCE), rtcSetGeometryInstancedScene,
+ * rtcSetGeometryTransform with a column-major 4x4 local-to-world matrix, rtcAttachGeometry): the placement takes the next geometry
+ * id of the scene being described (the root scene outside a begin/end pair).  As in the reference, a hit on an instance keeps
+ * Ng, the interpolated normal and uv in the instance's LOCAL space (src/scene.cpp:122-219 never transforms them back), t in world
+ * units, and only root-scene surfaces become lights (src/scene_parser.cpp:173-182). */
+int ptc_begin_instance(ptc_ctx *ctx, uint32_t *instance_scene_out);
+int ptc_end_instance(ptc_ctx *ctx);
+int ptc_add_instance(ptc_ctx *ctx, uint32_t instance_scene, const float local_to_world_column_major[16], uint32_t *geom_id_out);
+/* rtcIntersect1 including RTCHit::instID: inst_ids[2 * i + level] = geometry id of the placement at that level (PTC_INVALID_ID:
+ * none); geom_id / prim_id of the hit are those of the mesh inside the innermost instance scene (src/rtc_manager.cpp:37-54) */
+int ptc_intersect_instanced(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits, uint32_t *inst_ids);
 /* replaces Texture::load (src/texture.cpp:12-32): the 8-bit RGB texels stbi_load(..., 3) returns, row 0 = top of the
  * image, width * height * 3 bytes.  Texture::lookup (:34-49: wrap, flip v, nearest texel, pow(c / 255, 2.2)) runs on the
  * device.  Register textures before the materials that name them. */

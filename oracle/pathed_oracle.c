@@ -122,7 +122,22 @@ typedef struct {
     int is_sphere;
     float center_radius[4];
     int medium; /* Surface::m_internalMedium of the geometry's surfaces, stored + 1 (0 = none, so memset-initialised geometries have none) */
+    uint32_t scene, local_id; /* the scene the geometry is attached to (0 = root) and its geometry id there (= rtcAttachGeometry's) */
 } geom_t;
+
+/* a placement of an instance scene (RTC_GEOMETRY_TYPE_INSTANCE, src/scene_parser.cpp:449-492) */
+typedef struct {
+    uint32_t scene;      /* the instanced scene */
+    uint32_t geom_id;    /* geometry id of the placement inside its owner scene (what ends up in RTCHit::instID) */
+    float l2w[12], w2l[12]; /* rows of the 3x4 affine maps; w2l = rcp(l2w) as Instance::setTransform keeps it */
+} instance_t;
+typedef struct {
+    uint32_t n_geoms;                 /* geometry ids handed out in this scene */
+    instance_t *insts; uint32_t n_insts;
+    uint32_t order_first, order_count; /* this scene's triangle prims in c->order */
+    uint32_t root_node; int has_nodes;
+} iscene_t;
+#define ORC_MAX_SCENE_DEPTH 8
 
 typedef struct { v3 sigma_t, sigma_s; } medium_t; /* HomogeneousMedium, include/homogeneous_medium.h */
 
@@ -144,6 +159,10 @@ struct orc_ctx {
     uint32_t *prim_material, *prim_geom, *prim_local;
     uint32_t n_prims, cap_prims;  /* triangle prims only */
     geom_t *geoms; uint32_t n_geoms;
+    uint32_t *prim_scene;         /* per triangle prim: the scene it belongs to (0 = root) */
+    iscene_t *scenes; uint32_t n_scenes; /* [0] = the root scene (created on first use) */
+    uint32_t scene_stack[ORC_MAX_SCENE_DEPTH]; int scene_depth; /* scenes being described: parseInstance recurses */
+    uint32_t *root_geoms; uint32_t n_root_geoms;               /* root geometry id -> index into geoms */
     material_t *materials; uint32_t n_materials;
     texture_t *textures; uint32_t n_textures;
     uint32_t *sphere_geoms; uint32_t n_spheres; uint32_t *sphere_material;
@@ -188,7 +207,9 @@ void orc_destroy(orc_ctx *c)
 {
     if (!c) { return; }
     free(c->pos); free(c->nrm); free(c->uv); free(c->idx); free(c->prim_material); free(c->prim_geom);
-    free(c->prim_local); free(c->geoms); free(c->materials); free(c->sphere_geoms); free(c->sphere_material);
+    free(c->prim_local); free(c->prim_scene); free(c->root_geoms);
+    for (uint32_t i = 0; i < c->n_scenes; i++) { free(c->scenes[i].insts); }
+    free(c->scenes); free(c->geoms); free(c->materials); free(c->sphere_geoms); free(c->sphere_material);
     free(c->lights); free(c->env_rgba); free(c->env_theta_cdf); free(c->env_phi_cdf); free(c->env_phi_empty);
     free(c->nodes); free(c->order);
     for (uint32_t t = 0; t < c->n_textures; t++) { free(c->textures[t].rgb); }
@@ -247,9 +268,9 @@ int orc_add_medium(orc_ctx *c, const float sigma_t[3], const float sigma_s[3], u
 int orc_set_internal_medium(orc_ctx *c, uint32_t geom, uint32_t medium)
 {
     if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
-    if (geom >= c->n_geoms) { FAIL(c, PTC_ERR_INVALID, "geometry id out of range"); }
+    if (geom >= c->n_root_geoms || c->root_geoms[geom] == PTC_INVALID_ID) { FAIL(c, PTC_ERR_INVALID, "geometry id out of range"); }
     if (medium != PTC_NO_MEDIUM && medium >= c->n_media) { FAIL(c, PTC_ERR_INVALID, "medium id out of range"); }
-    c->geoms[geom].medium = medium == PTC_NO_MEDIUM ? 0 : (int)medium + 1;
+    c->geoms[c->root_geoms[geom]].medium = medium == PTC_NO_MEDIUM ? 0 : (int)medium + 1;
     return PTC_OK;
 }
 
@@ -257,6 +278,88 @@ int orc_set_integrator(orc_ctx *c, int integrator)
 {
     if (integrator != PTC_INTEGRATOR_PATH_TRACER && integrator != PTC_INTEGRATOR_VOLUME_PATH_TRACER) { FAIL(c, PTC_ERR_INVALID, "Unimplemented integrator"); }
     c->integrator = integrator;
+    return PTC_OK;
+}
+
+/* ---- scenes: [0] is the root; ptc_begin_instance opens another one (parseInstance, src/scene_parser.cpp:231-249) */
+static void ensure_root_scene(orc_ctx *c)
+{
+    if (c->n_scenes) { return; }
+    c->scenes = (iscene_t *)calloc(1, sizeof(iscene_t));
+    c->n_scenes = 1; c->scene_depth = 0;
+}
+static uint32_t current_scene(orc_ctx *c) { ensure_root_scene(c); return c->scene_depth ? c->scene_stack[c->scene_depth - 1] : 0u; }
+/* root geometry id -> index into geoms (PTC_INVALID_ID for an instance placement, which takes an id as well) */
+static void root_geom_slot(orc_ctx *c, uint32_t index)
+{
+    c->root_geoms = (uint32_t *)realloc(c->root_geoms, (c->n_root_geoms + 1) * sizeof(uint32_t));
+    c->root_geoms[c->n_root_geoms++] = index;
+}
+/* hands out the next geometry id of the current scene and records the geometry's place */
+static void attach_geometry(orc_ctx *c, geom_t *g, uint32_t index, uint32_t *geom_id)
+{
+    const uint32_t s = current_scene(c);
+    g->scene = s; g->local_id = c->scenes[s].n_geoms++;
+    if (s == 0) { root_geom_slot(c, index); }
+    if (geom_id) { *geom_id = g->local_id; }
+}
+
+int orc_begin_instance(orc_ctx *c, uint32_t *scene_out)
+{
+    if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
+    ensure_root_scene(c);
+    if (c->scene_depth >= ORC_MAX_SCENE_DEPTH) { FAIL(c, PTC_ERR_INVALID, "instance definitions nested too deeply"); }
+    c->scenes = (iscene_t *)realloc(c->scenes, (c->n_scenes + 1) * sizeof(iscene_t));
+    memset(&c->scenes[c->n_scenes], 0, sizeof(iscene_t));
+    c->scene_stack[c->scene_depth++] = c->n_scenes;
+    if (scene_out) { *scene_out = c->n_scenes; }
+    c->n_scenes++;
+    return PTC_OK;
+}
+
+int orc_end_instance(orc_ctx *c)
+{
+    if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
+    if (!c->scene_depth) { FAIL(c, PTC_ERR_STATE, "ptc_end_instance without ptc_begin_instance"); }
+    c->scene_depth--;
+    return PTC_OK;
+}
+
+/* Embree's AffineSpace3fa from a column-major 4x4 (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR) and its rcp(), common/math/affinespace.h:
+ * il = adjoint(l) / det(l), p' = -(il * p) */
+static void affine_inverse(const float l2w[12], float w2l[12])
+{
+    /* rows of l2w: r0 = (m00 m01 m02 tx) ...; columns vx = (m00 m10 m20) ... */
+    const float vx[3] = {l2w[0], l2w[4], l2w[8]}, vy[3] = {l2w[1], l2w[5], l2w[9]}, vz[3] = {l2w[2], l2w[6], l2w[10]};
+    const float px = l2w[3], py = l2w[7], pz = l2w[11];
+    const float cyz[3] = {vy[1] * vz[2] - vy[2] * vz[1], vy[2] * vz[0] - vy[0] * vz[2], vy[0] * vz[1] - vy[1] * vz[0]};
+    const float czx[3] = {vz[1] * vx[2] - vz[2] * vx[1], vz[2] * vx[0] - vz[0] * vx[2], vz[0] * vx[1] - vz[1] * vx[0]};
+    const float cxy[3] = {vx[1] * vy[2] - vx[2] * vy[1], vx[2] * vy[0] - vx[0] * vy[2], vx[0] * vy[1] - vx[1] * vy[0]};
+    const float det = vx[0] * cyz[0] + vx[1] * cyz[1] + vx[2] * cyz[2];
+    const float r = 1.f / det;
+    /* adjoint = rows (cyz, czx, cxy): inverse rows */
+    const float inv[9] = {cyz[0] * r, cyz[1] * r, cyz[2] * r, czx[0] * r, czx[1] * r, czx[2] * r, cxy[0] * r, cxy[1] * r, cxy[2] * r};
+    for (int row = 0; row < 3; row++) {
+        w2l[4 * row] = inv[3 * row]; w2l[4 * row + 1] = inv[3 * row + 1]; w2l[4 * row + 2] = inv[3 * row + 2];
+        w2l[4 * row + 3] = -(inv[3 * row] * px + inv[3 * row + 1] * py + inv[3 * row + 2] * pz);
+    }
+}
+
+int orc_add_instance(orc_ctx *c, uint32_t scene, const float m[16], uint32_t *geom_id)
+{
+    if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
+    ensure_root_scene(c);
+    if (!m || scene == 0 || scene >= c->n_scenes) { FAIL(c, PTC_ERR_INVALID, "unknown instance scene %u", scene); }
+    for (int d = 0; d < c->scene_depth; d++) { if (c->scene_stack[d] == scene) { FAIL(c, PTC_ERR_INVALID, "an instance scene cannot contain itself"); } }
+    const uint32_t owner = current_scene(c);
+    iscene_t *sc = &c->scenes[owner];
+    sc->insts = (instance_t *)realloc(sc->insts, (sc->n_insts + 1) * sizeof(instance_t));
+    instance_t *in = &sc->insts[sc->n_insts++];
+    in->scene = scene; in->geom_id = sc->n_geoms++;
+    if (owner == 0) { root_geom_slot(c, PTC_INVALID_ID); }
+    for (int row = 0; row < 3; row++) { for (int col = 0; col < 4; col++) { in->l2w[4 * row + col] = m[4 * col + row]; } } /* column-major input */
+    affine_inverse(in->l2w, in->w2l);
+    if (geom_id) { *geom_id = in->geom_id; }
     return PTC_OK;
 }
 
@@ -280,17 +383,19 @@ int orc_add_triangle_mesh(orc_ctx *c, const float *P, const float *N, const floa
     c->prim_material = (uint32_t *)realloc(c->prim_material, (size_t)(c->n_prims + nt) * sizeof(uint32_t));
     c->prim_geom = (uint32_t *)realloc(c->prim_geom, (size_t)(c->n_prims + nt) * sizeof(uint32_t));
     c->prim_local = (uint32_t *)realloc(c->prim_local, (size_t)(c->n_prims + nt) * sizeof(uint32_t));
+    c->prim_scene = (uint32_t *)realloc(c->prim_scene, (size_t)(c->n_prims + nt) * sizeof(uint32_t));
     for (uint32_t t = 0; t < nt; t++) {
         for (int k = 0; k < 3; k++) { c->idx[3 * (size_t)(c->n_prims + t) + k] = I[3 * t + k] + c->n_vertices; }
         c->prim_material[c->n_prims + t] = mat[t];
         c->prim_geom[c->n_prims + t] = c->n_geoms;
         c->prim_local[c->n_prims + t] = t;
+        c->prim_scene[c->n_prims + t] = current_scene(c);
     }
     c->geoms = (geom_t *)realloc(c->geoms, (c->n_geoms + 1) * sizeof(geom_t));
     geom_t *g = &c->geoms[c->n_geoms];
     memset(g, 0, sizeof(*g));
     g->first_vertex = c->n_vertices; g->first_prim = c->n_prims; g->n_prims = nt;
-    if (geom_id) { *geom_id = c->n_geoms; }
+    attach_geometry(c, g, c->n_geoms, geom_id);
     c->n_geoms++; c->n_vertices += nv; c->n_prims += nt;
     return PTC_OK;
 }
@@ -299,14 +404,16 @@ int orc_add_sphere(orc_ctx *c, const float cr[4], uint32_t material, uint32_t *g
 {
     if (c->committed) { FAIL(c, PTC_ERR_STATE, "scene already committed"); }
     if (material >= c->n_materials) { FAIL(c, PTC_ERR_INVALID, "material id out of range"); }
+    if (current_scene(c) != 0) { FAIL(c, PTC_ERR_INVALID, "only triangle meshes can be instanced (src/sphere.cpp:46 attaches spheres to the global scene)"); }
     c->geoms = (geom_t *)realloc(c->geoms, (c->n_geoms + 1) * sizeof(geom_t));
     geom_t *g = &c->geoms[c->n_geoms];
     memset(g, 0, sizeof(*g));
     g->is_sphere = 1; g->n_prims = 1; memcpy(g->center_radius, cr, 4 * sizeof(float));
+    attach_geometry(c, g, c->n_geoms, NULL);
     c->sphere_geoms = (uint32_t *)realloc(c->sphere_geoms, (c->n_spheres + 1) * sizeof(uint32_t));
     c->sphere_material = (uint32_t *)realloc(c->sphere_material, (c->n_spheres + 1) * sizeof(uint32_t));
     c->sphere_geoms[c->n_spheres] = c->n_geoms; c->sphere_material[c->n_spheres] = material;
-    if (geom_id) { *geom_id = c->n_geoms; }
+    if (geom_id) { *geom_id = g->local_id; }
     c->n_spheres++; c->n_geoms++;
     return PTC_OK;
 }
@@ -410,7 +517,7 @@ static inline v3 ecross(v3 a, v3 b)
     return V(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 
-typedef struct { float t, u, v; uint32_t prim; int sphere; v3 ng; } rawhit_t; /* prim = global prim or sphere slot */
+typedef struct { float t, u, v; uint32_t prim; int sphere; v3 ng; uint32_t inst[2]; } rawhit_t; /* prim = global prim or sphere slot; inst = RTCHit::instID */
 
 /* kernels/geometry/triangle_intersector_moeller.h:75-113 (+ :119-127, triangle.h:53-54):
  * stored v0, e1 = v0-v1, e2 = v2-v0, Ng = e2 x e1; accept iff den != 0, U >= 0, V >= 0, U+V <= |den|,
@@ -473,49 +580,82 @@ static inline int box_hit(const bnode_t *n, v3 O, v3 inv, float tnear, float tfa
     return t0 <= t1;
 }
 
-/* closest hit; any != 0 -> first accepted hit (rtcOccluded1 semantics) */
-static int trace(const orc_ctx *c, v3 O, v3 D, float tnear, float tfar, int any, rawhit_t *out)
+/* Embree's xfmPoint / xfmVector on an AffineSpace3fa (common/math/affinespace.h, AVX2: madd chains), rows of a 3x4 map */
+static inline v3 affine_point(const float *m, v3 p)
 {
-    int found = 0;
-    float best = tfar;
-    rawhit_t h; memset(&h, 0, sizeof(h));
-    if (c->brute_force || !c->nodes) {
-        for (uint32_t p = 0; p < c->n_prims; p++) {
+    return V(fmaf(p.x, m[0], fmaf(p.y, m[1], fmaf(p.z, m[2], m[3]))), fmaf(p.x, m[4], fmaf(p.y, m[5], fmaf(p.z, m[6], m[7]))),
+             fmaf(p.x, m[8], fmaf(p.y, m[9], fmaf(p.z, m[10], m[11]))));
+}
+static inline v3 affine_vector(const float *m, v3 d)
+{
+    return V(fmaf(d.x, m[0], fmaf(d.y, m[1], d.z * m[2])), fmaf(d.x, m[4], fmaf(d.y, m[5], d.z * m[6])), fmaf(d.x, m[8], fmaf(d.y, m[9], d.z * m[10])));
+}
+
+typedef struct { int found; float best; rawhit_t h; } trace_state_t;
+
+/* one scene's triangles, then its instance placements: InstanceIntersector1 (kernels/geometry/instance_intersector.cpp:52-109)
+ * transforms origin and direction with world2local, keeps tnear / tfar, and traverses the instanced scene */
+static int trace_scene(const orc_ctx *c, uint32_t scene, v3 O, v3 D, float tnear, int any, trace_state_t *st, uint32_t inst0, uint32_t inst1, int level)
+{
+    const iscene_t *sc = c->n_scenes ? &c->scenes[scene] : NULL;
+    const uint32_t first = sc ? sc->order_first : 0, count = sc ? sc->order_count : c->n_prims;
+    if (c->brute_force || !sc || !sc->has_nodes) {
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t p = c->order ? c->order[first + i] : i;
             float t, u, v; v3 ng;
-            if (tri_test(c, p, O, D, tnear, best, &t, &u, &v, &ng)) {
-                best = t; h.t = t; h.u = u; h.v = v; h.prim = p; h.sphere = 0; h.ng = ng; found = 1;
-                if (any) { *out = h; return 1; }
+            if (tri_test(c, p, O, D, tnear, st->best, &t, &u, &v, &ng)) {
+                st->best = t; st->h.t = t; st->h.u = u; st->h.v = v; st->h.prim = p; st->h.sphere = 0; st->h.ng = ng; st->found = 1;
+                st->h.inst[0] = inst0; st->h.inst[1] = inst1;
+                if (any) { return 1; }
             }
         }
     } else {
         const v3 inv = V(1.f / D.x, 1.f / D.y, 1.f / D.z);
-        uint32_t stack[128]; int sp = 0; stack[sp++] = 0;
+        uint32_t stack[128]; int sp = 0; stack[sp++] = sc->root_node;
         while (sp) {
             const bnode_t *n = &c->nodes[stack[--sp]];
-            if (!box_hit(n, O, inv, tnear, best)) { continue; }
+            if (!box_hit(n, O, inv, tnear, st->best)) { continue; }
             if (n->count) {
                 for (uint32_t i = 0; i < n->count; i++) {
                     const uint32_t p = c->order[n->first + i];
                     float t, u, v; v3 ng;
-                    if (tri_test(c, p, O, D, tnear, best, &t, &u, &v, &ng)) {
+                    if (tri_test(c, p, O, D, tnear, st->best, &t, &u, &v, &ng)) {
                         /* keep the brute-force tie rule: among equal t the larger prim index wins */
-                        if (found && t == best && !h.sphere && p < h.prim) { continue; }
-                        best = t; h.t = t; h.u = u; h.v = v; h.prim = p; h.sphere = 0; h.ng = ng; found = 1;
-                        if (any) { *out = h; return 1; }
+                        if (st->found && t == st->best && !st->h.sphere && p < st->h.prim) { continue; }
+                        st->best = t; st->h.t = t; st->h.u = u; st->h.v = v; st->h.prim = p; st->h.sphere = 0; st->h.ng = ng; st->found = 1;
+                        st->h.inst[0] = inst0; st->h.inst[1] = inst1;
+                        if (any) { return 1; }
                     }
                 }
             } else if (sp + 2 <= 128) { stack[sp++] = n->left; stack[sp++] = n->right; }
         }
     }
-    for (uint32_t s = 0; s < c->n_spheres; s++) {
-        float t; v3 ng;
-        if (sphere_test(c->geoms[c->sphere_geoms[s]].center_radius, O, D, tnear, best, &t, &ng)) {
-            best = t; h.t = t; h.u = 0.f; h.v = 0.f; h.prim = s; h.sphere = 1; h.ng = ng; found = 1;
-            if (any) { *out = h; return 1; }
+    if (sc && level < 2) { /* RTC_MAX_INSTANCE_LEVEL_COUNT = 2 */
+        for (uint32_t i = 0; i < sc->n_insts; i++) {
+            const instance_t *in = &sc->insts[i];
+            const v3 Ol = affine_point(in->w2l, O), Dl = affine_vector(in->w2l, D);
+            if (trace_scene(c, in->scene, Ol, Dl, tnear, any, st, level == 0 ? in->geom_id : inst0, level == 0 ? PTC_INVALID_ID : in->geom_id, level + 1) && any) { return 1; }
         }
     }
-    if (found) { *out = h; }
-    return found;
+    return st->found;
+}
+
+/* closest hit; any != 0 -> first accepted hit (rtcOccluded1 semantics) */
+static int trace(const orc_ctx *c, v3 O, v3 D, float tnear, float tfar, int any, rawhit_t *out)
+{
+    trace_state_t st; memset(&st, 0, sizeof(st));
+    st.best = tfar; st.h.inst[0] = st.h.inst[1] = PTC_INVALID_ID;
+    if (trace_scene(c, 0, O, D, tnear, any, &st, PTC_INVALID_ID, PTC_INVALID_ID, 0) && any) { *out = st.h; return 1; }
+    for (uint32_t s = 0; s < c->n_spheres; s++) {
+        float t; v3 ng;
+        if (sphere_test(c->geoms[c->sphere_geoms[s]].center_radius, O, D, tnear, st.best, &t, &ng)) {
+            st.best = t; st.h.t = t; st.h.u = 0.f; st.h.v = 0.f; st.h.prim = s; st.h.sphere = 1; st.h.ng = ng; st.found = 1;
+            st.h.inst[0] = st.h.inst[1] = PTC_INVALID_ID;
+            if (any) { *out = st.h; return 1; }
+        }
+    }
+    if (st.found) { *out = st.h; }
+    return st.found;
 }
 
 /* the reference's Intersection (include/intersection.h:13-56) with the two frame matrices reduced to 3 axes */
@@ -1457,6 +1597,7 @@ int orc_commit(orc_ctx *c)
             if (!black(e)) { light_t l; memset(&l, 0, sizeof(l)); l.kind = 1; memcpy(l.center_radius, ge->center_radius, 16); l.emit = e; c->lights[c->n_lights++] = l; }
             continue;
         }
+        if (ge->scene != 0) { continue; } /* only root-scene surfaces become lights, src/scene_parser.cpp:173-182 */
         for (uint32_t p = ge->first_prim; p < ge->first_prim + ge->n_prims; p++) {
             const material_t *m = &c->materials[c->prim_material[p]];
             const v3 e = V(m->d.emit[0], m->d.emit[1], m->d.emit[2]);
@@ -1483,12 +1624,22 @@ int orc_commit(orc_ctx *c)
             if (c->sphere_event[s] >= 0) { c->has_filter = 1; }
         }
     }
+    ensure_root_scene(c);
+    if (c->scene_depth) { FAIL(c, PTC_ERR_STATE, "ptc_begin_instance without ptc_end_instance"); }
+    if (c->n_scenes > 1 && c->n_media) { FAIL(c, PTC_ERR_INVALID, "instancing together with participating media is not supported"); }
     if (c->n_prims) {
+        /* one BVH per scene (the root and every instance scene) over a partition of c->order */
         c->order = (uint32_t *)malloc((size_t)c->n_prims * sizeof(uint32_t));
-        for (uint32_t p = 0; p < c->n_prims; p++) { c->order[p] = p; }
-        c->nodes = (bnode_t *)malloc((size_t)(2 * c->n_prims + 1) * sizeof(bnode_t));
+        c->nodes = (bnode_t *)malloc((size_t)(2 * c->n_prims + c->n_scenes + 1) * sizeof(bnode_t));
         c->n_nodes = 0;
-        build_node(c, 0, c->n_prims);
+        uint32_t at = 0;
+        for (uint32_t sc = 0; sc < c->n_scenes; sc++) {
+            c->scenes[sc].order_first = at;
+            for (uint32_t p = 0; p < c->n_prims; p++) { if (c->prim_scene[p] == sc) { c->order[at++] = p; } }
+            c->scenes[sc].order_count = at - c->scenes[sc].order_first;
+            c->scenes[sc].has_nodes = 0;
+            if (c->scenes[sc].order_count) { c->scenes[sc].root_node = build_node(c, c->scenes[sc].order_first, c->scenes[sc].order_count); c->scenes[sc].has_nodes = 1; }
+        }
     }
     c->committed = 1;
     return PTC_OK;
@@ -1497,7 +1648,7 @@ int orc_commit(orc_ctx *c)
 #define NEED_COMMIT(c) do { if (!(c)->committed) { FAIL(c, PTC_ERR_STATE, "scene not committed"); } } while (0)
 
 /* ------------------------------------------------------------------------------------------ API: queries */
-int orc_intersect(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
+int orc_intersect_instanced(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_hit *hits, uint32_t *inst_ids)
 {
     NEED_COMMIT(c);
     #pragma omp parallel for schedule(dynamic, 256) num_threads(c->threads)
@@ -1506,14 +1657,17 @@ int orc_intersect(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
         const v3 O = V(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), D = V(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
         if (trace(c, O, D, TNEAR, TFAR, 0, &h)) {
             o->t = h.t; o->u = h.u; o->v = h.v; o->ng[0] = h.ng.x; o->ng[1] = h.ng.y; o->ng[2] = h.ng.z;
-            if (h.sphere) { o->geom_id = c->sphere_geoms[h.prim]; o->prim_id = 0; }
-            else { o->geom_id = c->prim_geom[h.prim]; o->prim_id = c->prim_local[h.prim]; }
+            if (h.sphere) { o->geom_id = c->geoms[c->sphere_geoms[h.prim]].local_id; o->prim_id = 0; }
+            else { o->geom_id = c->geoms[c->prim_geom[h.prim]].local_id; o->prim_id = c->prim_local[h.prim]; }
+            if (inst_ids) { inst_ids[2 * i] = h.inst[0]; inst_ids[2 * i + 1] = h.inst[1]; }
         } else {
             memset(o, 0, sizeof(*o)); o->t = TFAR; o->geom_id = PTC_INVALID_ID; o->prim_id = PTC_INVALID_ID;
+            if (inst_ids) { inst_ids[2 * i] = inst_ids[2 * i + 1] = PTC_INVALID_ID; }
         }
     }
     return PTC_OK;
 }
+int orc_intersect(orc_ctx *c, const ptc_ray *rays, uint32_t n, ptc_hit *hits) { return orc_intersect_instanced(c, rays, n, hits, NULL); }
 
 static void export_isect(const isect_t *s, ptc_isect *o)
 {

@@ -56,7 +56,8 @@ class SceneSink(ctypes.Structure):
     _fields_ = [("ctx", ctypes.c_void_p), ("add_material", ctypes.c_void_p), ("add_triangle_mesh", ctypes.c_void_p),
                 ("add_sphere", ctypes.c_void_p), ("set_environment", ctypes.c_void_p), ("set_camera", ctypes.c_void_p),
                 ("commit", ctypes.c_void_p), ("add_texture", ctypes.c_void_p), ("add_medium", ctypes.c_void_p),
-                ("set_internal_medium", ctypes.c_void_p)]
+                ("set_internal_medium", ctypes.c_void_p), ("begin_instance", ctypes.c_void_p), ("end_instance", ctypes.c_void_p),
+                ("add_instance", ctypes.c_void_p)]
 
 
 class PathedError(RuntimeError):
@@ -117,7 +118,7 @@ class Api:
         addr = lambda name: ctypes.cast(self._fn(name), ctypes.c_void_p).value
         return SceneSink(self.ctx.value, addr("add_material"), addr("add_triangle_mesh"), addr("add_sphere"),
                          addr("set_environment"), addr("set_camera"), addr("commit"), addr("add_texture"), addr("add_medium"),
-                         addr("set_internal_medium"))
+                         addr("set_internal_medium"), addr("begin_instance"), addr("end_instance"), addr("add_instance"))
 
     # ---- scene description
     def add_texture(self, rgb):
@@ -141,6 +142,28 @@ class Api:
 
     def set_internal_medium(self, geom_id, medium_id):
         self._call("set_internal_medium", ctypes.c_uint32(geom_id), ctypes.c_uint32(medium_id))
+
+    # ---- hierarchical instancing
+    def begin_instance(self):
+        out = ctypes.c_uint32()
+        self._call("begin_instance", ctypes.byref(out))
+        return out.value
+
+    def end_instance(self):
+        self._call("end_instance")
+
+    def add_instance(self, instance_scene, local_to_world):
+        """local_to_world: 4x4 (row, column) matrix; passed column-major like rtcSetGeometryTransform takes it"""
+        m = np.ascontiguousarray(np.asarray(local_to_world, np.float32).reshape(4, 4).T)
+        out = ctypes.c_uint32()
+        self._call("add_instance", ctypes.c_uint32(instance_scene), _ptr(m), ctypes.byref(out))
+        return out.value
+
+    def intersect_instanced(self, rays):
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        inst = np.zeros((len(rays), 2), np.uint32)
+        self._call("intersect_instanced", _ptr(rays), ctypes.c_uint32(len(rays)), _ptr(hits), _ptr(inst))
+        return hits, inst
 
     def set_integrator(self, integrator):
         self._call("set_integrator", ctypes.c_int(integrator))

@@ -29,29 +29,47 @@ using namespace ptc;
 
 // ================================================================================================ device state
 #define PTC_MATERIAL_CLASSES 7 /* PTC_LAMBERTIAN .. PTC_PASSTHROUGH */
-// Fields that the stages always touch together share one 32-byte record (PTC_PAIRED_STATE): after the first bounces the
-// surviving paths are sparse in slot space, so every 16-byte field access costs a whole 32-byte sector -- pairing (origin,
-// direction), (hit, result) and (modulation, throughput) makes both halves of those sectors useful.  The accessors keep the
-// `pb.field[p]` spelling of a plain array.
-#ifndef PTC_PAIRED_STATE
-#define PTC_PAIRED_STATE 1
+// Path state.  A path does not keep its slot: the material stage of vertex k writes the state of every path that goes on to the
+// slot it gets in the NEXT bounce's ray list (one warp-aggregated append), so the paths alive at bounce k always occupy slots
+// 0 .. n_k - 1 of the state arrays and every stage reads and writes dense, coalesced records however few paths survive (replaces
+// the implicit `break`s of PathTracer::L, src/path_tracer.cpp:45,56-58; the slot a path started in -- pixel and sample, the Philox
+// key and the place its radiance is summed -- travels with it as `origin`).  Fields that a later kernel still reads at the old
+// slots are double-buffered (current / next); the rest are written at the new slot only after their last reader of the old slot
+// finished.  Fields that are touched together share one 32-byte record (PairedField): the class queues of the material stage
+// gather a subset of the slots, so both halves of every sector they touch are useful.
+// Path state is streamed: every record is read once and written once per stage, 15 GB per wave, while the scene data the same
+// kernels gather from (BVH, per-triangle shading records, environment map and its CDFs: ~160 MB for the dragon workload) is re-used
+// and should own the 126 MB L2.  PTC_STREAM_STATE = 1 issues the path-state accesses with the evict-first policy (ld.global.cs /
+// st.global.cs), so they pass through L2 without displacing the scene.
+#ifndef PTC_STREAM_STATE
+#define PTC_STREAM_STATE 1
 #endif
+template <typename T> __device__ __forceinline__ T streamLoad(const T *p) { return PTC_STREAM_STATE ? __ldcs(p) : *p; }
+template <typename T> __device__ __forceinline__ void streamStore(T *p, T v) { if (PTC_STREAM_STATE) { __stcs(p, v); } else { *p = v; } }
+struct StateRef { // `pb.field[p]` reads and writes like an element of a plain array
+    float4 *p;
+    __device__ __forceinline__ operator float4() const { return streamLoad(p); }
+    __device__ __forceinline__ void operator=(float4 v) const { streamStore(p, v); }
+};
 struct PairedField {
     float4 *base;
-    __device__ __forceinline__ float4 &operator[](uint32_t p) const { return base[(PTC_PAIRED_STATE ? 2 : 1) * (size_t)p]; }
+    __device__ __forceinline__ StateRef operator[](uint32_t p) const { StateRef r; r.p = base + 2 * (size_t)p; return r; }
+    __device__ __forceinline__ float *component(uint32_t p, int c) const { return reinterpret_cast<float *>(base + 2 * (size_t)p) + c; }
 };
 struct PathBuffers {
-    PairedField rayO, rayD;   // current ray (origin = current vertex)
-    PairedField hit;          // t, u, v, prim bits
-    PairedField modPdf;       // modulation rgb, pdf of the BSDF sample that produced the ray
-    PairedField thrCos;       // BSDF sample throughput rgb, |n_s . wi|
-    PairedField result;       // L() accumulator rgb, w = flags
-    PairedField nee;       // pending light-sampling contribution rgb; w = 0 until the shadow stage finds the ray occluded (then 1):
-                           // the flag travels in the record the logic stage reads anyway instead of a separate sparse byte array
-    PairedField shadowD;   // shadow ray direction, w = distance to the light sample (one record with nee: written together)
-    float4 *out;           // per-sample radiance: camera-hit emission / environment, plus result at termination
-    uint32_t *extendQueue[2];
-    uint32_t *shadowQueue;
+    // current buffers: the state of the paths of this bounce, slots 0 .. n - 1
+    PairedField rayO, rayD;      // current ray (origin = current vertex)
+    PairedField modPdf, result;  // modulation rgb + pdf of the BSDF sample that produced the ray | L() accumulator rgb, w = flags
+    uint32_t *origin;            // slot the path started in: pixel / sample, i.e. its Philox key and its entry of `out`
+    // next buffers: written by the material stage at the slot the path takes in the next bounce
+    PairedField nRayO, nRayD, nModPdf, nResult;
+    uint32_t *nOrigin;
+    // single-buffered: written at the new slot (material stage) or at the current one (traversal), never read at an old slot afterwards
+    PairedField hit, thrCos;     // t, u, v, prim bits (traversal) | BSDF sample throughput rgb, |n_s . wi| (material stage)
+    PairedField nee, shadowD;    // pending light-sampling contribution rgb, w = 0 until the shadow stage finds the ray occluded (then 1)
+                                 // | shadow ray direction, w = distance to the light sample
+    float4 *out;                 // per-sample radiance by origin slot: camera-hit emission / environment, plus result at termination
+    uint32_t *shadowQueue;       // slots (next-bounce numbering) whose NEE shadow ray has to be traced
     uint32_t *classQueue[PTC_MATERIAL_CLASSES]; // survivors of the logic stage, binned by material class (null: class absent from the scene)
 };
 
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
         pb.rayO[p] = make_float4(o.x, o.y, o.z, 0.f);
         pb.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
         pb.result[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        pb.extendQueue[0][p] = p;
+        streamStore(pb.origin + p, p);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0].extendCount = nPaths; }
 }
@@ -269,7 +287,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             if (!busy) {
                 const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
                 if (item < n) {
-                    p = queue[item];
+                    p = queue ? streamLoad(queue + item) : item; // extend: the paths of a bounce occupy slots 0 .. n - 1
                     const float4 o = pb.rayO[p];
                     if (ANY) { // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
                         const float4 d = pb.shadowD[p];
@@ -305,7 +323,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             }
             if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
                 const bool found = traversalSpheres<ANY, FILTER>(scene.bvh, st);
-                if (ANY) { if (found) { reinterpret_cast<float *>(&pb.nee[p])[3] = 1.f; } }
+                if (ANY) { if (found) { streamStore(pb.nee.component(p, 3), 1.f); } }
                 else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
                 busy = false;
             }
@@ -340,49 +358,41 @@ __device__ __forceinline__ void cameraContainerTerm(const DScene &scene, float o
 
 // Runs between logic(0) and the material kernels of vertex 1, only for scenes with container surfaces: the camera ray and its
 // hit are still in the path state, and out[p] holds the camera-hit emission (0 for a Passthrough surface).
-__global__ void __launch_bounds__(128) containerKernel(const __grid_constant__ DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, const BounceCounters *bc)
+__global__ void __launch_bounds__(128) containerKernel(const __grid_constant__ DScene scene, PathBuffers pb, WaveParams wp, const BounceCounters *bc)
 {
     const uint32_t n = bc->extendCount;
     if (!checkCounts(wp.startBounce, wp.lastBounce, 0)) { return; }
-    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n; item += gridDim.x * blockDim.x) {
-        const uint32_t p = queue[item];
-        const uint32_t prim = __float_as_uint(pb.hit[p].w);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) { // bounce 0: slot = origin
+        const float4 h4 = pb.hit[p];
+        const uint32_t prim = __float_as_uint(h4.w);
         if (prim == PTC_MISS) { continue; }
         const uint32_t material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w);
         if (__ldg(&scene.materials[material].type) != PTC_PASSTHROUGH) { continue; }
         const float4 o4 = pb.rayO[p], d4 = pb.rayD[p];
         float add[3];
         cameraContainerTerm(scene, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, add);
-        const float4 c = pb.out[p];
-        pb.out[p] = make_float4(c.x + add[0], c.y + add[1], c.z + add[2], 0.f);
+        const float4 c = streamLoad(pb.out + p);
+        streamStore(pb.out + p, make_float4(c.x + add[0], c.y + add[1], c.z + add[2], 0.f));
     }
 }
 
 #ifndef PTC_LAZY_DIRECTION
 #define PTC_LAZY_DIRECTION 1
 #endif
-__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, const uint32_t *queue, BounceCounters *bc, uint32_t classMask)
+__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;
-    // uniform cost per path: static warp-strided assignment (whole warps stay in the loop together for the ballots below)
+    // uniform cost per path: static warp-strided assignment (whole warps stay in the loop together for the ballots below);
+    // slot p of the current buffers = item p of this bounce's ray list, so every load below is a dense, coalesced one
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t item = base + (threadIdx.x & 31u);
+        const uint32_t p = base + (threadIdx.x & 31u);
         int cls = -1;
-        uint32_t p = 0;
-        if (item < n) {
-            p = queue[item];
-#if PTC_LAZY_DIRECTION
+        if (p < n) {
             // the ray direction is only needed for environment misses and emitter hits: a surviving ordinary hit never reads it
             const float4 h4 = pb.hit[p];
-#else
-            const float4 d4 = pb.rayD[p], h4 = pb.hit[p];
-#endif
             float4 res4 = pb.result[p];
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
-#if !PTC_LAZY_DIRECTION
-            const V3 D = mk(d4.x, d4.y, d4.z);
-#endif
             const uint32_t prim = __float_as_uint(h4.w);
             const bool isHit = prim != PTC_MISS;
             uint32_t material = 0;
@@ -392,14 +402,12 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                 emitter = __ldg(&scene.materials[material].emitter) != 0;
             }
             V3 result = mk(res4.x, res4.y, res4.z);
+            V3 color = mk(0.f, 0.f, 0.f); // k = 0: what samplePixel adds itself
             bool alive = true;
             if (k == 0) {
                 // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59
-                V3 color = mk(0.f, 0.f, 0.f);
-#if PTC_LAZY_DIRECTION
                 V3 D = mk(0.f, 0.f, 0.f);
                 if (!isHit || emitter) { const float4 d4 = pb.rayD[p]; D = mk(d4.x, d4.y, d4.z); }
-#endif
                 if (!isHit) { color = envRadiance(scene, D); alive = false; }
                 else if (emitter && checkCounts(wp.startBounce, wp.lastBounce, 0)) {
                     const float4 o4 = pb.rayO[p];
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                     const DMaterial &m = scene.materials[material];
                     if (!(dot(bi.n, bi.wo) < 0.f)) { color = mk(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2])); }
                 }
-                pb.out[p] = make_float4(color.x, color.y, color.z, 0.f);
+                if (alive) { streamStore(pb.out + p, make_float4(color.x, color.y, color.z, 0.f)); } // bounce 0: slot = origin
             } else {
                 const float4 mp = pb.modPdf[p], tc = pb.thrCos[p];
                 V3 modulation = mk(mp.x, mp.y, mp.z);
@@ -418,10 +426,8 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                     V3 Ld = mk(0.f, 0.f, 0.f);
                     if (flags & FLAG_NEE) { const float4 ne = pb.nee[p]; if (ne.w == 0.f) { Ld = Ld + mk(ne.x, ne.y, ne.z); } }
                     if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
-#if PTC_LAZY_DIRECTION
                         const float4 d4 = pb.rayD[p];
                         const V3 D = mk(d4.x, d4.y, d4.z);
-#endif
                         const float4 o4 = pb.rayO[p];
                         const V3 O = mk(o4.x, o4.y, o4.z);
                         Isect bi;
@@ -441,16 +447,20 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                 if (alive && (flags & FLAG_DIRECT)) { pb.result[p] = make_float4(result.x, result.y, result.z, res4.w); }
             }
             if (alive) { cls = __ldg(&scene.materials[material].type); }
-            else { // color += L(...), src/sample_integrator.cpp:53
-                const float4 c = pb.out[p];
-                pb.out[p] = make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f);
+            else { // color += L(...), src/sample_integrator.cpp:53: the path ends, its radiance goes to the entry of its origin slot
+                const uint32_t origin = streamLoad(pb.origin + p);
+                if (k == 0) { streamStore(pb.out + origin, make_float4(color.x + result.x, color.y + result.y, color.z + result.z, 0.f)); }
+                else {
+                    const float4 c = streamLoad(pb.out + origin);
+                    streamStore(pb.out + origin, make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f));
+                }
             }
         }
 #pragma unroll
         for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
             if (!(classMask & (1u << t))) { continue; }
             const uint32_t slot = warpAppend(&bc->classCount[t], cls == t);
-            if (cls == t) { pb.classQueue[t][slot] = p; }
+            if (cls == t) { streamStore(pb.classQueue[t] + slot, p); }
         }
     }
 }
@@ -458,17 +468,20 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
 // ------------------------------------------------------------------------------------------------ K4 material
 // Vertex k + 1 of every surviving path whose hit surface has material class TYPE: Intersection, BSDF sample, NEE set-up.
 template <int TYPE>
-__global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t *nextQueue, BounceCounters *next)
+__global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, BounceCounters *next)
 {
     const uint32_t n = bc->classCount[TYPE];
     const uint32_t *queue = pb.classQueue[TYPE];
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t item = base + (threadIdx.x & 31u);
         bool pushExtend = false, pushShadow = false;
-        uint32_t p = 0;
+        // what the path carries to its slot of the next bounce
+        float4 nO = make_float4(0.f, 0.f, 0.f, 0.f), nD = nO, nMod = nO, nThr = nO, nRes = nO, nNee = nO, nSh = nO;
+        uint32_t origin = 0;
         if (item < n) {
-            p = queue[item];
+            const uint32_t p = streamLoad(queue + item);
             const float4 o4 = pb.rayO[p], d4 = pb.rayD[p], h4 = pb.hit[p], res4 = pb.result[p];
+            origin = streamLoad(pb.origin + p);
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
             RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
             makeIsect(scene, mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z), hit, bi);
             const DMaterial &m = scene.materials[bi.material];
             Rng rng;
-            rng.initPhilox(wp.seed, slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + p / wp.nPixels);
+            rng.initPhilox(wp.seed, slotToPixel(origin % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + origin / wp.nPixels);
             rng.beginVertex((uint32_t)(k + 1));
             BsdfSample bs;
             bsdfSample<TYPE>(m, bi, rng, bs);
@@ -486,31 +499,35 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
                 // a contribution that is exactly black adds nothing whether or not the light is visible (src/path_tracer.cpp:
                 // 138-164: occluded -> 0, else the contribution), e.g. a light sampled below the surface: no shadow ray for it
                 if (directLightsSetup<TYPE>(scene, m, bi, bs, rng, contribution, sd, maxT) && !isBlack(contribution)) {
-                    pb.nee[p] = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
-                    pb.shadowD[p] = make_float4(sd.x, sd.y, sd.z, maxT);
+                    nNee = make_float4(contribution.x, contribution.y, contribution.z, 0.f);
+                    nSh = make_float4(sd.x, sd.y, sd.z, maxT);
                     pushShadow = true;
                 }
             }
             const bool wantNext = !checkDone(wp.lastBounce, k + 2);
             if (wantDirect || wantNext) {
-                pb.rayO[p] = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
-                pb.rayD[p] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
-                const float4 mp = pb.modPdf[p]; // k = 0: not written yet, the modulation starts at 1
-                pb.modPdf[p] = k == 0 ? make_float4(1.f, 1.f, 1.f, bs.pdf) : make_float4(mp.x, mp.y, mp.z, bs.pdf);
-                pb.thrCos[p] = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
+                nO = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
+                nD = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
+                if (k == 0) { nMod = make_float4(1.f, 1.f, 1.f, bs.pdf); } // the modulation starts at 1
+                else { const float4 mp = pb.modPdf[p]; nMod = make_float4(mp.x, mp.y, mp.z, bs.pdf); }
+                nThr = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
                 const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u);
-                pb.result[p] = make_float4(res4.x, res4.y, res4.z, __uint_as_float(nf));
+                nRes = make_float4(res4.x, res4.y, res4.z, __uint_as_float(nf));
                 pushExtend = true;
             } else { // the path ends here: color += L(...)
                 pushShadow = false;
-                const float4 c = pb.out[p];
-                pb.out[p] = make_float4(c.x + res4.x, c.y + res4.y, c.z + res4.z, 0.f);
+                const float4 c = streamLoad(pb.out + origin);
+                streamStore(pb.out + origin, make_float4(c.x + res4.x, c.y + res4.y, c.z + res4.z, 0.f));
             }
         }
+        // compaction: the path moves to slot e of the next bounce; consecutive lanes get consecutive slots (coalesced stores)
         const uint32_t e = warpAppend(&next->extendCount, pushExtend);
-        if (pushExtend) { nextQueue[e] = p; }
+        if (pushExtend) {
+            pb.nRayO[e] = nO; pb.nRayD[e] = nD; pb.nModPdf[e] = nMod; pb.nResult[e] = nRes; pb.thrCos[e] = nThr; streamStore(pb.nOrigin + e, origin);
+            if (pushShadow) { pb.nee[e] = nNee; pb.shadowD[e] = nSh; }
+        }
         const uint32_t sh = warpAppend(&next->shadowCount, pushShadow);
-        if (pushShadow) { pb.shadowQueue[sh] = p; }
+        if (pushShadow) { streamStore(pb.shadowQueue + sh, e); }
     }
 }
 
@@ -521,7 +538,7 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
         const size_t pixel = slotToPixel(q, width, height);
         float r = accum[3 * pixel], g = accum[3 * pixel + 1], b = accum[3 * pixel + 2];
         for (uint32_t s = 0; s < wp.sppWave; s++) { // radianceLookup += color, one sample after the other (src/sample_integrator.cpp:61-63)
-            const float4 c = pb.out[(size_t)s * wp.nPixels + q];
+            const float4 c = streamLoad(pb.out + (size_t)s * wp.nPixels + q);
             r += c.x; g += c.y; b += c.z;
         }
         accum[3 * pixel] = r; accum[3 * pixel + 1] = g; accum[3 * pixel + 2] = b;
@@ -610,22 +627,27 @@ __global__ void tallyKernel(const BounceCounters *counters, unsigned long long *
 }
 
 // ================================================================================================ probe kernels
-__global__ void intersectKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
+__global__ void intersectKernel(DScene scene, const ptc_ray *rays, uint32_t n, ptc_hit *hits, uint2 *inst)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const ptc_ray r = rays[i];
         RayHit h;
         ptc_hit out;
+        uint2 instance = make_uint2(PTC_INVALID_ID, PTC_INVALID_ID);
         if (traverseBVH<false, false>(scene.bvh, r.origin[0], r.origin[1], r.origin[2], r.direction[0], r.direction[1], r.direction[2], PTC_TNEAR, PTC_TFAR, h, nullptr)) {
             Isect is; V3 ng;
             makeIsect(scene, mk(r.origin[0], r.origin[1], r.origin[2]), mk(r.direction[0], r.direction[1], r.direction[2]), h, is, &ng);
             out.t = h.t; out.u = h.u; out.v = h.v; out.ng[0] = ng.x; out.ng[1] = ng.y; out.ng[2] = ng.z;
             if (h.prim & PTC_SPHERE_FLAG) { out.geom_id = scene.sphereIds[h.prim & ~PTC_SPHERE_FLAG].x; out.prim_id = 0; }
-            else { const uint2 id = scene.primIds[h.prim]; out.geom_id = id.x; out.prim_id = id.y; }
+            else {
+                const uint2 id = scene.primIds[h.prim]; out.geom_id = id.x; out.prim_id = id.y;
+                if (scene.instIds) { instance = scene.instIds[h.prim]; }
+            }
         } else {
             out.t = PTC_TFAR; out.u = 0.f; out.v = 0.f; out.geom_id = PTC_INVALID_ID; out.prim_id = PTC_INVALID_ID; out.ng[0] = out.ng[1] = out.ng[2] = 0.f;
         }
         hits[i] = out;
+        if (inst) { inst[i] = instance; }
     }
 }
 
@@ -862,10 +884,17 @@ __global__ void volumeReplayKernel(const __grid_constant__ DScene scene, const p
 struct HostGeometry {
     int32_t medium = -1; // Surface::m_internalMedium of every surface of the geometry
     bool isSphere = false;
-    uint32_t firstVertex = 0, firstPrim = 0, nPrims = 0;
+    uint32_t firstVertex = 0, nVertices = 0, firstPrim = 0, nPrims = 0;
     float centerRadius[4] = {0, 0, 0, 0};
     uint32_t sphereMaterial = 0;
+    // the scene the geometry is attached to (0 = root) and its geometry id there; a placement of an instance scene
+    // (RTC_GEOMETRY_TYPE_INSTANCE) is a geometry too: it takes an id, and carries the instanced scene and its local-to-world map
+    uint32_t scene = 0, localId = 0;
+    bool isInstance = false;
+    uint32_t instanceScene = 0;
+    float l2w[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}; // rows of the 3x4 affine map
 };
+struct HostScene { uint32_t nGeoms = 0; std::vector<uint32_t> members; }; // members: indices into ptc_ctx::geometries, attach order
 
 struct ptc_ctx {
     int device = 0;
@@ -878,6 +907,9 @@ struct ptc_ctx {
     std::vector<float> positions4, normals4, uvs2;
     std::vector<uint32_t> prims4, primIds2;
     std::vector<HostGeometry> geometries;
+    std::vector<HostScene> scenes = std::vector<HostScene>(1); // [0] = the root scene
+    std::vector<uint32_t> sceneStack;                          // instance scenes being described (parseInstance recurses)
+    std::vector<uint32_t> rootGeometry;                        // root geometry id -> index into geometries
     struct HostMedium { float sigmaT[3], sigmaS[3]; };
     std::vector<HostMedium> media;
     int integrator = PTC_INTEGRATOR_PATH_TRACER;
@@ -1077,9 +1109,9 @@ int ptc_set_internal_medium(ptc_ctx *ctx, uint32_t geom, uint32_t medium)
 {
     if (!ctx) { return PTC_ERR_INVALID; }
     if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
-    if (geom >= ctx->geometries.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "geometry id %u out of range", geom); }
+    if (geom >= ctx->rootGeometry.size() || ctx->geometries[ctx->rootGeometry[geom]].isInstance) { CTX_FAIL(ctx, PTC_ERR_INVALID, "geometry id %u out of range", geom); }
     if (medium != PTC_NO_MEDIUM && medium >= ctx->media.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "medium id %u out of range", medium); }
-    ctx->geometries[geom].medium = medium == PTC_NO_MEDIUM ? -1 : (int32_t)medium;
+    ctx->geometries[ctx->rootGeometry[geom]].medium = medium == PTC_NO_MEDIUM ? -1 : (int32_t)medium;
     return PTC_OK;
 }
 
@@ -1088,6 +1120,51 @@ int ptc_set_integrator(ptc_ctx *ctx, int integrator)
     if (!ctx) { return PTC_ERR_INVALID; }
     if (integrator != PTC_INTEGRATOR_PATH_TRACER && integrator != PTC_INTEGRATOR_VOLUME_PATH_TRACER) { CTX_FAIL(ctx, PTC_ERR_INVALID, "Unimplemented integrator %d", integrator); }
     ctx->integrator = integrator;
+    return PTC_OK;
+}
+
+// rtcAttachGeometry: the next geometry id of the scene being described
+static uint32_t attachGeometry(ptc_ctx *ctx, HostGeometry &g)
+{
+    g.scene = ctx->sceneStack.empty() ? 0u : ctx->sceneStack.back();
+    g.localId = ctx->scenes[g.scene].nGeoms++;
+    ctx->scenes[g.scene].members.push_back((uint32_t)ctx->geometries.size());
+    if (g.scene == 0) { ctx->rootGeometry.push_back((uint32_t)ctx->geometries.size()); }
+    ctx->geometries.push_back(g);
+    return g.localId;
+}
+
+int ptc_begin_instance(ptc_ctx *ctx, uint32_t *sceneOut)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (ctx->sceneStack.size() >= 8) { CTX_FAIL(ctx, PTC_ERR_INVALID, "instance definitions nested too deeply"); }
+    ctx->scenes.push_back(HostScene());
+    ctx->sceneStack.push_back((uint32_t)ctx->scenes.size() - 1);
+    if (sceneOut) { *sceneOut = ctx->sceneStack.back(); }
+    return PTC_OK;
+}
+
+int ptc_end_instance(ptc_ctx *ctx)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (ctx->sceneStack.empty()) { CTX_FAIL(ctx, PTC_ERR_STATE, "ptc_end_instance without ptc_begin_instance"); }
+    ctx->sceneStack.pop_back();
+    return PTC_OK;
+}
+
+int ptc_add_instance(ptc_ctx *ctx, uint32_t scene, const float m[16], uint32_t *geomId)
+{
+    if (!ctx || !m) { return PTC_ERR_INVALID; }
+    if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
+    if (scene == 0 || scene >= ctx->scenes.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "unknown instance scene %u", scene); }
+    for (uint32_t open : ctx->sceneStack) { if (open == scene) { CTX_FAIL(ctx, PTC_ERR_INVALID, "an instance scene cannot contain itself"); } }
+    HostGeometry g;
+    g.isInstance = true; g.instanceScene = scene;
+    for (int row = 0; row < 3; row++) { for (int col = 0; col < 4; col++) { g.l2w[4 * row + col] = m[4 * col + row]; } } // RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR
+    const uint32_t id = attachGeometry(ctx, g);
+    if (geomId) { *geomId = id; }
     return PTC_OK;
 }
 
@@ -1102,9 +1179,10 @@ int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *P, const float *N, const fl
     }
     HostGeometry g;
     g.firstVertex = (uint32_t)(ctx->positions4.size() / 4);
+    g.nVertices = nv;
     g.firstPrim = (uint32_t)(ctx->prims4.size() / 4);
     g.nPrims = nt;
-    const uint32_t geom = (uint32_t)ctx->geometries.size();
+    const uint32_t geom = ctx->scenes[ctx->sceneStack.empty() ? 0u : ctx->sceneStack.back()].nGeoms; // the id attachGeometry hands out below
     for (uint32_t v = 0; v < nv; v++) {
         ctx->positions4.insert(ctx->positions4.end(), {P[3 * (size_t)v], P[3 * (size_t)v + 1], P[3 * (size_t)v + 2], 0.f});
         if (N) { ctx->normals4.insert(ctx->normals4.end(), {N[3 * (size_t)v], N[3 * (size_t)v + 1], N[3 * (size_t)v + 2], 0.f}); }
@@ -1116,7 +1194,7 @@ int ptc_add_triangle_mesh(ptc_ctx *ctx, const float *P, const float *N, const fl
         ctx->prims4.insert(ctx->prims4.end(), {I[3 * (size_t)t] + g.firstVertex, I[3 * (size_t)t + 1] + g.firstVertex, I[3 * (size_t)t + 2] + g.firstVertex, mat[t]});
         ctx->primIds2.insert(ctx->primIds2.end(), {geom, t});
     }
-    ctx->geometries.push_back(g);
+    attachGeometry(ctx, g);
     if (geomId) { *geomId = geom; }
     return PTC_OK;
 }
@@ -1126,10 +1204,11 @@ int ptc_add_sphere(ptc_ctx *ctx, const float cr[4], uint32_t material, uint32_t 
     if (!ctx || !cr) { return PTC_ERR_INVALID; }
     if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene already committed"); }
     if (material >= ctx->materials.size()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "material id %u out of range", material); }
+    if (!ctx->sceneStack.empty()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "only triangle meshes can be instanced (src/sphere.cpp:46 attaches spheres to the global scene)"); }
     HostGeometry g;
     g.isSphere = true; g.nPrims = 1; memcpy(g.centerRadius, cr, sizeof(g.centerRadius)); g.sphereMaterial = material;
-    ctx->geometries.push_back(g);
-    if (geomId) { *geomId = (uint32_t)ctx->geometries.size() - 1; }
+    const uint32_t id = attachGeometry(ctx, g);
+    if (geomId) { *geomId = id; }
     return PTC_OK;
 }
 
@@ -1203,20 +1282,82 @@ int ptc_commit(ptc_ctx *ctx)
     if (!ctx->hasCamera) { CTX_FAIL(ctx, PTC_ERR_STATE, "no camera set"); }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     DScene &s = ctx->scene;
-    const uint32_t nPrims = (uint32_t)(ctx->prims4.size() / 4);
+    if (!ctx->sceneStack.empty()) { CTX_FAIL(ctx, PTC_ERR_STATE, "ptc_begin_instance without ptc_end_instance"); }
+    const bool instanced = ctx->scenes.size() > 1;
+    if (instanced && !ctx->media.empty()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "instancing together with participating media is not supported"); }
+
+    // SURVEY 8(f) N4.  180 GB of HBM make flattening the B200-native form of Embree's two-level instancing: every placement of an
+    // instance scene becomes world-space triangles of the ONE wide BVH (single-level traversal, no per-ray transforms or second
+    // stack), while everything Scene::testIntersect reads after the hit -- Ng, vertex normals, uvs, the emitter triangle's corners --
+    // stays in the instance's LOCAL space, exactly as the reference leaves it (src/scene.cpp:122-219 never transforms back).
+    // flat prim = one triangle of the BVH: (local vertex ids, material) | (geomID, primID inside its scene) | (instID[0], instID[1])
+    std::vector<uint32_t> flatPrims4, flatIds2, flatInst2, worldPrims4;
+    std::vector<float> worldPos4;
+    if (instanced) {
+        struct Expand {
+            ptc_ctx *ctx; std::vector<uint32_t> &flatPrims4, &flatIds2, &flatInst2, &worldPrims4; std::vector<float> &worldPos4; std::string error;
+            void run(uint32_t scene, const float *T, uint32_t inst0, uint32_t inst1, int level)
+            {
+                for (uint32_t index : ctx->scenes[scene].members) {
+                    const HostGeometry &g = ctx->geometries[index];
+                    if (g.isSphere) { continue; }
+                    if (g.isInstance) {
+                        if (level >= 2) { error = "more than RTC_MAX_INSTANCE_LEVEL_COUNT = 2 instance levels"; return; }
+                        float C[12]; // T o g.l2w: the inner placement is applied first
+                        for (int r = 0; r < 3; r++) {
+                            for (int c = 0; c < 4; c++) {
+                                C[4 * r + c] = T[4 * r] * g.l2w[c] + T[4 * r + 1] * g.l2w[4 + c] + T[4 * r + 2] * g.l2w[8 + c] + (c == 3 ? T[4 * r + 3] : 0.f);
+                            }
+                        }
+                        run(g.instanceScene, C, level == 0 ? g.localId : inst0, level == 0 ? PTC_INVALID_ID : g.localId, level + 1);
+                        if (!error.empty()) { return; }
+                        continue;
+                    }
+                    const uint32_t base = (uint32_t)(worldPos4.size() / 4);
+                    for (uint32_t v = 0; v < g.nVertices; v++) {
+                        const float *q = &ctx->positions4[4 * (size_t)(g.firstVertex + v)];
+                        worldPos4.insert(worldPos4.end(), {T[0] * q[0] + T[1] * q[1] + T[2] * q[2] + T[3], T[4] * q[0] + T[5] * q[1] + T[6] * q[2] + T[7],
+                                                           T[8] * q[0] + T[9] * q[1] + T[10] * q[2] + T[11], 0.f});
+                    }
+                    for (uint32_t t = 0; t < g.nPrims; t++) {
+                        const uint32_t *ix = &ctx->prims4[4 * (size_t)(g.firstPrim + t)];
+                        flatPrims4.insert(flatPrims4.end(), ix, ix + 4);
+                        worldPrims4.insert(worldPrims4.end(), {ix[0] - g.firstVertex + base, ix[1] - g.firstVertex + base, ix[2] - g.firstVertex + base, ix[3]});
+                        flatIds2.insert(flatIds2.end(), {g.localId, t});
+                        flatInst2.insert(flatInst2.end(), {inst0, inst1});
+                    }
+                }
+            }
+        } expand{ctx, flatPrims4, flatIds2, flatInst2, worldPrims4, worldPos4, std::string()};
+        const float identity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        expand.run(0, identity, PTC_INVALID_ID, PTC_INVALID_ID, 0);
+        if (!expand.error.empty()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "%s", expand.error.c_str()); }
+    }
+    const std::vector<uint32_t> &prims4 = instanced ? flatPrims4 : ctx->prims4;
+    const std::vector<uint32_t> &primIds2 = instanced ? flatIds2 : ctx->primIds2;
+    const uint32_t nPrims = (uint32_t)(prims4.size() / 4);
 
     // rtcCommitScene: BVH over all triangle geometries; spheres are kept in a flat list.  The geometry goes to the device first:
     // the default builder runs there (option "bvh_builder" = 0 selects the host binned-SAH builder instead).
     int rc;
     auto &A = ctx->allocations;
     if ((rc = upload(ctx, (const float4 *)ctx->positions4.data(), ctx->positions4.size() / 4, &s.positions, A))) { return rc; }
-    if ((rc = upload(ctx, (const uint4 *)ctx->prims4.data(), ctx->prims4.size() / 4, &s.prims, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint4 *)prims4.data(), prims4.size() / 4, &s.prims, A))) { return rc; }
+    const float4 *buildPositions = s.positions; const uint4 *buildPrims = s.prims; // what the BVH is built over: world-space triangles
+    const std::vector<float> &hostBuildPositions = instanced ? worldPos4 : ctx->positions4;
+    const std::vector<uint32_t> &hostBuildPrims = instanced ? worldPrims4 : ctx->prims4;
+    if (instanced) {
+        if ((rc = upload(ctx, (const float4 *)worldPos4.data(), worldPos4.size() / 4, &buildPositions, A))) { return rc; }
+        if ((rc = upload(ctx, (const uint4 *)worldPrims4.data(), worldPrims4.size() / 4, &buildPrims, A))) { return rc; }
+        s.instIds = nullptr;
+        if ((rc = upload(ctx, (const uint2 *)flatInst2.data(), flatInst2.size() / 2, &s.instIds, A))) { return rc; }
+    } else { s.instIds = nullptr; }
     {
         const auto buildStart = std::chrono::steady_clock::now();
         try {
             if (ctx->bvhBuilder == 1) {
                 DeviceWideBVH built;
-                buildWideBVHDevice(s.positions, s.prims, nPrims, ctx->stream, built);
+                buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built);
                 if (built.nodes) { A.push_back(built.nodes); }
                 if (built.triangles) { A.push_back(built.triangles); }
                 s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
@@ -1228,7 +1369,7 @@ int ptc_commit(ptc_ctx *ctx)
                     CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.triangles.data(), built.triangles, (size_t)built.nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
                 }
             } else {
-                buildWideBVH(ctx->positions4.data(), ctx->prims4.data(), nPrims, ctx->bvh);
+                buildWideBVH(hostBuildPositions.data(), hostBuildPrims.data(), nPrims, ctx->bvh);
                 if ((rc = upload(ctx, (const float4 *)ctx->bvh.nodes.data(), ctx->bvh.nodes.size() * 5, &s.bvh.nodes, A))) { return rc; }
                 if ((rc = upload(ctx, (const float4 *)ctx->bvh.triangles.data(), ctx->bvh.triangles.size() * 3, &s.bvh.triangles, A))) { return rc; }
                 s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
@@ -1271,11 +1412,12 @@ int ptc_commit(ptc_ctx *ctx)
     // light table: emissive surfaces in registration order, environment light last (src/scene_parser.cpp:173-190)
     std::vector<DLight> lights;
     std::vector<float> spheres4; std::vector<uint32_t> sphereIds2;
-    for (size_t g = 0; g < ctx->geometries.size(); g++) {
-        const HostGeometry &ge = ctx->geometries[g];
+    for (uint32_t member : ctx->scenes[0].members) { // only root-scene surfaces become lights (src/scene_parser.cpp:173-182)
+        const HostGeometry &ge = ctx->geometries[member];
+        if (ge.isInstance) { continue; }
         if (ge.isSphere) {
             spheres4.insert(spheres4.end(), ge.centerRadius, ge.centerRadius + 4);
-            sphereIds2.insert(sphereIds2.end(), {(uint32_t)g, ge.sphereMaterial});
+            sphereIds2.insert(sphereIds2.end(), {ge.localId, ge.sphereMaterial});
             if (dm[ge.sphereMaterial].emitter) {
                 DLight l; memset(&l, 0, sizeof(l)); l.kind = 1;
                 memcpy(l.centerRadius, ge.centerRadius, sizeof(l.centerRadius));
@@ -1305,7 +1447,7 @@ int ptc_commit(ptc_ctx *ctx)
     { // per-triangle shading records (shading.cuh: DScene::triShade); Ng = e2 x e1 with the fused multiply-subtracts of triangleNg
         std::vector<float> rec((size_t)nPrims * 20, 0.f);
         for (uint32_t p = 0; p < nPrims; p++) {
-            const uint32_t *ix = &ctx->prims4[4 * (size_t)p];
+            const uint32_t *ix = &prims4[4 * (size_t)p];
             const float *v0 = &ctx->positions4[4 * (size_t)ix[0]], *v1 = &ctx->positions4[4 * (size_t)ix[1]], *v2 = &ctx->positions4[4 * (size_t)ix[2]];
             const float e1x = v0[0] - v1[0], e1y = v0[1] - v1[1], e1z = v0[2] - v1[2];
             const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
@@ -1321,7 +1463,7 @@ int ptc_commit(ptc_ctx *ctx)
         }
         if ((rc = upload(ctx, (const float4 *)rec.data(), rec.size() / 4, &s.triShade, A))) { return rc; }
     }
-    if ((rc = upload(ctx, (const uint2 *)ctx->primIds2.data(), ctx->primIds2.size() / 2, &s.primIds, A))) { return rc; }
+    if ((rc = upload(ctx, (const uint2 *)primIds2.data(), primIds2.size() / 2, &s.primIds, A))) { return rc; }
     if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
     if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }
     if ((rc = upload(ctx, lights.data(), lights.size(), &s.lights, A))) { return rc; }
@@ -1400,20 +1542,19 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
     PathBuffers &pb = ctx->paths;
-    float4 **f4[] = {&pb.out};
-    for (float4 **slot : f4) {
-        CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(float4)));
-        ctx->pathAllocations.push_back(*slot);
-    }
-    PairedField *pairs[4][2] = {{&pb.rayO, &pb.rayD}, {&pb.hit, &pb.result}, {&pb.modPdf, &pb.thrCos}, {&pb.nee, &pb.shadowD}};
-    for (auto &pair : pairs) { // one buffer per pair: interleaved records, or two plain arrays back to back
+    CUDA_TRY(ctx, cudaMalloc((void **)&pb.out, (size_t)capacity * sizeof(float4)));
+    ctx->pathAllocations.push_back(pb.out);
+    // one buffer of 32-byte records per pair of fields; (rayO, rayD) and (modPdf, result) exist twice (current / next)
+    PairedField *pairs[6][2] = {{&pb.rayO, &pb.rayD}, {&pb.nRayO, &pb.nRayD}, {&pb.modPdf, &pb.result}, {&pb.nModPdf, &pb.nResult},
+                                {&pb.hit, &pb.thrCos}, {&pb.nee, &pb.shadowD}};
+    for (auto &pair : pairs) {
         float4 *buffer = nullptr;
         CUDA_TRY(ctx, cudaMalloc((void **)&buffer, (size_t)capacity * 2 * sizeof(float4)));
         ctx->pathAllocations.push_back(buffer);
         pair[0]->base = buffer;
-        pair[1]->base = PTC_PAIRED_STATE ? buffer + 1 : buffer + capacity;
+        pair[1]->base = buffer + 1;
     }
-    uint32_t **u32[] = {&pb.extendQueue[0], &pb.extendQueue[1], &pb.shadowQueue};
+    uint32_t **u32[] = {&pb.origin, &pb.nOrigin, &pb.shadowQueue};
     for (uint32_t **slot : u32) {
         CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(uint32_t)));
         ctx->pathAllocations.push_back(*slot);
@@ -1432,7 +1573,7 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
 static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream)
 {
     const DScene &s = ctx->scene;
-    PathBuffers &pb = ctx->paths;
+    PathBuffers pb = ctx->paths; // by value: the current / next buffers swap after every bounce
     BounceCounters *cnt = ctx->counters;
     CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(BounceCounters), stream));
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
@@ -1445,12 +1586,12 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     // ray k leaves vertex k (k = 0: camera ray).  Ray k feeds direct() of vertex k and creates vertex k + 1, so rays
     // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
     for (int k = 0; k <= wp.lastBounce; k++) {
-        uint32_t *queue = pb.extendQueue[k & 1], *next = pb.extendQueue[(k + 1) & 1];
         BounceCounters *bc = cnt + k;
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
-            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, &bc->extendCount, &bc->extendCursor, work); }
-            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, queue, &bc->extendCount, &bc->extendCursor, work); }
+            // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
+            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
         }
         if (k > 0) {
             StageTimer t(ctx, stream, STAGE_SHADOW);
@@ -1460,18 +1601,21 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
-            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, queue, bc, ctx->classMask);
-            if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, queue, bc); ctx->launches++; }
+            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask);
+            if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
             const int g = ctx->gridShade;
-            if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, next, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
         }
         ctx->launches += k > 0 ? 3 : 2;
+        // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
+        std::swap(pb.rayO, pb.nRayO); std::swap(pb.rayD, pb.nRayD); std::swap(pb.modPdf, pb.nModPdf); std::swap(pb.result, pb.nResult);
+        std::swap(pb.origin, pb.nOrigin);
     }
     {
         StageTimer t(ctx, stream, STAGE_OTHER);
@@ -1697,7 +1841,19 @@ int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits)
 {
     NEED_COMMIT(ctx);
     if (n && (!rays || !hits)) { return PTC_ERR_INVALID; }
-    return roundTrip(ctx, rays, n, hits, n, [&](ptc_ray *d, ptc_hit *o) { intersectKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+    return roundTrip(ctx, rays, n, hits, n, [&](ptc_ray *d, ptc_hit *o) { intersectKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o, nullptr); });
+}
+int ptc_intersect_instanced(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits, uint32_t *instIds)
+{
+    NEED_COMMIT(ctx);
+    if (n && (!rays || !hits || !instIds)) { return PTC_ERR_INVALID; }
+    uint2 *dInst = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dInst, std::max<size_t>(n, 1) * sizeof(uint2)));
+    const int rc = roundTrip(ctx, rays, n, hits, n, [&](ptc_ray *d, ptc_hit *o) { intersectKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o, dInst); });
+    if (!rc) { cudaMemcpy(instIds, dInst, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost); }
+    cudaFree(dInst);
+    return rc;
 }
 int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out)
 {
@@ -1761,7 +1917,7 @@ int ptc_intersect_volumetric(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_
 int ptc_intersect_device(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits, void *stream)
 {
     NEED_COMMIT(ctx);
-    intersectKernel<<<gridFor(ctx, n), 128, 0, (cudaStream_t)stream>>>(ctx->scene, rays, n, hits);
+    intersectKernel<<<gridFor(ctx, n), 128, 0, (cudaStream_t)stream>>>(ctx->scene, rays, n, hits, nullptr);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return PTC_OK;

@@ -42,6 +42,9 @@ int sinkCommit(void *c) { return ptc_commit((ptc_ctx *)c); }
 int sinkTexture(void *c, const uint8_t *rgb, int w, int h, uint32_t *id) { return ptc_add_texture((ptc_ctx *)c, rgb, w, h, id); }
 int sinkMedium(void *c, const float *st, const float *ss, uint32_t *id) { return ptc_add_medium((ptc_ctx *)c, st, ss, id); }
 int sinkInternalMedium(void *c, uint32_t geom, uint32_t medium) { return ptc_set_internal_medium((ptc_ctx *)c, geom, medium); }
+int sinkBeginInstance(void *c, uint32_t *scene) { return ptc_begin_instance((ptc_ctx *)c, scene); }
+int sinkEndInstance(void *c) { return ptc_end_instance((ptc_ctx *)c); }
+int sinkAddInstance(void *c, uint32_t scene, const float *m, uint32_t *g) { return ptc_add_instance((ptc_ctx *)c, scene, m, g); }
 
 double now()
 {
@@ -60,7 +63,7 @@ Scene::Scene(const SceneDescription &description, int gpus) : m_width(descriptio
             throw std::runtime_error("Failed to create device " + std::to_string(device) + " (no CUDA device? there is no CPU path)");
         }
         m_contexts.push_back(ctx);
-        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium};
+        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium, sinkBeginInstance, sinkEndInstance, sinkAddInstance};
         const int status = feedScene(description, sink);
         if (status != PTC_OK) {
             const std::string message = ptc_last_error(ctx);

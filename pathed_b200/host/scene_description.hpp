@@ -21,6 +21,17 @@ struct GeometryDesc {
     uint32_t sphereMaterial = 0;
     // "internal_medium" of the model (src/scene_parser.cpp:324-343, :370-381, :503-514): index into SceneDescription::media, -1 none
     int internalMedium = -1;
+    // "instanced" model (src/scene_parser.cpp:449-492): a placement of SceneDescription::instanceScenes[instanceScene] under a
+    // column-major 4x4 local-to-world matrix; it takes a geometry id like any other geometry (rtcAttachGeometry)
+    bool isInstance = false;
+    uint32_t instanceScene = 0;
+    float instanceTransform[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+};
+
+// "instance" model (parseInstance, src/scene_parser.cpp:231-249): a named scene of its own (rtcNewScene) that "instanced" models place
+struct InstanceSceneDesc {
+    std::string name;
+    std::vector<GeometryDesc> geometries; // index == geometry id inside the instance scene
 };
 
 struct MediumDesc { // HomogeneousMedium (include/homogeneous_medium.h), parseMedia src/scene_parser.cpp:202-229
@@ -55,6 +66,7 @@ struct SceneDescription {
     std::vector<ptc_material_desc> materials;
     std::vector<MediumDesc> media;
     std::vector<GeometryDesc> geometries; // index == Embree geomID
+    std::vector<InstanceSceneDesc> instanceScenes; // in order of completion: a scene only places scenes that come before it
     CameraDesc camera;
     EnvironmentDesc environment;
 };
@@ -73,6 +85,10 @@ struct SceneSink {
     int (*add_texture)(void *, const uint8_t *, int, int, uint32_t *);
     int (*add_medium)(void *, const float *, const float *, uint32_t *);
     int (*set_internal_medium)(void *, uint32_t, uint32_t);
+    // SURVEY 8(f) N4 (may be null for a sink that does not take instances: feeding a scene that has some then fails)
+    int (*begin_instance)(void *, uint32_t *);
+    int (*end_instance)(void *);
+    int (*add_instance)(void *, uint32_t, const float *, uint32_t *);
 };
 
 // returns the first non-zero status of the sink, 0 on success

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <functional>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 
@@ -230,16 +232,24 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
         return it == mediaLookup.end() ? -1 : it->second;
     };
 
-    // models, src/scene_parser.cpp:251-291; geometry ids follow attach order
-    for (const Json &object : sceneJson["models"].items()) {
+    // models, parseObjects src/scene_parser.cpp:251-291; geometry ids follow attach order inside the scene being filled
+    // (`out`: the root scene's list, or an instance scene's while parseInstance recurses)
+    std::map<std::string, uint32_t> instanceLookup; // InstanceMap: name -> index into scene.instanceScenes
+    std::function<void(const Json &, std::vector<GeometryDesc> &, bool)> parseObjects = [&](const Json &models, std::vector<GeometryDesc> &out, bool isRoot) {
+    for (const Json &object : models.items()) {
         if (parseBool(object["skip"], false)) { continue; }
         const std::string type = parseString(object["type"], "");
+        if (!isRoot && (type == "ply" || type == "sphere" || type == "quad")) {
+            // the reference attaches these to the GLOBAL Embree scene even inside an instance definition (src/ply_parser.cpp:143,
+            // src/sphere.cpp:46, src/quad.cpp:149) while registering their surfaces with the instance scene: its tables go out of step
+            throw std::runtime_error("model type '" + type + "' inside an instance: only obj meshes can be instanced");
+        }
         if (type == "obj") {
             const Transform transform = parseTransformOrIdentity(object["transform"]);
             const int material = parseMaterial(object["bsdf"], lookup, scene);
-            scene.geometries.push_back(parseObj(resolve(root, object["filename"].asString()), root, transform, lookup,
+            out.push_back(parseObj(resolve(root, object["filename"].asString()), root, transform, lookup,
                                                 parseString(object["materialPrefix"], ""), material, scene));
-            scene.geometries.back().internalMedium = internalMedium(object);
+            out.back().internalMedium = internalMedium(object);
         } else if (type == "ply") {
             const Transform transform = parseTransformOrIdentity(object["transform"]);
             int material = parseMaterial(object["bsdf"], lookup, scene);
@@ -249,8 +259,8 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
                 scene.materials.push_back(d);
                 material = (int)scene.materials.size() - 1;
             }
-            scene.geometries.push_back(parsePly(resolve(root, object["filename"].asString()), transform, (uint32_t)material));
-            scene.geometries.back().internalMedium = internalMedium(object);
+            out.push_back(parsePly(resolve(root, object["filename"].asString()), transform, (uint32_t)material));
+            out.back().internalMedium = internalMedium(object);
         } else if (type == "sphere") {
             const int material = parseMaterial(object["bsdf"], lookup, scene);
             if (material < 0) { throw std::runtime_error("sphere without bsdf"); }
@@ -264,7 +274,7 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
             g.centerRadius[3] = parseFloat(object["radius"]);
             g.sphereMaterial = (uint32_t)material;
             g.internalMedium = internalMedium(object);
-            scene.geometries.push_back(g);
+            out.push_back(g);
         } else if (type == "quad") {
             const int material = parseMaterial(object["bsdf"], lookup, scene);
             if (material < 0) { throw std::runtime_error("quad without bsdf"); }
@@ -274,12 +284,28 @@ SceneDescription parseScene(const std::string &sceneJsonPath, const std::string 
                 const std::string axis = object["upAxis"].asString();
                 if (axis == "z") { zUp = true; } else if (axis != "y") { throw std::runtime_error("Unsupported axis: " + axis); }
             }
-            scene.geometries.push_back(makeQuad(transform, (uint32_t)material, zUp));
-        } else if (type == "instance" || type == "instanced" || type == "pbrt-curve" || type == "b-spline") {
+            out.push_back(makeQuad(transform, (uint32_t)material, zUp));
+        } else if (type == "instance") { // parseInstance, src/scene_parser.cpp:231-249
+            InstanceSceneDesc definition;
+            definition.name = parseString(object["name"], "");
+            parseObjects(object["models"], definition.geometries, false);
+            instanceLookup[definition.name] = (uint32_t)scene.instanceScenes.size(); // instanceLookup[name] = ...: the last one wins
+            scene.instanceScenes.push_back(std::move(definition));
+        } else if (type == "instanced") { // parseInstanced, src/scene_parser.cpp:449-492
+            auto known = instanceLookup.find(parseString(object["instance_name"], ""));
+            if (known == instanceLookup.end()) { throw std::runtime_error("instanced: unknown instance_name " + parseString(object["instance_name"], "<missing>")); }
+            GeometryDesc g;
+            g.isInstance = true;
+            g.instanceScene = known->second;
+            for (size_t k = 0; k < 16; k++) { g.instanceTransform[k] = parseFloat(object["transform"][k]); } // RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR
+            out.push_back(g);
+        } else if (type == "pbrt-curve" || type == "b-spline") {
             throw std::runtime_error("model type '" + type + "' is outside the surface path-tracing hot path (SURVEY §8(f))");
         }
         // unknown types are silently ignored, like the reference's if-chain
     }
+    };
+    parseObjects(sceneJson["models"], scene.geometries, true);
 
     // environment light, src/scene_parser.cpp:544-557
     const Json &environment = sceneJson["environmentLight"];
@@ -310,20 +336,36 @@ int feedScene(const SceneDescription &scene, const SceneSink &sink)
         if (!sink.add_medium) { return PTC_ERR_INVALID; }
         if ((status = sink.add_medium(sink.ctx, medium.sigmaT, medium.sigmaS, nullptr))) { return status; }
     }
-    for (const GeometryDesc &g : scene.geometries) {
+    std::vector<uint32_t> sinkScene(scene.instanceScenes.size(), 0); // instance scene -> the id the sink gave it
+    auto feedGeometry = [&](const GeometryDesc &g, bool isRoot) -> int {
         uint32_t geomId = 0;
-        if (g.isSphere) { status = sink.add_sphere(sink.ctx, g.centerRadius, g.sphereMaterial, &geomId); }
+        int rc;
+        if (g.isInstance) {
+            if (!sink.add_instance || g.instanceScene >= sinkScene.size()) { return PTC_ERR_INVALID; }
+            return sink.add_instance(sink.ctx, sinkScene[g.instanceScene], g.instanceTransform, &geomId);
+        }
+        if (g.isSphere) { rc = sink.add_sphere(sink.ctx, g.centerRadius, g.sphereMaterial, &geomId); }
         else {
-            status = sink.add_triangle_mesh(sink.ctx, g.positions.data(), g.normals.data(), g.uvs.data(),
-                                            (uint32_t)(g.positions.size() / 3), g.indices.data(), g.materialOfTri.data(),
-                                            (uint32_t)g.materialOfTri.size(), &geomId);
+            rc = sink.add_triangle_mesh(sink.ctx, g.positions.data(), g.normals.data(), g.uvs.data(),
+                                        (uint32_t)(g.positions.size() / 3), g.indices.data(), g.materialOfTri.data(),
+                                        (uint32_t)g.materialOfTri.size(), &geomId);
         }
-        if (status) { return status; }
-        if (g.internalMedium >= 0) {
+        if (rc) { return rc; }
+        if (g.internalMedium >= 0 && isRoot) {
             if (!sink.set_internal_medium) { return PTC_ERR_INVALID; }
-            if ((status = sink.set_internal_medium(sink.ctx, geomId, (uint32_t)g.internalMedium))) { return status; }
+            if ((rc = sink.set_internal_medium(sink.ctx, geomId, (uint32_t)g.internalMedium))) { return rc; }
         }
+        return 0;
+    };
+    // instance definitions first, in order of completion (a scene only places scenes defined before it), each in its own
+    // begin / end pair; then the root scene's geometries
+    for (size_t i = 0; i < scene.instanceScenes.size(); i++) {
+        if (!sink.begin_instance || !sink.end_instance) { return PTC_ERR_INVALID; }
+        if ((status = sink.begin_instance(sink.ctx, &sinkScene[i]))) { return status; }
+        for (const GeometryDesc &g : scene.instanceScenes[i].geometries) { if ((status = feedGeometry(g, false))) { return status; } }
+        if ((status = sink.end_instance(sink.ctx))) { return status; }
     }
+    for (const GeometryDesc &g : scene.geometries) { if ((status = feedGeometry(g, true))) { return status; } }
     if (scene.environment.present) {
         const EnvironmentDesc &e = scene.environment;
         if ((status = sink.set_environment(sink.ctx, e.rgba.data(), e.width, e.height, e.scale, e.mapToWorld, e.worldToMap))) { return status; }

@@ -40,15 +40,18 @@ def test_bsdf_matches_reference(name):
     f, pdf = ctx.bsdf_eval(mat, isects, wi)
     ok_f, e_f = frac_within(f, g["f"])
     ok_p, e_p = frac_within(pdf, g["pdf"])
-    # libdevice expf/sinf/acosf differ from glibc by <= 2 ulp; exp(-tan^2/alpha^2) amplifies that for narrow lobes
-    assert ok_f >= 0.98 and e_f.max() < 2e-4, (ok_f, e_f.max())
-    assert ok_p >= 0.98 and e_p.max() < 2e-4, (ok_p, e_p.max())
+    # eval and pdf: every tuple of every configuration within 1e-5 (measured on 2^16 tuples: <= 1.8e-6, tests/golden/bsdf_error_table.json)
+    assert ok_f == 1.0 and ok_p == 1.0, (ok_f, e_f.max(), ok_p, e_p.max())
     swi, spdf, sthr = ctx.bsdf_sample(mat, isects, xi)
     ok_wi, e_wi = frac_within(swi, g["sample_wi"])
-    ok_pdf, e_pdf = frac_within(spdf, g["sample_pdf"], tol=2e-5)
-    ok_thr, e_thr = frac_within(sthr, g["sample_throughput"], tol=2e-5)
-    assert ok_wi >= 0.99 and e_wi.max() < 1e-3, (ok_wi, e_wi.max())
-    assert ok_pdf >= 0.97 and ok_thr >= 0.97, (ok_pdf, ok_thr, e_pdf.max(), e_thr.max())
+    ok_pdf, e_pdf = frac_within(spdf, g["sample_pdf"])
+    ok_thr, e_thr = frac_within(sthr, g["sample_throughput"])
+    if BSDF_CONFIGS[name]["type"] in (4, 5):
+        # what sample() of the microfacet family returns is ill-conditioned in the sampled direction, which goes through the host's
+        # libm (see tests/test_large_batches.py): at most one of the 512 tuples may leave 1e-5, and never by more than 5e-4
+        assert min(ok_wi, ok_pdf, ok_thr) >= 1.0 - 1.5 / len(spdf) and max(e_wi.max(), e_pdf.max(), e_thr.max()) <= 5e-4, (ok_wi, ok_pdf, ok_thr)
+    else:
+        assert ok_wi == 1.0 and ok_pdf == 1.0 and ok_thr == 1.0, (ok_wi, e_wi.max(), ok_pdf, e_pdf.max(), ok_thr, e_thr.max())
 
 
 def test_shape_lights_match_reference():
@@ -106,6 +109,9 @@ def test_intersection_matches_embree(name):
         assert frac_within(full["point"][ok], g[prefix + "point"][ok])[0] >= 0.9999
         assert frac_within(full["shading_normal"][ok], g[prefix + "shading_normal"][ok], tol=2e-5)[0] >= 0.999
     occ = ctx.occluded(to_rays(g["shadow_rays"]), g["shadow_max_t"])
+    # this 2-8 k-ray fixture joins pairs of surface points, many of them in one plane with a box resting on it (knife-edge
+    # hits along the box's base, where Embree's exact node test culls what the inclusive triangle test would accept): at most a few
+    # rays differ.  The north-star gate (>= 99.99 % on 2^20 NEE shadow rays per scene) is tests/test_large_batches.py.
     assert (occ == g["shadow_occluded"]).mean() >= 0.999
     if "ls_ref" in g:
         m = len(g["ls_ref"])
@@ -133,7 +139,7 @@ def test_paths_match_reference_with_replayed_stream(name):
     rgb = ctx.radiance_replay(to_rays(g["cam_rays"][:m]), xi, 0, cfg["last_bounce"])
     ok, e = frac_within(rgb, g["path_rgb"], tol=1e-4, floor=1e-4)
     print(name, "paths within 1e-4:", ok)
-    assert ok >= 0.985, (ok, np.sort(e)[-10:])
+    assert ok >= 0.998, (ok, np.sort(e)[-10:])  # measured: 0.9990 - 1.0 (a path whose branch flips on the last bit of a libm result)
     assert abs(rgb.mean() - g["path_rgb"].mean()) <= 0.02 * abs(g["path_rgb"].mean()) + 1e-6
 
 
@@ -158,7 +164,7 @@ def test_wavefront_render_matches_oracle_per_pixel(name):
     err = np.abs(img - ref) / (np.abs(ref) + 1e-3 * max(ref.mean(), 1e-3))
     frac = float((err.max(-1) < 1e-3).mean())
     print(name, "pixels within 1e-3:", frac, "mean", img.mean(), ref.mean())
-    assert frac >= 0.97
+    assert frac >= 0.995  # measured: 1.0 on every scene
     assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean() + 1e-7
 
 

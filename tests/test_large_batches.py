@@ -159,7 +159,8 @@ def test_cuda_intersection_matches_oracle_on_fresh_full_size_dragon_rays():
 # by tools/measure_parity.py on the B200), and (b) exactly, by test_cuda_sampled_pdf_is_the_reference_pdf_of_the_sampled_direction.
 MICROFACET_FAMILY = {"beckmann_0005", "beckmann_002", "beckmann_005", "beckmann_01", "beckmann_05", "ggx_01", "ggx_05",
                      "plastic_dragon", "plastic_ggx", "plastic_plate1", "plastic_textured"}
-SAMPLE_SLACK = {"sample_pdf": (0.995, 5e-3), "sample_throughput": (0.995, 5e-3), "sample_wi": (0.9999, 1e-4)}  # (fraction, cap)
+# (fraction within 1e-5, cap on the largest error); measured worst cases: pdf 0.99988 / 1.2e-4 (ggx_05), throughput 0.99976 / 7.7e-5, wi 0.99998 / 1.3e-5
+SAMPLE_SLACK = {"sample_pdf": (0.9995, 5e-4), "sample_throughput": (0.9995, 5e-4), "sample_wi": (0.9999, 5e-5)}
 
 
 def _gpu_bsdf(name, n):
