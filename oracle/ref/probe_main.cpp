@@ -163,6 +163,28 @@ void ref_intersect_raw(
     }
 }
 
+// RTCHit::instID of the same query (hierarchical instancing, RTC_MAX_INSTANCE_LEVEL_COUNT = 2)
+void ref_intersect_inst(int n, const float *rays, unsigned *instID /*2n*/)
+{
+    #pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        RTCRayHit rh;
+        rh.ray.org_x = rays[6 * i + 0]; rh.ray.org_y = rays[6 * i + 1]; rh.ray.org_z = rays[6 * i + 2];
+        rh.ray.dir_x = rays[6 * i + 3]; rh.ray.dir_y = rays[6 * i + 4]; rh.ray.dir_z = rays[6 * i + 5];
+        rh.ray.tnear = 1e-3f; rh.ray.tfar = 1e5f; rh.ray.flags = 0; rh.ray.time = 0.f; rh.ray.mask = -1;
+        rh.hit.geomID = RTC_INVALID_GEOMETRY_ID;
+        for (int l = 0; l < RTC_MAX_INSTANCE_LEVEL_COUNT; l++) { rh.hit.instID[l] = RTC_INVALID_GEOMETRY_ID; }
+        CustomRTCIntersectContext context;
+        rtcInitIntersectContext(&context.context);
+        context.rtcManagerPtr = nullptr;
+        context.shouldIntersectPassthroughs = true;
+        rtcIntersect1(g_rtcScene, &context.context, &rh);
+        const bool hit = rh.hit.geomID != RTC_INVALID_GEOMETRY_ID;
+        instID[2 * i] = hit ? rh.hit.instID[0] : RTC_INVALID_GEOMETRY_ID;
+        instID[2 * i + 1] = hit && RTC_MAX_INSTANCE_LEVEL_COUNT > 1 ? rh.hit.instID[1] : RTC_INVALID_GEOMETRY_ID;
+    }
+}
+
 // processed Intersection as the integrator sees it
 void ref_intersect(
     int n, const float *rays,

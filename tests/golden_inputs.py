@@ -271,6 +271,10 @@ SCENES = {
     "cornell_medium_pt": dict(scene="scenes/cornell-medium.json", width=64, height=64, last_bounce=10, seed=20, n_rays=2048,
                               n_paths=2048, image_width=64, image_height=64, image_spp=2048, integrator=0, image_noise=3.0),
 }
+# hierarchical instancing -- `instance` / `instanced` models, two levels, rotated / scaled / mirrored placements; the ray
+# fixtures carry RTCHit::instID
+SCENES["instanced"] = dict(scene="scenes/instanced.json", width=96, height=72, last_bounce=10, seed=21, n_rays=8192, n_paths=2048,
+                           image_width=96, image_height=72, image_spp=2048, instanced=True)
 INTEGRATOR_NAMES = {0: "PathTracer", 1: "VolumePathTracer"}
 
 

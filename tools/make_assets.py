@@ -17,6 +17,7 @@ and the CUDA path read byte-identical inputs:
   scenes/teapot.json             glass surface-of-revolution "teapot" body + lid, checkerboard quad, env map
   test_scenes/1_pixel_test.exr   1000x500 environment map, one texel = 10000 at row 239, col 753
   test_scenes/environment_map_sampling.json   white quad lit only by that map
+  scenes/instanced.json          SURVEY N4: `instance` / `instanced` models, two instance levels, rotated / scaled / mirrored placements
 
 Outputs are git-ignored (scenes/, assets/, test_scenes/ are listed in .gitignore) and travel with gpurun.
 Usage: python tools/make_assets.py [--root DIR] [--dragon-segments N] [--force]
@@ -542,6 +543,65 @@ def make_textured(root):
     })
 
 
+# ----------------------------------------------------------------------------------------- instancing
+def column_major(rows):
+    """4x4 given as rows -> the 16 strings of an `instanced` model's transform (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR)"""
+    m = np.asarray(rows, np.float64).reshape(4, 4)
+    return [s(float(np.float32(v))) for v in m.T.reshape(-1)]
+
+
+def trs(translate, rotate_y_deg=0.0, rotate_x_deg=0.0, scale=(1.0, 1.0, 1.0)):
+    ry, rx = math.radians(rotate_y_deg), math.radians(rotate_x_deg)
+    S = np.diag([scale[0], scale[1], scale[2], 1.0])
+    Ry = np.array([[math.cos(ry), 0, math.sin(ry), 0], [0, 1, 0, 0], [-math.sin(ry), 0, math.cos(ry), 0], [0, 0, 0, 1]])
+    Rx = np.array([[1, 0, 0, 0], [0, math.cos(rx), -math.sin(rx), 0], [0, math.sin(rx), math.cos(rx), 0], [0, 0, 0, 1]])
+    T = np.eye(4); T[:3, 3] = translate
+    return T @ Ry @ Rx @ S
+
+
+def make_instanced(root):
+    """scenes/instanced.json: no scene of the reference uses `instance` / `instanced`, so this one exercises the parser paths
+    (src/scene_parser.cpp:231-249, :449-492) and both instance levels: a smooth-shaded blob (v//vn faces) and a flat-shaded box
+    (no normals: n_s = n_g) defined once, placed under rotations, non-uniform scales and a mirroring, and a `cluster` instance
+    scene that itself places the blob twice (instID[0] = cluster placement, instID[1] = blob placement)."""
+    d = os.path.join(root, "assets/instanced")
+    os.makedirs(d, exist_ok=True)
+    verts, normals, faces = uv_sphere((0.0, 0.0, 0.0), 1.0, segments=24, rings=11)
+    bump = 1.0 + 0.25 * np.sin(3.0 * verts[:, 0]) * np.cos(2.0 * verts[:, 2])  # not a sphere: hits depend on the rotation
+    write_obj(os.path.join(d, "blob.obj"), verts * bump[:, None] * 0.3, faces, normals, header="# instanced blob, tools/make_assets.py\n")
+    lines = ["# instanced box, tools/make_assets.py"]
+    for quad in closed_box((-0.25, 0.0, -0.25), (0.25, 0.5, 0.25)):
+        lines += ["v %.4f %.4f %.4f" % p for p in quad] + ["f -4 -3 -2", "f -2 -1 -4"]
+    write_text(os.path.join(d, "box.obj"), "\n".join(lines) + "\n")
+    blob = {"type": "obj", "filename": "assets/instanced/blob.obj",
+            "bsdf": {"type": "plastic", "diffuseReflectance": vec(0.6, 0.25, 0.2), "distribution": {"type": "beckmann", "alpha": s(0.2)}}}
+    box = {"type": "obj", "filename": "assets/instanced/box.obj", "transform": {"translate": vec(0.0, 0.0, 0.0)},
+           "bsdf": {"type": "lambertian", "diffuseReflectance": vec(0.3, 0.5, 0.7)}}
+    mirror = np.diag([-1.0, 1.0, 1.0, 1.0])
+    write_json(os.path.join(root, "scenes/instanced.json"), {
+        "sensor": {"lookAt": {"origin": vec(0, 1.6, 4.2), "target": vec(0, 0.45, 0), "up": vec(0, 1, 0)}, "fov": s(36)},
+        "models": [
+            {"type": "quad", "transform": {"scale": vec(2.5, 1, 2.5)},  # geometry 0 of the root scene
+             "bsdf": {"type": "lambertian", "diffuseReflectance": vec(0.7, 0.7, 0.7)}},
+            {"type": "instance", "name": "blob", "models": [blob]},      # definitions take no geometry id
+            {"type": "instance", "name": "box", "models": [box]},
+            {"type": "instance", "name": "cluster", "models": [
+                {"type": "instanced", "instance_name": "blob", "transform": column_major(trs((0.35, 0.0, 0.0), 40.0, 0.0, (0.6, 0.6, 0.6)))},
+                {"type": "instanced", "instance_name": "blob", "transform": column_major(trs((-0.3, 0.15, 0.1), -70.0, 25.0, (0.5, 0.8, 0.5)))},
+                {"type": "obj", "filename": "assets/instanced/box.obj", "transform": {"scale": vec(0.4, 0.4, 0.4), "translate": vec(0.0, -0.35, 0.0)},
+                 "bsdf": {"type": "lambertian", "diffuseReflectance": vec(0.8, 0.7, 0.2)}},
+            ]},
+            {"type": "instanced", "instance_name": "blob", "transform": column_major(trs((-1.1, 0.45, 0.2), 30.0, 0.0, (1.0, 1.3, 1.0)))},   # geometry 1
+            {"type": "instanced", "instance_name": "box", "transform": column_major(trs((0.0, 0.0, -0.6), 35.0, 0.0, (1.2, 1.6, 0.8)))},     # geometry 2
+            {"type": "instanced", "instance_name": "box", "transform": column_major(trs((1.2, 0.0, 0.5), -20.0, 0.0) @ mirror)},              # 3: mirrored
+            {"type": "instanced", "instance_name": "cluster", "transform": column_major(trs((0.15, 0.75, 0.9), 15.0, 10.0, (0.9, 0.9, 0.9)))},  # 4
+            {"type": "instanced", "instance_name": "cluster", "transform": column_major(trs((-0.2, 1.35, -0.9), 200.0, -15.0, (1.1, 1.1, 1.1)))},  # 5
+            {"type": "quad", "transform": {"legacy": True, "scale": vec(0.7, 1, 0.7), "rotate": vec(180, 0, 0), "translate": vec(0, 3.0, 0.5)},  # 6
+             "bsdf": {"type": "lambertian", "diffuseReflectance": vec(0, 0, 0), "emit": vec(20, 19, 17)}},
+        ],
+    })
+
+
 # ----------------------------------------------------------------------------------------- test scenes
 def make_test_scenes(root):
     img = np.zeros((500, 1000, 3), np.float32)
@@ -567,10 +627,10 @@ def main():
     ap.add_argument("--dragon-segments", type=int, default=2048, help="knot segments along the curve (x212x2 triangles)")
     ap.add_argument("--force", action="store_true")
     args = ap.parse_args()
-    stamp = os.path.join(args.root, "assets/.generated-v4-%d" % args.dragon_segments)
+    stamp = os.path.join(args.root, "assets/.generated-v5-%d" % args.dragon_segments)
     expected = ["scenes/cornell.json", "scenes/cornell-glass.json", "scenes/dragon.json", "scenes/mis-pbrt.json", "scenes/teapot.json",
                 "assets/dragon.obj", "assets/20060807_wells6_hd.exr", "assets/teapot/envmap.exr", "test_scenes/1_pixel_test.exr",
-                "scenes/textured.json", "assets/textured/wood.png", "scenes/cornell-medium.json", "test_scenes/medium_sphere.json"]
+                "scenes/textured.json", "assets/textured/wood.png", "scenes/cornell-medium.json", "test_scenes/medium_sphere.json", "scenes/instanced.json", "assets/instanced/blob.obj"]
     if os.path.exists(stamp) and all(os.path.exists(os.path.join(args.root, f)) for f in expected) and not args.force:
         print("assets up to date:", stamp)
         return 0
@@ -581,6 +641,7 @@ def main():
     make_test_scenes(args.root)
     make_textured(args.root)
     make_cornell_medium(args.root)
+    make_instanced(args.root)
     make_dragon(args.root, args.dragon_segments)
     write_text(stamp, "ok\n")
     print("generated scenes/, assets/, test_scenes/ under", args.root)

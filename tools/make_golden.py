@@ -133,7 +133,12 @@ def trace(rays):
     nn = np.zeros((m, 3), np.float32); ns = np.zeros((m, 3), np.float32); tuv = np.zeros((m, 2), np.float32)
     em = np.zeros((m, 3), np.float32); dl = np.zeros(m, np.int32)
     lib.ref_intersect(m, fptr(rays), fptr(hit), fptr(t2), fptr(pt), fptr(nn), fptr(ns), fptr(tuv), fptr(em), fptr(dl))
-    return dict(t=t, geom=g, prim=p, bary=uv, ng=ng, hit=hit, point=pt, normal=nn, shading_normal=ns, tex_uv=tuv, emit=em, delta=dl)
+    res = dict(t=t, geom=g, prim=p, bary=uv, ng=ng, hit=hit, point=pt, normal=nn, shading_normal=ns, tex_uv=tuv, emit=em, delta=dl)
+    if cfg.get('instanced'):  # RTCHit::instID (SURVEY N4)
+        inst = np.zeros((m, 2), np.uint32)
+        lib.ref_intersect_inst(m, fptr(rays), fptr(inst))
+        res['inst'] = inst
+    return res
 
 first = trace(cam)
 for k, v in first.items(): out['cam_' + k] = v
