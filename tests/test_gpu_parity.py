@@ -114,7 +114,9 @@ def test_intersection_matches_embree(name):
             assert np.array_equal(inst[exact], g[prefix + "inst"][exact])
             assert (g[prefix + "inst"][:, 0] != 0xFFFFFFFF).sum() > 500 and (g[prefix + "inst"][:, 1] != 0xFFFFFFFF).sum() > 50  # both levels are exercised
         ok = agree & ref_hit & same_prim
-        assert frac_within(hits["u"][ok], g[prefix + "bary"][ok, 0], floor=1e-3, tol=1e-4)[0] >= (0.995 if cfg.get("instanced") else 0.999)
+        # flattened placements are intersected in world space, Embree's in the instance's space: barycentrics agree absolutely (1e-5), not
+        # relative to a small u
+        assert frac_within(hits["u"][ok], g[prefix + "bary"][ok, 0], floor=0.1 if cfg.get("instanced") else 1e-3, tol=1e-4)[0] >= 0.999
         # sphere Ng = td*D - perp cancels, and Embree's rd2 is an rcp + Newton step, so allow a few ulp more there
         assert frac_within(hits["ng"][ok], g[prefix + "ng"][ok], tol=1e-4)[0] >= (0.995 if cfg.get("instanced") else 0.999)
         full = ctx.intersect_full(rays)

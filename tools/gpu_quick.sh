@@ -1,7 +1,7 @@
+# quick GPU-box session: build, the GPU test suite, a short bench
 set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/s_build.log 2>&1
-( time timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 ) > gpurun_out/s_pytest.log 2>&1
-SWEEP_BENCH_ARGS="--steps 4" bash tools/sweep.sh "" "-DPTC_STREAM_STATE=0" > gpurun_out/s_sweep.log 2>&1; cp gpurun_out/sweep.txt gpurun_out/s_sweep.txt
-timeout 600 python tools/measure_parity.py gpurun_out/bsdf_error_table.json > gpurun_out/s_parity.log 2>&1
-tail -3 gpurun_out/s_pytest.log; cat gpurun_out/s_sweep.txt
+( time timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 ) > gpurun_out/s_pytest.log 2>&1
+timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/s_bench.log 2>&1
+tail -5 gpurun_out/s_pytest.log; tail -1 gpurun_out/s_bench.log | cut -c1-200
