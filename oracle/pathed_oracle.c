@@ -325,8 +325,11 @@ int orc_end_instance(orc_ctx *c)
     return PTC_OK;
 }
 
-/* Embree's AffineSpace3fa from a column-major 4x4 (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR) and its rcp(), common/math/affinespace.h:
- * il = adjoint(l) / det(l), p' = -(il * p) */
+/* Embree's AffineSpace3fa from a column-major 4x4 (RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR) and its rcp(), which Instance::setTransform
+ * (kernels/common/scene_instance.cpp:77-85, part of the lowest-ISA build: SSE2, no fused multiply-add, no dpps) stores as world2local0:
+ * common/math/affinespace.h:91 il = rcp(l), p' = -(il * p); linearspace3.h:57-63 il = adjoint(l) / det(l) -- a true division per
+ * element (vec3fa.h:187) --, det = dot(vx, cross(vy, vz)) summed as (x + y) + z (vec3fa.h:251-256), il * p = p.x*il.vx + (p.y*il.vy +
+ * p.z*il.vz) (linearspace3.h:159 with the non-FMA madd, vec3fa.h:225) */
 static void affine_inverse(const float l2w[12], float w2l[12])
 {
     /* rows of l2w: r0 = (m00 m01 m02 tx) ...; columns vx = (m00 m10 m20) ... */
@@ -335,13 +338,12 @@ static void affine_inverse(const float l2w[12], float w2l[12])
     const float cyz[3] = {vy[1] * vz[2] - vy[2] * vz[1], vy[2] * vz[0] - vy[0] * vz[2], vy[0] * vz[1] - vy[1] * vz[0]};
     const float czx[3] = {vz[1] * vx[2] - vz[2] * vx[1], vz[2] * vx[0] - vz[0] * vx[2], vz[0] * vx[1] - vz[1] * vx[0]};
     const float cxy[3] = {vx[1] * vy[2] - vx[2] * vy[1], vx[2] * vy[0] - vx[0] * vy[2], vx[0] * vy[1] - vx[1] * vy[0]};
-    const float det = vx[0] * cyz[0] + vx[1] * cyz[1] + vx[2] * cyz[2];
-    const float r = 1.f / det;
+    const float det = (vx[0] * cyz[0] + vx[1] * cyz[1]) + vx[2] * cyz[2];
     /* adjoint = rows (cyz, czx, cxy): inverse rows */
-    const float inv[9] = {cyz[0] * r, cyz[1] * r, cyz[2] * r, czx[0] * r, czx[1] * r, czx[2] * r, cxy[0] * r, cxy[1] * r, cxy[2] * r};
+    const float inv[9] = {cyz[0] / det, cyz[1] / det, cyz[2] / det, czx[0] / det, czx[1] / det, czx[2] / det, cxy[0] / det, cxy[1] / det, cxy[2] / det};
     for (int row = 0; row < 3; row++) {
         w2l[4 * row] = inv[3 * row]; w2l[4 * row + 1] = inv[3 * row + 1]; w2l[4 * row + 2] = inv[3 * row + 2];
-        w2l[4 * row + 3] = -(inv[3 * row] * px + inv[3 * row + 1] * py + inv[3 * row + 2] * pz);
+        w2l[4 * row + 3] = -(px * inv[3 * row] + (py * inv[3 * row + 1] + pz * inv[3 * row + 2]));
     }
 }
 

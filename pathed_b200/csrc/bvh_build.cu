@@ -371,6 +371,8 @@ bool traverseReference(const WideBVH &bvh, const float o[3], const float d[3], f
     view.nodes = (const float4 *)bvh.nodes.data();
     view.triangles = (const float4 *)bvh.triangles.data();
     view.spheres = nullptr; view.nSpheres = 0; view.nNodes = (uint32_t)bvh.nodes.size();
+    view.primEvent = nullptr; view.sphereEvent = nullptr;
+    view.placements = bvh.placements.empty() ? nullptr : (const float4 *)bvh.placements.data();
     RayHit hit; TraverseCounters c = {0, 0};
     const bool found = anyHit ? traverseBVH<true, true>(view, o[0], o[1], o[2], d[0], d[1], d[2], tnear, tfar, hit, &c)
                               : traverseBVH<false, true>(view, o[0], o[1], o[2], d[0], d[1], d[2], tnear, tfar, hit, &c);

@@ -33,10 +33,13 @@ using namespace ptc;
 // slot it gets in the NEXT bounce's ray list (one warp-aggregated append), so the paths alive at bounce k always occupy slots
 // 0 .. n_k - 1 of the state arrays and every stage reads and writes dense, coalesced records however few paths survive (replaces
 // the implicit `break`s of PathTracer::L, src/path_tracer.cpp:45,56-58; the slot a path started in -- pixel and sample, the Philox
-// key and the place its radiance is summed -- travels with it as `origin`).  Fields that a later kernel still reads at the old
-// slots are double-buffered (current / next); the rest are written at the new slot only after their last reader of the old slot
-// finished.  Fields that are touched together share one 32-byte record (PairedField): the class queues of the material stage
-// gather a subset of the slots, so both halves of every sector they touch are useful.
+// key and the place its radiance is written -- travels with it in the spare word of the ray record).
+// Layout rule: what one stage reads or writes TOGETHER is one 32-byte record moved by ONE 256-bit instruction (sm_100:
+// ld/st.global.v8.f32), what stages touch separately is a 16-byte array of its own -- so that every store covers whole 32-byte
+// sectors (a 16-byte store into half of a sector that is not in L2 costs a DRAM read to fill the other half plus a full-sector
+// write; measured on the earlier paired layout: +32 B read per hit record, per throughput record, ...).  Fields that a later kernel
+// still reads at the old slots are double-buffered (current / next); the rest are written at the new slot only after their last
+// reader of the old slot finished.
 // Path state is streamed: every record is read once and written once per stage, 15 GB per wave, while the scene data the same
 // kernels gather from (BVH, per-triangle shading records, environment map and its CDFs: ~160 MB for the dragon workload) is re-used
 // and should own the 126 MB L2.  PTC_STREAM_STATE = 1 issues the path-state accesses with the evict-first policy (ld.global.cs /
@@ -46,29 +49,43 @@ using namespace ptc;
 #endif
 template <typename T> __device__ __forceinline__ T streamLoad(const T *p) { return PTC_STREAM_STATE ? __ldcs(p) : *p; }
 template <typename T> __device__ __forceinline__ void streamStore(T *p, T v) { if (PTC_STREAM_STATE) { __stcs(p, v); } else { *p = v; } }
-struct StateRef { // `pb.field[p]` reads and writes like an element of a plain array
-    float4 *p;
-    __device__ __forceinline__ operator float4() const { return streamLoad(p); }
-    __device__ __forceinline__ void operator=(float4 v) const { streamStore(p, v); }
-};
-struct PairedField {
-    float4 *base;
-    __device__ __forceinline__ StateRef operator[](uint32_t p) const { StateRef r; r.p = base + 2 * (size_t)p; return r; }
-    __device__ __forceinline__ float *component(uint32_t p, int c) const { return reinterpret_cast<float *>(base + 2 * (size_t)p) + c; }
-};
+struct Rec32 { float4 a, b; };
+__device__ __forceinline__ Rec32 loadRec(const float4 *base, uint32_t slot) // 32-byte record `slot`: one LDG.256
+{
+    const float4 *p = base + 2 * (size_t)slot;
+    Rec32 r;
+#if PTC_STREAM_STATE
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void storeRec(float4 *base, uint32_t slot, const float4 a, const float4 b) // one STG.256: a whole sector
+{
+    float4 *p = base + 2 * (size_t)slot;
+#if PTC_STREAM_STATE
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#else
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+#endif
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 struct PathBuffers {
-    // current buffers: the state of the paths of this bounce, slots 0 .. n - 1
-    PairedField rayO, rayD;      // current ray (origin = current vertex)
-    PairedField modPdf, result;  // modulation rgb + pdf of the BSDF sample that produced the ray | L() accumulator rgb, w = flags
-    uint32_t *origin;            // slot the path started in: pixel / sample, i.e. its Philox key and its entry of `out`
-    // next buffers: written by the material stage at the slot the path takes in the next bounce
-    PairedField nRayO, nRayD, nModPdf, nResult;
-    uint32_t *nOrigin;
-    // single-buffered: written at the new slot (material stage) or at the current one (traversal), never read at an old slot afterwards
-    PairedField hit, thrCos;     // t, u, v, prim bits (traversal) | BSDF sample throughput rgb, |n_s . wi| (material stage)
-    PairedField nee, shadowD;    // pending light-sampling contribution rgb, w = 0 until the shadow stage finds the ray occluded (then 1)
-                                 // | shadow ray direction, w = distance to the light sample
-    float4 *out;                 // per-sample radiance by origin slot: camera-hit emission / environment, plus result at termination
+    // 32-byte records, current / next
+    float4 *ray, *nRay;          // a = ray origin (= current vertex) xyz, w = origin slot bits | b = ray direction xyz
+    float4 *modThr, *nModThr;    // a = modulation rgb up to the previous vertex, w = pdf of the BSDF sample that produced the ray |
+                                 // b = that sample's throughput rgb, w = |n_s . wi|.  The modulation up to THIS vertex is a product of
+                                 // the two halves (advanceModulation): the logic stage tests it, the material stage recomputes it
+    // 32-byte record, single-buffered (written by the material stage at the new slot, read by the next shadow and logic stages)
+    float4 *nee;                 // a = pending light-sampling contribution rgb | b = shadow ray direction, w = distance to the light sample
+    // 16-byte arrays
+    float4 *hit;                 // t, u, v, prim bits: written by the traversal, read by logic and material at the same slot
+    float4 *result, *nResult;    // L() accumulator rgb, w = flags (current / next)
+    uint8_t *occluded;           // outcome of the NEE shadow ray of the path in this slot (written for every traced shadow ray)
+    float4 *out;                 // per-sample radiance by origin slot, written once when the path ends (FLAG_BASE: added to the
+                                 // camera-hit emission the logic stage of bounce 0 stored there)
     uint32_t *shadowQueue;       // slots (next-bounce numbering) whose NEE shadow ray has to be traced
     uint32_t *classQueue[PTC_MATERIAL_CLASSES]; // survivors of the logic stage, binned by material class (null: class absent from the scene)
 };
@@ -77,6 +94,7 @@ struct PathBuffers {
 #define FLAG_DELTA 0x100u
 #define FLAG_DIRECT 0x200u
 #define FLAG_NEE 0x400u
+#define FLAG_BASE 0x800u /* out[origin] already holds the camera-hit emission of this path */
 
 struct WaveParams {
     uint64_t seed;
@@ -106,6 +124,28 @@ __device__ __forceinline__ uint32_t slotToPixel(uint32_t q, uint32_t width, uint
     return row * width + col;
 }
 
+// Origin slot p of a wave -> (pixel slot q, sample s of the wave).  PTC_SAMPLE_GROUP consecutive slots hold consecutive samples of
+// one pixel, so a warp covers 32 / G neighbouring pixels x G samples: the rays of a warp start from (nearly) the same point of the
+// scene at every bounce and the per-triangle gathers of the shading kernels hit the same sectors.  G = 1 is sample-major order
+// (a warp = one 8x4 tile of one sample).  Waves whose sample count G does not divide fall back to G = 1.
+#ifndef PTC_SAMPLE_GROUP
+#define PTC_SAMPLE_GROUP 1
+#endif
+__device__ __forceinline__ uint32_t sampleGroup(const WaveParams &wp) { return (PTC_SAMPLE_GROUP > 1 && wp.sppWave % PTC_SAMPLE_GROUP == 0) ? PTC_SAMPLE_GROUP : 1u; }
+__device__ __forceinline__ void slotToPixelSample(uint32_t p, const WaveParams &wp, uint32_t &q, uint32_t &s)
+{
+    const uint32_t G = sampleGroup(wp);
+    if (G == 1u) { q = p % wp.nPixels; s = p / wp.nPixels; return; }
+    const uint32_t block = p / G; // block = sBlock * nPixels + q
+    q = block % wp.nPixels; s = (block / wp.nPixels) * G + p % G;
+}
+__device__ __forceinline__ size_t pixelSampleToSlot(uint32_t q, uint32_t s, const WaveParams &wp)
+{
+    const uint32_t G = sampleGroup(wp);
+    if (G == 1u) { return (size_t)s * wp.nPixels + q; }
+    return ((size_t)(s / G) * wp.nPixels + q) * G + s % G;
+}
+
 __device__ __forceinline__ uint32_t warpAppend(uint32_t *counter, bool pred)
 {
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, pred); // called by all 32 lanes of the (warp-uniform) work loop
@@ -123,7 +163,9 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
 {
     const uint32_t nPaths = wp.nPixels * wp.sppWave;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += gridDim.x * blockDim.x) {
-        const uint32_t pixel = slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), s = p / wp.nPixels;
+        uint32_t q, s;
+        slotToPixelSample(p, wp, q, s);
+        const uint32_t pixel = slotToPixel(q, (uint32_t)scene.width, (uint32_t)scene.height);
         Rng rng;
         rng.initPhilox(wp.seed, pixel, wp.firstSample + s);
         rng.beginVertex(0);
@@ -132,10 +174,8 @@ __global__ void __launch_bounds__(256) generateKernel(DScene scene, PathBuffers 
         const int row = (int)(pixel / (uint32_t)scene.width), col = (int)(pixel % (uint32_t)scene.width);
         V3 o, d;
         cameraRay(scene, row + jitterY, col + jitterX, o, d);
-        pb.rayO[p] = make_float4(o.x, o.y, o.z, 0.f);
-        pb.rayD[p] = make_float4(d.x, d.y, d.z, 0.f);
-        pb.result[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        streamStore(pb.origin + p, p);
+        storeRec(pb.ray, p, make_float4(o.x, o.y, o.z, __uint_as_float(p)), make_float4(d.x, d.y, d.z, 0.f));
+        streamStore(pb.result + p, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0].extendCount = nPaths; }
 }
@@ -262,7 +302,8 @@ __device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState
 }
 
 // FILTER (shadow rays of a scene with container surfaces): Scene::testOcclusion's filter, src/scene.cpp:42-84, :369-370
-template <bool ANY, bool COUNT, bool FILTER = false>
+// INSTANCES: the scene holds flattened instance placements, whose triangles are tested in the instance's space (traverse.cuh: rayToPlacement)
+template <bool ANY, bool COUNT, bool FILTER = false, bool INSTANCES = false>
 __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor,
                                                       unsigned long long *work)
 {
@@ -288,13 +329,12 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
                 const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
                 if (item < n) {
                     p = queue ? streamLoad(queue + item) : item; // extend: the paths of a bounce occupy slots 0 .. n - 1
-                    const float4 o = pb.rayO[p];
                     if (ANY) { // Scene::testOcclusion, src/scene.cpp:355-381: any hit in (1e-3, maxT - 1e-3]
-                        const float4 d = pb.shadowD[p];
+                        const float4 o = streamLoad(pb.ray + 2 * (size_t)p), d = streamLoad(pb.nee + 2 * (size_t)p + 1);
                         traversalInit(st, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, d.w - 1e-3f);
                     } else {   // Scene::testIntersect, src/scene.cpp:91-120
-                        const float4 d = pb.rayD[p];
-                        traversalInit(st, o.x, o.y, o.z, d.x, d.y, d.z, PTC_TNEAR, PTC_TFAR);
+                        const Rec32 r = loadRec(pb.ray, p);
+                        traversalInit(st, r.a.x, r.a.y, r.a.z, r.b.x, r.b.y, r.b.z, PTC_TNEAR, PTC_TFAR);
                     }
                     if (!hasNodes) { st.ngroup.y = 0u; }
                     busy = true;
@@ -308,7 +348,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             // a ray whose triangle group is not finished yet (more triangles than PTC_TRI_ROUNDS) sits out this node phase
             if (busy && hasNodes && st.tgroup.y == 0u) { traversalNode<COUNT>(scene.bvh, st, &tc, fast); }
             bool done = false; // this ray needs no further BVH work
-            if (PTC_COOP_TRI && !COUNT && !FILTER) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
+            if (PTC_COOP_TRI && !COUNT && !FILTER && !INSTANCES) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
             else {
                 for (int round = 0; round < PTC_TRI_ROUNDS; round++) { // triangle rounds, warp-uniform control flow
                     bool pending = busy && !done && st.tgroup.y != 0u;
@@ -318,13 +358,13 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
                         if (pending && traversalPostpone(st, fast)) { pending = false; }
                         if (!__any_sync(0xFFFFFFFFu, pending)) { break; }
                     }
-                    if (pending && traversalTriangle<COUNT, FILTER>(scene.bvh, st, &tc) && ANY) { done = true; }
+                    if (pending && traversalTriangle<COUNT, FILTER, INSTANCES>(scene.bvh, st, &tc) && ANY) { done = true; }
                 }
             }
             if (busy && (done || (st.tgroup.y == 0u && traversalPop(st, fast)))) {
                 const bool found = traversalSpheres<ANY, FILTER>(scene.bvh, st);
-                if (ANY) { if (found) { streamStore(pb.nee.component(p, 3), 1.f); } }
-                else { pb.hit[p] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim)); }
+                if (ANY) { pb.occluded[p] = found ? 1 : 0; }
+                else { streamStore(pb.hit + p, make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.prim))); }
                 busy = false;
             }
             active = __ballot_sync(0xFFFFFFFFu, busy);
@@ -363,22 +403,40 @@ __global__ void __launch_bounds__(128) containerKernel(const __grid_constant__ D
     const uint32_t n = bc->extendCount;
     if (!checkCounts(wp.startBounce, wp.lastBounce, 0)) { return; }
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) { // bounce 0: slot = origin
-        const float4 h4 = pb.hit[p];
+        const float4 h4 = streamLoad(pb.hit + p);
         const uint32_t prim = __float_as_uint(h4.w);
         if (prim == PTC_MISS) { continue; }
         const uint32_t material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w);
         if (__ldg(&scene.materials[material].type) != PTC_PASSTHROUGH) { continue; }
-        const float4 o4 = pb.rayO[p], d4 = pb.rayD[p];
+        const Rec32 r = loadRec(pb.ray, p);
         float add[3];
-        cameraContainerTerm(scene, o4.x, o4.y, o4.z, d4.x, d4.y, d4.z, add);
-        const float4 c = streamLoad(pb.out + p);
-        streamStore(pb.out + p, make_float4(c.x + add[0], c.y + add[1], c.z + add[2], 0.f));
+        cameraContainerTerm(scene, r.a.x, r.a.y, r.a.z, r.b.x, r.b.y, r.b.z, add);
+        // a Passthrough surface is no emitter, so logic(0) stored no base colour: this term becomes the base (FLAG_BASE)
+        streamStore(pb.out + p, make_float4(add[0], add[1], add[2], 0.f));
+        const float4 res4 = streamLoad(pb.result + p);
+        streamStore(pb.result + p, make_float4(res4.x, res4.y, res4.z, __uint_as_float(__float_as_uint(res4.w) | FLAG_BASE)));
     }
 }
 
 #ifndef PTC_LAZY_DIRECTION
 #define PTC_LAZY_DIRECTION 1
 #endif
+// modulation up to the vertex a ray arrives at, from the (modulation up to the previous vertex, pdf | throughput, cosine) record of
+// the ray: PathTracer::L, src/path_tracer.cpp:51-53.  One function for the logic stage (tests it) and the material stage (carries it on)
+__device__ __forceinline__ V3 advanceModulation(const float4 mp, const float4 tc)
+{
+    const float invPDF = 1.f / mp.w;
+    return mk(mp.x, mp.y, mp.z) * ((mk(tc.x, tc.y, tc.z) * tc.w) * invPDF);
+}
+
+// color += L(...), src/sample_integrator.cpp:53: the path ends, its radiance goes to the entry of its origin slot
+__device__ __forceinline__ void finishPath(const PathBuffers &pb, uint32_t origin, uint32_t flags, const V3 result)
+{
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flags & FLAG_BASE) { c = streamLoad(pb.out + origin); }
+    streamStore(pb.out + origin, make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f));
+}
+
 __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->extendCount;
@@ -388,9 +446,8 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
         const uint32_t p = base + (threadIdx.x & 31u);
         int cls = -1;
         if (p < n) {
-            // the ray direction is only needed for environment misses and emitter hits: a surviving ordinary hit never reads it
-            const float4 h4 = pb.hit[p];
-            float4 res4 = pb.result[p];
+            const float4 h4 = streamLoad(pb.hit + p);
+            const float4 res4 = streamLoad(pb.result + p);
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
             const uint32_t prim = __float_as_uint(h4.w);
@@ -402,59 +459,49 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                 emitter = __ldg(&scene.materials[material].emitter) != 0;
             }
             V3 result = mk(res4.x, res4.y, res4.z);
-            V3 color = mk(0.f, 0.f, 0.f); // k = 0: what samplePixel adds itself
             bool alive = true;
+            // the ray (origin, direction) is only needed for environment misses and emitter hits: a surviving ordinary hit never reads it
+            const bool needRay = PTC_LAZY_DIRECTION ? (!isHit || emitter) : true;
+            Rec32 ray;
+            if (needRay) { ray = loadRec(pb.ray, p); }
             if (k == 0) {
-                // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59
-                V3 D = mk(0.f, 0.f, 0.f);
-                if (!isHit || emitter) { const float4 d4 = pb.rayD[p]; D = mk(d4.x, d4.y, d4.z); }
-                if (!isHit) { color = envRadiance(scene, D); alive = false; }
-                else if (emitter && checkCounts(wp.startBounce, wp.lastBounce, 0)) {
-                    const float4 o4 = pb.rayO[p];
+                // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59; bounce 0: slot = origin slot
+                if (!isHit) {
+                    const V3 color = envRadiance(scene, mk(ray.b.x, ray.b.y, ray.b.z));
+                    streamStore(pb.out + p, make_float4(color.x + result.x, color.y + result.y, color.z + result.z, 0.f));
+                    alive = false;
+                } else if (emitter && checkCounts(wp.startBounce, wp.lastBounce, 0)) {
                     RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = prim;
                     Isect bi;
-                    makeIsect(scene, mk(o4.x, o4.y, o4.z), D, hit, bi);
+                    makeIsect(scene, mk(ray.a.x, ray.a.y, ray.a.z), mk(ray.b.x, ray.b.y, ray.b.z), hit, bi);
                     const DMaterial &m = scene.materials[material];
-                    if (!(dot(bi.n, bi.wo) < 0.f)) { color = mk(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2])); }
+                    if (!(dot(bi.n, bi.wo) < 0.f)) { // what samplePixel adds itself waits in `out` for the end of the path
+                        streamStore(pb.out + p, make_float4(__ldg(&m.emit[0]), __ldg(&m.emit[1]), __ldg(&m.emit[2]), 0.f));
+                        streamStore(pb.result + p, make_float4(res4.x, res4.y, res4.z, __uint_as_float(flags | FLAG_BASE)));
+                    }
                 }
-                if (alive) { streamStore(pb.out + p, make_float4(color.x, color.y, color.z, 0.f)); } // bounce 0: slot = origin
             } else {
-                const float4 mp = pb.modPdf[p], tc = pb.thrCos[p];
-                V3 modulation = mk(mp.x, mp.y, mp.z);
-                const V3 thr = mk(tc.x, tc.y, tc.z);
+                const Rec32 mt = loadRec(pb.modThr, p);
                 if (flags & FLAG_DIRECT) { // direct() of vertex k, src/path_tracer.cpp:79-111
                     V3 Ld = mk(0.f, 0.f, 0.f);
-                    if (flags & FLAG_NEE) { const float4 ne = pb.nee[p]; if (ne.w == 0.f) { Ld = Ld + mk(ne.x, ne.y, ne.z); } }
+                    if ((flags & FLAG_NEE) && !pb.occluded[p]) { const float4 ne = streamLoad(pb.nee + 2 * (size_t)p); Ld = Ld + mk(ne.x, ne.y, ne.z); }
                     if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
-                        const float4 d4 = pb.rayD[p];
-                        const V3 D = mk(d4.x, d4.y, d4.z);
-                        const float4 o4 = pb.rayO[p];
-                        const V3 O = mk(o4.x, o4.y, o4.z);
+                        const V3 O = mk(ray.a.x, ray.a.y, ray.a.z), D = mk(ray.b.x, ray.b.y, ray.b.z);
                         Isect bi;
                         if (isHit) { RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = prim; makeIsect(scene, O, D, hit, bi); }
-                        Ld = Ld + directBsdf(scene, O, tc.w, D, mp.w, thr, (flags & FLAG_DELTA) != 0, isHit, &bi);
+                        Ld = Ld + directBsdf(scene, O, mt.b.w, D, mt.a.w, mk(mt.b.x, mt.b.y, mt.b.z), (flags & FLAG_DELTA) != 0, isHit, &bi);
                     }
-                    result = result + Ld * modulation;
+                    result = result + Ld * mk(mt.a.x, mt.a.y, mt.a.z);
                 }
                 // loop header and body of PathTracer::L, src/path_tracer.cpp:41-58
-                if (checkDone(wp.lastBounce, k + 1) || !isHit) { alive = false; }
-                else {
-                    const float invPDF = 1.f / mp.w;
-                    modulation = modulation * ((thr * tc.w) * invPDF);
-                    if (isBlack(modulation)) { alive = false; }
-                    else { pb.modPdf[p] = make_float4(modulation.x, modulation.y, modulation.z, mp.w); }
+                if (checkDone(wp.lastBounce, k + 1) || !isHit || isBlack(advanceModulation(mt.a, mt.b))) { alive = false; }
+                if (alive && (flags & FLAG_DIRECT)) { streamStore(pb.result + p, make_float4(result.x, result.y, result.z, res4.w)); }
+                if (!alive) {
+                    const uint32_t origin = needRay ? __float_as_uint(ray.a.w) : __float_as_uint(streamLoad(&pb.ray[2 * (size_t)p].w));
+                    finishPath(pb, origin, flags, result);
                 }
-                if (alive && (flags & FLAG_DIRECT)) { pb.result[p] = make_float4(result.x, result.y, result.z, res4.w); }
             }
             if (alive) { cls = __ldg(&scene.materials[material].type); }
-            else { // color += L(...), src/sample_integrator.cpp:53: the path ends, its radiance goes to the entry of its origin slot
-                const uint32_t origin = streamLoad(pb.origin + p);
-                if (k == 0) { streamStore(pb.out + origin, make_float4(color.x + result.x, color.y + result.y, color.z + result.z, 0.f)); }
-                else {
-                    const float4 c = streamLoad(pb.out + origin);
-                    streamStore(pb.out + origin, make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f));
-                }
-            }
         }
 #pragma unroll
         for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
@@ -477,19 +524,21 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
         bool pushExtend = false, pushShadow = false;
         // what the path carries to its slot of the next bounce
         float4 nO = make_float4(0.f, 0.f, 0.f, 0.f), nD = nO, nMod = nO, nThr = nO, nRes = nO, nNee = nO, nSh = nO;
-        uint32_t origin = 0;
         if (item < n) {
             const uint32_t p = streamLoad(queue + item);
-            const float4 o4 = pb.rayO[p], d4 = pb.rayD[p], h4 = pb.hit[p], res4 = pb.result[p];
-            origin = streamLoad(pb.origin + p);
+            const Rec32 ray = loadRec(pb.ray, p);
+            const float4 h4 = streamLoad(pb.hit + p), res4 = streamLoad(pb.result + p);
+            const uint32_t origin = __float_as_uint(ray.a.w);
             const uint32_t flags = __float_as_uint(res4.w);
             const int k = (int)(flags & FLAG_BOUNCE_MASK);
             RayHit hit; hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
             Isect bi;
-            makeIsect(scene, mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z), hit, bi);
+            makeIsect(scene, mk(ray.a.x, ray.a.y, ray.a.z), mk(ray.b.x, ray.b.y, ray.b.z), hit, bi);
             const DMaterial &m = scene.materials[bi.material];
             Rng rng;
-            rng.initPhilox(wp.seed, slotToPixel(origin % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + origin / wp.nPixels);
+            uint32_t oq, os;
+            slotToPixelSample(origin, wp, oq, os);
+            rng.initPhilox(wp.seed, slotToPixel(oq, (uint32_t)scene.width, (uint32_t)scene.height), wp.firstSample + os);
             rng.beginVertex((uint32_t)(k + 1));
             BsdfSample bs;
             bsdfSample<TYPE>(m, bi, rng, bs);
@@ -506,25 +555,26 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
             }
             const bool wantNext = !checkDone(wp.lastBounce, k + 2);
             if (wantDirect || wantNext) {
-                nO = make_float4(bi.point.x, bi.point.y, bi.point.z, 0.f);
+                nO = make_float4(bi.point.x, bi.point.y, bi.point.z, ray.a.w);
                 nD = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.f);
                 if (k == 0) { nMod = make_float4(1.f, 1.f, 1.f, bs.pdf); } // the modulation starts at 1
-                else { const float4 mp = pb.modPdf[p]; nMod = make_float4(mp.x, mp.y, mp.z, bs.pdf); }
+                else { const Rec32 mt = loadRec(pb.modThr, p); const V3 mod = advanceModulation(mt.a, mt.b); nMod = make_float4(mod.x, mod.y, mod.z, bs.pdf); }
                 nThr = make_float4(bs.thr.x, bs.thr.y, bs.thr.z, fabsf(dot(bi.ns, bs.wi)));
-                const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u);
+                const uint32_t nf = (uint32_t)(k + 1) | (bs.delta ? FLAG_DELTA : 0u) | (wantDirect ? FLAG_DIRECT : 0u) | (pushShadow ? FLAG_NEE : 0u) | (flags & FLAG_BASE);
                 nRes = make_float4(res4.x, res4.y, res4.z, __uint_as_float(nf));
                 pushExtend = true;
             } else { // the path ends here: color += L(...)
                 pushShadow = false;
-                const float4 c = streamLoad(pb.out + origin);
-                streamStore(pb.out + origin, make_float4(c.x + res4.x, c.y + res4.y, c.z + res4.z, 0.f));
+                finishPath(pb, origin, flags, mk(res4.x, res4.y, res4.z));
             }
         }
         // compaction: the path moves to slot e of the next bounce; consecutive lanes get consecutive slots (coalesced stores)
         const uint32_t e = warpAppend(&next->extendCount, pushExtend);
         if (pushExtend) {
-            pb.nRayO[e] = nO; pb.nRayD[e] = nD; pb.nModPdf[e] = nMod; pb.nResult[e] = nRes; pb.thrCos[e] = nThr; streamStore(pb.nOrigin + e, origin);
-            if (pushShadow) { pb.nee[e] = nNee; pb.shadowD[e] = nSh; }
+            storeRec(pb.nRay, e, nO, nD);
+            storeRec(pb.nModThr, e, nMod, nThr);
+            streamStore(pb.nResult + e, nRes);
+            if (pushShadow) { storeRec(pb.nee, e, nNee, nSh); }
         }
         const uint32_t sh = warpAppend(&next->shadowCount, pushShadow);
         if (pushShadow) { streamStore(pb.shadowQueue + sh, e); }
@@ -538,7 +588,7 @@ __global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WavePara
         const size_t pixel = slotToPixel(q, width, height);
         float r = accum[3 * pixel], g = accum[3 * pixel + 1], b = accum[3 * pixel + 2];
         for (uint32_t s = 0; s < wp.sppWave; s++) { // radianceLookup += color, one sample after the other (src/sample_integrator.cpp:61-63)
-            const float4 c = streamLoad(pb.out + (size_t)s * wp.nPixels + q);
+            const float4 c = streamLoad(pb.out + pixelSampleToSlot(q, s, wp));
             r += c.x; g += c.y; b += c.z;
         }
         accum[3 * pixel] = r; accum[3 * pixel + 1] = g; accum[3 * pixel + 2] = b;
@@ -568,7 +618,9 @@ __global__ void __launch_bounds__(128, PTC_VOLUME_MIN_BLOCKS) volumePathKernel(c
         if (base >= nPaths) { break; }
         const uint32_t p = base + lane;
         if (p < nPaths) {
-            const uint32_t pixel = slotToPixel(p % wp.nPixels, (uint32_t)scene.width, (uint32_t)scene.height), s = p / wp.nPixels;
+            uint32_t q, s;
+            slotToPixelSample(p, wp, q, s);
+            const uint32_t pixel = slotToPixel(q, (uint32_t)scene.width, (uint32_t)scene.height);
             Rng rng;
             rng.initPhilox(wp.seed, pixel, wp.firstSample + s);
             rng.beginVertex(0);
@@ -614,6 +666,23 @@ __global__ void __launch_bounds__(256) gatherResolveKernel(FramebufferSet set, f
         float sum = set.fb[0][i];
         for (int g = 1; g < set.count; g++) { sum += set.fb[g][i]; }
         out[i] = sum / (int)divisor;
+    }
+}
+
+// SURVEY 8(f) N4, after the BVH build over the flattened (world-space) placements: the leaf triangles of a placement get the
+// instance's LOCAL-space corners back and the tag of their placement, so that the traversal tests them where Embree does
+__global__ void localizeLeavesKernel(LeafTriangle *triangles, uint32_t n, const float4 *positions, const uint4 *prims, const uint32_t *tags)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        LeafTriangle t = triangles[i];
+        const uint32_t tag = tags[t.prim];
+        if (!tag) { continue; }
+        const uint4 ix = prims[t.prim];
+        const float4 v0 = positions[ix.x], v1 = positions[ix.y], v2 = positions[ix.z];
+        t.v0[0] = v0.x; t.v0[1] = v0.y; t.v0[2] = v0.z;
+        t.e1[0] = v0.x - v1.x; t.e1[1] = v0.y - v1.y; t.e1[2] = v0.z - v1.z; t.pad0 = tag;
+        t.e2[0] = v2.x - v0.x; t.e2[1] = v2.y - v0.y; t.e2[2] = v2.z - v0.z;
+        triangles[i] = t;
     }
 }
 
@@ -893,6 +962,7 @@ struct HostGeometry {
     bool isInstance = false;
     uint32_t instanceScene = 0;
     float l2w[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}; // rows of the 3x4 affine map
+    float w2l[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}; // its inverse as Embree keeps it (Instance::setTransform: world2local = rcp(local2world))
 };
 struct HostScene { uint32_t nGeoms = 0; std::vector<uint32_t> members; }; // members: indices into ptc_ctx::geometries, attach order
 
@@ -1154,6 +1224,28 @@ int ptc_end_instance(ptc_ctx *ctx)
     return PTC_OK;
 }
 
+// Instance::setTransform's world2local0 = rcp(local2world) (ext/embree/kernels/common/scene_instance.cpp:77-85; part of Embree's
+// lowest-ISA build: no fused multiply-add).  common/math/affinespace.h:91 and linearspace3.h:57-63: l^-1 = adjoint(l) / det(l) with a
+// true division per element, the adjoint's rows = cross products of l's columns, det summed as (x + y) + z, and
+// p' = -(p.x * c0 + (p.y * c1 + p.z * c2)) over the columns c of l^-1.  The order matters: the ray origin in the instance's space is
+// rounded at the magnitude of the transformed point, so one ulp in this matrix moves t of a short bounce ray by 1e-5 and more.
+static void inverseAffine(const float l2w[12], float w2l[12])
+{
+    const float vx[3] = {l2w[0], l2w[4], l2w[8]}, vy[3] = {l2w[1], l2w[5], l2w[9]}, vz[3] = {l2w[2], l2w[6], l2w[10]};
+    auto cross = [](const float *a, const float *b, volatile float *out) { out[0] = a[1] * b[2] - a[2] * b[1]; out[1] = a[2] * b[0] - a[0] * b[2]; out[2] = a[0] * b[1] - a[1] * b[0]; };
+    volatile float rows[3][3]; // volatile: every product and sum is rounded to float on its own, whatever the host compiler's contraction setting
+    cross(vy, vz, rows[0]); cross(vz, vx, rows[1]); cross(vx, vy, rows[2]);
+    volatile float p0 = vx[0] * rows[0][0], p1 = vx[1] * rows[0][1], p2 = vx[2] * rows[0][2];
+    volatile float s01 = p0 + p1;
+    const float det = s01 + p2;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) { w2l[4 * i + j] = rows[i][j] / det; }
+        volatile float a = l2w[3] * w2l[4 * i], b = l2w[7] * w2l[4 * i + 1], c = l2w[11] * w2l[4 * i + 2];
+        volatile float bc = b + c;
+        w2l[4 * i + 3] = -(a + bc);
+    }
+}
+
 int ptc_add_instance(ptc_ctx *ctx, uint32_t scene, const float m[16], uint32_t *geomId)
 {
     if (!ctx || !m) { return PTC_ERR_INVALID; }
@@ -1163,6 +1255,7 @@ int ptc_add_instance(ptc_ctx *ctx, uint32_t scene, const float m[16], uint32_t *
     HostGeometry g;
     g.isInstance = true; g.instanceScene = scene;
     for (int row = 0; row < 3; row++) { for (int col = 0; col < 4; col++) { g.l2w[4 * row + col] = m[4 * col + row]; } } // RTC_FORMAT_FLOAT4X4_COLUMN_MAJOR
+    inverseAffine(g.l2w, g.w2l);
     const uint32_t id = attachGeometry(ctx, g);
     if (geomId) { *geomId = id; }
     return PTC_OK;
@@ -1287,17 +1380,27 @@ int ptc_commit(ptc_ctx *ctx)
     if (instanced && !ctx->media.empty()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "instancing together with participating media is not supported"); }
 
     // SURVEY 8(f) N4.  180 GB of HBM make flattening the B200-native form of Embree's two-level instancing: every placement of an
-    // instance scene becomes world-space triangles of the ONE wide BVH (single-level traversal, no per-ray transforms or second
-    // stack), while everything Scene::testIntersect reads after the hit -- Ng, vertex normals, uvs, the emitter triangle's corners --
-    // stays in the instance's LOCAL space, exactly as the reference leaves it (src/scene.cpp:122-219 never transforms back).
+    // instance scene becomes world-space boxes of the ONE wide BVH (single-level traversal, no second stack).  The leaf triangles
+    // keep the instance's LOCAL-space corners and the traversal moves the ray into the placement's space for the triangle test only
+    // (traverse.cuh: rayToPlacement -- Embree's own arithmetic, so t, u, v round as they do in the reference), and everything
+    // Scene::testIntersect reads after the hit -- Ng, vertex normals, uvs, the emitter triangle's corners -- stays in LOCAL space as
+    // well, exactly as the reference leaves it (src/scene.cpp:122-219 never transforms back).
     // flat prim = one triangle of the BVH: (local vertex ids, material) | (geomID, primID inside its scene) | (instID[0], instID[1])
-    std::vector<uint32_t> flatPrims4, flatIds2, flatInst2, worldPrims4;
+    std::vector<uint32_t> flatPrims4, flatIds2, flatInst2, worldPrims4, flatTag;
     std::vector<float> worldPos4;
+    std::vector<float> placements; // per flattened placement: world-to-local rows of the outer, then of the inner level
     if (instanced) {
         struct Expand {
-            ptc_ctx *ctx; std::vector<uint32_t> &flatPrims4, &flatIds2, &flatInst2, &worldPrims4; std::vector<float> &worldPos4; std::string error;
-            void run(uint32_t scene, const float *T, uint32_t inst0, uint32_t inst1, int level)
+            ptc_ctx *ctx; std::vector<uint32_t> &flatPrims4, &flatIds2, &flatInst2, &worldPrims4, &flatTag; std::vector<float> &worldPos4, &placements; std::string error;
+            void run(uint32_t scene, const float *T, uint32_t inst0, uint32_t inst1, int level, const float *outerW2L = nullptr, const float *innerW2L = nullptr)
             {
+                uint32_t tag = 0; // what the leaf triangles of this placement carry (0: root-scene geometry, tested in world space)
+                if (level > 0) {
+                    static const float identity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+                    placements.insert(placements.end(), outerW2L, outerW2L + 12);
+                    placements.insert(placements.end(), innerW2L ? innerW2L : identity, (innerW2L ? innerW2L : identity) + 12);
+                    tag = (uint32_t)(placements.size() / 24) | (level == 2 ? 0x80000000u : 0u);
+                }
                 for (uint32_t index : ctx->scenes[scene].members) {
                     const HostGeometry &g = ctx->geometries[index];
                     if (g.isSphere) { continue; }
@@ -1309,7 +1412,8 @@ int ptc_commit(ptc_ctx *ctx)
                                 C[4 * r + c] = T[4 * r] * g.l2w[c] + T[4 * r + 1] * g.l2w[4 + c] + T[4 * r + 2] * g.l2w[8 + c] + (c == 3 ? T[4 * r + 3] : 0.f);
                             }
                         }
-                        run(g.instanceScene, C, level == 0 ? g.localId : inst0, level == 0 ? PTC_INVALID_ID : g.localId, level + 1);
+                        run(g.instanceScene, C, level == 0 ? g.localId : inst0, level == 0 ? PTC_INVALID_ID : g.localId, level + 1,
+                            level == 0 ? g.w2l : outerW2L, level == 0 ? nullptr : g.w2l);
                         if (!error.empty()) { return; }
                         continue;
                     }
@@ -1325,10 +1429,11 @@ int ptc_commit(ptc_ctx *ctx)
                         worldPrims4.insert(worldPrims4.end(), {ix[0] - g.firstVertex + base, ix[1] - g.firstVertex + base, ix[2] - g.firstVertex + base, ix[3]});
                         flatIds2.insert(flatIds2.end(), {g.localId, t});
                         flatInst2.insert(flatInst2.end(), {inst0, inst1});
+                        flatTag.push_back(tag);
                     }
                 }
             }
-        } expand{ctx, flatPrims4, flatIds2, flatInst2, worldPrims4, worldPos4, std::string()};
+        } expand{ctx, flatPrims4, flatIds2, flatInst2, worldPrims4, flatTag, worldPos4, placements, std::string()};
         const float identity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         expand.run(0, identity, PTC_INVALID_ID, PTC_INVALID_ID, 0);
         if (!expand.error.empty()) { CTX_FAIL(ctx, PTC_ERR_INVALID, "%s", expand.error.c_str()); }
@@ -1375,6 +1480,18 @@ int ptc_commit(ptc_ctx *ctx)
                 s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
             }
         } catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
+        s.bvh.placements = nullptr;
+        ctx->bvh.placements = placements;
+        if (!placements.empty() && !ctx->bvh.triangles.empty()) {
+            const uint32_t *tags = nullptr;
+            if ((rc = upload(ctx, flatTag.data(), flatTag.size(), &tags, A))) { return rc; }
+            if ((rc = upload(ctx, (const float4 *)placements.data(), placements.size() / 4, &s.bvh.placements, A))) { return rc; }
+            const uint32_t nTriangles = (uint32_t)ctx->bvh.triangles.size();
+            LeafTriangle *leaves = (LeafTriangle *)s.bvh.triangles;
+            localizeLeavesKernel<<<(nTriangles + 255) / 256, 256, 0, ctx->stream>>>(leaves, nTriangles, s.positions, s.prims, tags);
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bvh.triangles.data(), leaves, (size_t)nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         ctx->bvhBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - buildStart).count();
     }
 
@@ -1544,20 +1661,12 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
     PathBuffers &pb = ctx->paths;
     CUDA_TRY(ctx, cudaMalloc((void **)&pb.out, (size_t)capacity * sizeof(float4)));
     ctx->pathAllocations.push_back(pb.out);
-    // one buffer of 32-byte records per pair of fields; (rayO, rayD) and (modPdf, result) exist twice (current / next)
-    PairedField *pairs[6][2] = {{&pb.rayO, &pb.rayD}, {&pb.nRayO, &pb.nRayD}, {&pb.modPdf, &pb.result}, {&pb.nModPdf, &pb.nResult},
-                                {&pb.hit, &pb.thrCos}, {&pb.nee, &pb.shadowD}};
-    for (auto &pair : pairs) {
-        float4 *buffer = nullptr;
-        CUDA_TRY(ctx, cudaMalloc((void **)&buffer, (size_t)capacity * 2 * sizeof(float4)));
-        ctx->pathAllocations.push_back(buffer);
-        pair[0]->base = buffer;
-        pair[1]->base = buffer + 1;
-    }
-    uint32_t **u32[] = {&pb.origin, &pb.nOrigin, &pb.shadowQueue};
-    for (uint32_t **slot : u32) {
-        CUDA_TRY(ctx, cudaMalloc((void **)slot, (size_t)capacity * sizeof(uint32_t)));
-        ctx->pathAllocations.push_back(*slot);
+    struct { void **slot; size_t bytesPerPath; } arrays[] = {
+        {(void **)&pb.ray, 32}, {(void **)&pb.nRay, 32}, {(void **)&pb.modThr, 32}, {(void **)&pb.nModThr, 32}, {(void **)&pb.nee, 32},
+        {(void **)&pb.hit, 16}, {(void **)&pb.result, 16}, {(void **)&pb.nResult, 16}, {(void **)&pb.occluded, 1}, {(void **)&pb.shadowQueue, 4}};
+    for (auto &a : arrays) {
+        CUDA_TRY(ctx, cudaMalloc(a.slot, (size_t)capacity * a.bytesPerPath));
+        ctx->pathAllocations.push_back(*a.slot);
     }
     for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
         pb.classQueue[t] = nullptr;
@@ -1590,12 +1699,14 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
             // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
-            if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            if (s.bvh.placements) { traverseKernel<false, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            else if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
             else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
         }
         if (k > 0) {
             StageTimer t(ctx, stream, STAGE_SHADOW);
-            if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
             else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
             else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
         }
@@ -1614,8 +1725,7 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         }
         ctx->launches += k > 0 ? 3 : 2;
         // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
-        std::swap(pb.rayO, pb.nRayO); std::swap(pb.rayD, pb.nRayD); std::swap(pb.modPdf, pb.nModPdf); std::swap(pb.result, pb.nResult);
-        std::swap(pb.origin, pb.nOrigin);
+        std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
     }
     {
         StageTimer t(ctx, stream, STAGE_OTHER);

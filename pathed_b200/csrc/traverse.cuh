@@ -138,6 +138,10 @@ struct BvhView {
     // occlusion filter (src/scene.cpp:42-84): per triangle / per sphere the medium of a Passthrough surface that encloses one
     // (such a hit is rejected and leaves a volume event), -1 for every other surface; null when the scene has no such surface
     const int32_t *primEvent, *sphereEvent;
+    // world-to-local maps of the flattened instance placements, 6 float4 each (rows of the outer placement's 3x4
+    // map, then of the inner one's for a two-level placement); null without instances.  A leaf triangle of a placement keeps its
+    // LOCAL-space corners and carries (placement + 1) | two-level flag << 31 in the spare word of its second float4
+    const float4 *placements;
 };
 
 #define PTC_SPHERE_FLAG 0x80000000u
@@ -207,6 +211,22 @@ PTC_HD bool sphereTest(const float4 s, float ox, float oy, float oz, float dx, f
     t = validIn ? tIn : tOut;
     ngx = dx * td - px; ngy = dy * td - py; ngz = dz * td - pz;
     return true;
+}
+
+// Embree's InstanceIntersector1 (ext/embree/kernels/geometry/instance_intersector.cpp:52-109): the ray enters an instance by
+// xfmPoint(world2local, org) / xfmVector(world2local, dir) (AVX2 madd chains, common/math/affinespace.h), tnear / tfar unchanged, and
+// the triangle is tested there -- so t, u, v carry the rounding of the instance's space, not of world space.  The placements are
+// flattened into the one BVH (world-space boxes); the triangle test repeats Embree's transforms, level by level.
+PTC_HD void rayToPlacement(const float4 *placements, uint32_t tag, float &ox, float &oy, float &oz, float &dx, float &dy, float &dz)
+{
+    const float4 *m = placements + (size_t)((tag & 0x7FFFFFFFu) - 1u) * 6;
+    for (uint32_t level = 0; level < 1u + (tag >> 31); level++, m += 3) {
+        const float4 r0 = loadNodeWord(m), r1 = loadNodeWord(m + 1), r2 = loadNodeWord(m + 2);
+        const float px = fmaf(ox, r0.x, fmaf(oy, r0.y, fmaf(oz, r0.z, r0.w))), py = fmaf(ox, r1.x, fmaf(oy, r1.y, fmaf(oz, r1.z, r1.w))),
+                    pz = fmaf(ox, r2.x, fmaf(oy, r2.y, fmaf(oz, r2.z, r2.w)));
+        const float vx = fmaf(dx, r0.x, fmaf(dy, r0.y, dz * r0.z)), vy = fmaf(dx, r1.x, fmaf(dy, r1.y, dz * r1.z)), vz = fmaf(dx, r2.x, fmaf(dy, r2.y, dz * r2.z));
+        ox = px; oy = py; oz = pz; dx = vx; dy = vy; dz = vz;
+    }
 }
 
 struct TraverseCounters { uint32_t inner, tris; };
@@ -362,7 +382,8 @@ PTC_HD void traversalNode(const BvhView &bvh, TraversalState &st, TraverseCounte
 
 // Tests one triangle of the pending group (precondition: st.tgroup.y != 0).  Returns true when a hit was accepted.
 // FILTER: Scene::testOcclusion's shouldIntersectPassthroughs = false -- container surfaces are not hits.
-template <bool COUNT, bool FILTER = false>
+// INSTANCES = false: the caller knows the scene has no instance placements (the wavefront kernels of such a scene).
+template <bool COUNT, bool FILTER = false, bool INSTANCES = true>
 PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCounters *counters)
 {
     const uint32_t bit = highestBit(st.tgroup.y);
@@ -371,7 +392,11 @@ PTC_HD bool traversalTriangle(const BvhView &bvh, TraversalState &st, TraverseCo
     const float4 a = loadNodeWord(tri), b = loadNodeWord(tri + 1), c = loadNodeWord(tri + 2);
     if (COUNT) { counters->tris++; }
     float T, U, V, absDen;
-    if (!triangleTestRaw(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
+    if (INSTANCES && f2u(b.w)) {
+        float ox = st.ox, oy = st.oy, oz = st.oz, dx = st.dx, dy = st.dy, dz = st.dz;
+        rayToPlacement(bvh.placements, f2u(b.w), ox, oy, oz, dx, dy, dz);
+        if (!triangleTestRaw(a, b, c, ox, oy, oz, dx, dy, dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
+    } else if (!triangleTestRaw(a, b, c, st.ox, st.oy, st.oz, st.dx, st.dy, st.dz, st.tnear, st.hit.t, T, U, V, absDen)) { return false; }
     const float t = divIeee(T, absDen);
     const uint32_t prim = f2u(a.w);
     if (FILTER && bvh.primEvent[prim] >= 0) { return false; }

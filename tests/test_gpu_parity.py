@@ -96,13 +96,6 @@ def test_intersection_matches_embree(name):
         agree = ref_hit == got_hit
         same_prim = agree & (~ref_hit | ((hits["geom_id"] == g[prefix + "geom"]) & (hits["prim_id"] == g[prefix + "prim"])))
         t_ok = rel_err(hits["t"], g[prefix + "t"]) <= REL
-        if cfg.get("instanced"):
-            # Embree moves the ray into the instance's space with a rounded inverse matrix, so its own t carries an absolute error
-            # proportional to the distance of the origin from the instance's origin, not to t: a bounce ray that leaves an instanced
-            # surface and lands 0.002 away cannot agree to 1e-5 of t (measured: <= 1.6e-5 absolute).  Depth is compared relative to
-            # max(t, |origin|) there; camera rays meet the plain 1e-5 (measured 1.8e-6).
-            scale = np.maximum(np.abs(g[prefix + "t"]).astype(np.float64), np.linalg.norm(g[prefix + "rays"][:, :3].astype(np.float64), axis=1))
-            t_ok = np.abs(hits["t"].astype(np.float64) - g[prefix + "t"]) <= 2 * REL * scale
         tie = agree & ref_hit & ~same_prim & t_ok  # another primitive at the same depth (shared edge / coincident face)
         print(name, prefix, "hit/miss", agree.mean(), "prim", same_prim.mean(), "ties", tie.mean())
         assert agree.mean() >= 0.9999
@@ -114,14 +107,12 @@ def test_intersection_matches_embree(name):
             assert np.array_equal(inst[exact], g[prefix + "inst"][exact])
             assert (g[prefix + "inst"][:, 0] != 0xFFFFFFFF).sum() > 500 and (g[prefix + "inst"][:, 1] != 0xFFFFFFFF).sum() > 50  # both levels are exercised
         ok = agree & ref_hit & same_prim
-        # flattened placements are intersected in world space, Embree's in the instance's space: barycentrics agree absolutely (1e-5), not
-        # relative to a small u
-        assert frac_within(hits["u"][ok], g[prefix + "bary"][ok, 0], floor=0.1 if cfg.get("instanced") else 1e-3, tol=1e-4)[0] >= 0.999
+        assert frac_within(hits["u"][ok], g[prefix + "bary"][ok, 0], floor=1e-3, tol=1e-4)[0] >= 0.999
         # sphere Ng = td*D - perp cancels, and Embree's rd2 is an rcp + Newton step, so allow a few ulp more there
-        assert frac_within(hits["ng"][ok], g[prefix + "ng"][ok], tol=1e-4)[0] >= (0.995 if cfg.get("instanced") else 0.999)
+        assert frac_within(hits["ng"][ok], g[prefix + "ng"][ok], tol=1e-4)[0] >= 0.999
         full = ctx.intersect_full(rays)
-        assert frac_within(full["point"][ok], g[prefix + "point"][ok], tol=5e-5 if cfg.get("instanced") else REL)[0] >= 0.9999
-        assert frac_within(full["shading_normal"][ok], g[prefix + "shading_normal"][ok], tol=2e-5)[0] >= (0.995 if cfg.get("instanced") else 0.999)
+        assert frac_within(full["point"][ok], g[prefix + "point"][ok], tol=REL)[0] >= 0.9999
+        assert frac_within(full["shading_normal"][ok], g[prefix + "shading_normal"][ok], tol=2e-5)[0] >= 0.999
     occ = ctx.occluded(to_rays(g["shadow_rays"]), g["shadow_max_t"])
     # this 2-8 k-ray fixture joins pairs of surface points, many of them in one plane with a box resting on it (knife-edge
     # hits along the box's base, where Embree's exact node test culls what the inclusive triangle test would accept): at most a few

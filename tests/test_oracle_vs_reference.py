@@ -88,13 +88,6 @@ def test_scene_queries_match_reference(name):
         agree = (ref_hit == got_hit)
         same_prim = agree & (~ref_hit | ((hits["geom_id"] == g[prefix + "geom"]) & (hits["prim_id"] == g[prefix + "prim"])))
         t_ok = rel_err(hits["t"], g[prefix + "t"]) <= REL
-        if cfg.get("instanced"):
-            # Embree moves the ray into the instance's space with a rounded inverse matrix, so its own t carries an absolute error
-            # proportional to the distance of the origin from the instance's origin, not to t: a bounce ray that leaves an instanced
-            # surface and lands 0.002 away cannot agree to 1e-5 of t (measured: <= 1.6e-5 absolute).  Depth is compared relative to
-            # max(t, |origin|) there; camera rays meet the plain 1e-5 (measured 1.8e-6).
-            scale = np.maximum(np.abs(g[prefix + "t"]).astype(np.float64), np.linalg.norm(g[prefix + "rays"][:, :3].astype(np.float64), axis=1))
-            t_ok = np.abs(hits["t"].astype(np.float64) - g[prefix + "t"]) <= 2 * REL * scale
         # ties: a different primitive at the same depth (shared edges, the Cornell data set's duplicated quads)
         tie = agree & ref_hit & ~same_prim & t_ok
         assert agree.mean() >= 0.9999, (prefix, agree.mean())
@@ -107,12 +100,12 @@ def test_scene_queries_match_reference(name):
             assert (g[prefix + "inst"][:, 0] != 0xFFFFFFFF).sum() > 500 and (g[prefix + "inst"][:, 1] != 0xFFFFFFFF).sum() > 50  # both levels are exercised
         full = o.intersect_full(rays)
         both = agree & ref_hit & same_prim
-        assert frac_within(full["point"][both], g[prefix + "point"][both], tol=5e-5 if cfg.get("instanced") else REL)[0] >= 0.9999
+        assert frac_within(full["point"][both], g[prefix + "point"][both], tol=REL)[0] >= 0.9999
         assert frac_within(full["normal"][both], g[prefix + "normal"][both])[0] >= 0.9999
-        assert frac_within(full["shading_normal"][both], g[prefix + "shading_normal"][both], tol=2e-5)[0] >= (0.995 if cfg.get("instanced") else 0.999)
+        assert frac_within(full["shading_normal"][both], g[prefix + "shading_normal"][both], tol=2e-5)[0] >= 0.999
         # spheres: the reference leaves Intersection::uv uninitialised (src/scene.cpp:131, :177-184), so skip them
         tri = both & ~(g[prefix + "bary"] == 0).all(1)
-        assert frac_within(full["uv"][tri], g[prefix + "tex_uv"][tri], floor=1e-3)[0] >= (0.995 if cfg.get("instanced") else 0.999)
+        assert frac_within(full["uv"][tri], g[prefix + "tex_uv"][tri], floor=1e-3)[0] >= 0.999
     occ = o.occluded(to_rays(g["shadow_rays"]), g["shadow_max_t"])
     assert (occ == g["shadow_occluded"]).mean() >= 0.999, (occ == g["shadow_occluded"]).mean()
     if "ls_ref" in g:

@@ -1,7 +1,7 @@
-# quick GPU-box session: build, the GPU test suite, a short bench
+# quick GPU-box session: build, the GPU test suite, prebuilt variant sweep, optional source-level ncu capture
 set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/s_build.log 2>&1
-( time timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 ) > gpurun_out/s_pytest.log 2>&1
-timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/s_bench.log 2>&1
-tail -5 gpurun_out/s_pytest.log; tail -1 gpurun_out/s_bench.log | cut -c1-200
+if [ "${QUICK_TESTS:-1}" = "1" ]; then ( time timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 ) > gpurun_out/s_pytest.log 2>&1; tail -5 gpurun_out/s_pytest.log; fi
+if [ -d variants ]; then bash tools/sweep_prebuilt.sh ${QUICK_VARIANTS:-}; fi
+if [ "${QUICK_NCU:-}" != "" ]; then bash tools/ncu_source.sh $QUICK_NCU; fi
