@@ -214,6 +214,12 @@ int ptc_resolve_device(ptc_ctx *ctx, const float *accum_rgb_device, float *out_r
                        void *cuda_stream);
 #define PTC_MAX_BOUNCES 64
 
+/* SURVEY 8(e), "the BVH is built once and broadcast": a committed context copied to another GPU.  The new context owns copies of
+ * everything ptc_commit put on the device (BVH, shading records, material / light tables, environment map and its sampling
+ * tables, textures), made with peer copies over NVLink -- no second parse, feed or build (replaces calling the whole
+ * Scene::Scene / rtcCommitScene sequence of src/scene.cpp, src/rtc_manager.cpp once per device).  Options are inherited. */
+int ptc_replicate(ptc_ctx *src, int device, ptc_ctx **out);
+
 /* ---- context-owned device framebuffer: Integrator::run's radianceLookup kept in HBM ----------- */
 /* `std::vector<float> radianceLookup(3*W*H)` zero-filled (src/integrator.cpp:37-40) */
 int ptc_framebuffer_clear(ptc_ctx *ctx);
@@ -227,6 +233,21 @@ int ptc_framebuffer_render(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, u
  * peers may be NULL when n_peers = 0; at most PTC_MAX_PEERS peers. */
 int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t n_peers, uint32_t divisor, float *out_rgb_host);
 #define PTC_MAX_PEERS 15
+/* ptc_framebuffer_render that also keeps the images the reference checkpoints (src/integrator.cpp:87-92: `auto-%05dspp.exr` after
+ * 1, 2, 4, ... samples) WITHOUT ending a wave there: snapshot i = this context's sums over the samples it has rendered with a
+ * global index below sample_counts[i] (ascending; at most PTC_MAX_CHECKPOINTS).  The K7 resolve writes the copies while it adds
+ * the wave's samples in order, so a snapshot holds exactly the floats a render that stopped there would hold.  Snapshots stay
+ * valid until the context's next framebuffer render. */
+int ptc_framebuffer_render_checkpoints(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
+                                       int last_bounce, const uint32_t *sample_counts, uint32_t n_counts);
+#define PTC_MAX_CHECKPOINTS 32
+/* ptc_framebuffer_gather in two halves, so that the host enqueues the next wave before it waits for this one's image
+ * (src/integrator.cpp:42-105 alternates render and host work; here they overlap).  begin: enqueues reduce + resolve of the
+ * framebuffers (snapshot < 0) or of snapshot `snapshot` of every context and the copy to a pinned host buffer; later renders
+ * on any of the contexts are ordered after the reads.  end: waits for that copy and hands the image out. */
+int ptc_framebuffer_gather_begin(ptc_ctx *root, ptc_ctx *const *peers, uint32_t n_peers, int snapshot, uint32_t divisor,
+                                 uint32_t *ticket);
+int ptc_framebuffer_gather_end(ptc_ctx *root, uint32_t ticket, float *out_rgb_host);
 
 /* ---- ray queries (keep Scene::testIntersect / testOcclusion alive for CPU integrators; parity) */
 int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);        /* rtcIntersect1 */

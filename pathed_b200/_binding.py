@@ -94,6 +94,14 @@ class Api:
     def _fn(self, name):
         return getattr(self.lib, self.prefix + name)
 
+    def replicate(self, device):
+        """ptc_replicate: a committed context copied to another GPU (peer copies of the finished device data, no second build)"""
+        other = Api.__new__(Api)
+        other.lib, other.prefix, other.ctx = self.lib, self.prefix, ctypes.c_void_p()
+        other.width, other.height = self.width, self.height
+        self._call("replicate", ctypes.c_int(device), ctypes.byref(other.ctx))
+        return other
+
     def _call(self, name, *args):
         fn = self._fn(name)
         fn.restype = ctypes.c_int
@@ -230,6 +238,22 @@ class Api:
         out = np.zeros((self.height, self.width, 3), np.float32)
         arr = (ctypes.c_void_p * max(len(peers), 1))(*[p.ctx.value for p in peers])
         self._call("framebuffer_gather", arr, ctypes.c_uint32(len(peers)), ctypes.c_uint32(divisor), _ptr(out))
+        return out
+
+    def framebuffer_render_checkpoints(self, seed, first_sample, n_spp, start_bounce, last_bounce, sample_counts):
+        counts = np.ascontiguousarray(sample_counts, np.uint32)
+        self._call("framebuffer_render_checkpoints", ctypes.c_uint64(seed), ctypes.c_uint32(first_sample), ctypes.c_uint32(n_spp),
+                   ctypes.c_int(start_bounce), ctypes.c_int(last_bounce), _ptr(counts), ctypes.c_uint32(len(counts)))
+
+    def framebuffer_gather_begin(self, peers=(), snapshot=-1, divisor=1):
+        arr = (ctypes.c_void_p * max(len(peers), 1))(*[p.ctx.value for p in peers])
+        ticket = ctypes.c_uint32(0)
+        self._call("framebuffer_gather_begin", arr, ctypes.c_uint32(len(peers)), ctypes.c_int(snapshot), ctypes.c_uint32(divisor), ctypes.byref(ticket))
+        return ticket.value
+
+    def framebuffer_gather_end(self, ticket):
+        out = np.zeros((self.height, self.width, 3), np.float32)
+        self._call("framebuffer_gather_end", ctypes.c_uint32(ticket), _ptr(out))
         return out
 
     # ---- queries

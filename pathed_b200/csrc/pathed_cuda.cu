@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <chrono>
 #include <vector>
@@ -582,15 +583,21 @@ __global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers 
 }
 
 // ------------------------------------------------------------------------------------------------ K7 resolve
-__global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WaveParams wp, float *accum, uint32_t width, uint32_t height)
+// Checkpoints that fall inside a wave (src/integrator.cpp:87-92 saves the image after 1, 2, 4, ... samples): the resolve keeps a copy
+// of the running sums after `at[i]` samples of the wave in dst[i], so a wave does not have to end at every power of two
+struct CheckpointPlan { uint32_t n; uint32_t at[PTC_MAX_CHECKPOINTS]; float *dst[PTC_MAX_CHECKPOINTS]; };
+__global__ void __launch_bounds__(256) accumulateKernel(PathBuffers pb, WaveParams wp, float *accum, uint32_t width, uint32_t height, const __grid_constant__ CheckpointPlan plan)
 {
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < wp.nPixels; q += gridDim.x * blockDim.x) {
         const size_t pixel = slotToPixel(q, width, height);
         float r = accum[3 * pixel], g = accum[3 * pixel + 1], b = accum[3 * pixel + 2];
+        uint32_t next = 0;
         for (uint32_t s = 0; s < wp.sppWave; s++) { // radianceLookup += color, one sample after the other (src/sample_integrator.cpp:61-63)
+            while (next < plan.n && plan.at[next] == s) { float *d = plan.dst[next++]; d[3 * pixel] = r; d[3 * pixel + 1] = g; d[3 * pixel + 2] = b; }
             const float4 c = streamLoad(pb.out + pixelSampleToSlot(q, s, wp));
             r += c.x; g += c.y; b += c.z;
         }
+        while (next < plan.n) { float *d = plan.dst[next++]; d[3 * pixel] = r; d[3 * pixel + 1] = g; d[3 * pixel + 2] = b; }
         accum[3 * pixel] = r; accum[3 * pixel + 1] = g; accum[3 * pixel + 2] = b;
     }
 }
@@ -991,15 +998,20 @@ struct ptc_ctx {
     WideBVH bvh;
     uint32_t nLights = 0;
     // device
-    std::vector<void *> allocations;
+    std::vector<void *> allocations; std::vector<size_t> allocationBytes; // scene data on the device (what ptc_replicate copies)
+    std::vector<DMaterial> deviceMaterials;                              // the device material table as uploaded (holds texel pointers)
     DScene scene;
     PathBuffers paths; uint32_t pathCapacity = 0; std::vector<void *> pathAllocations;
     BounceCounters *counters = nullptr;
     uint32_t classMask = 0; // material classes present in the scene
     unsigned long long *totals = nullptr;
     float *accumScratch = nullptr; size_t accumScratchSize = 0;
-    float *framebuffer = nullptr, *gatherOut = nullptr, *gatherStage = nullptr; size_t framebufferSize = 0, gatherStageSize = 0;
+    float *framebuffer = nullptr, *gatherStage = nullptr; size_t framebufferSize = 0, gatherStageSize = 0;
     cudaEvent_t framebufferReady = nullptr;
+    std::vector<float *> snapshots;                      // checkpoint copies of the framebuffer (ptc_framebuffer_render_checkpoints)
+    struct Gather { float *device = nullptr, *pinned = nullptr; cudaEvent_t done = nullptr; bool busy = false; };
+    std::vector<Gather> gathers;                         // results of ptc_framebuffer_gather_begin in flight
+    cudaEvent_t gatherRead = nullptr;                    // the last gather kernel of this (root) context finished reading the framebuffers
     float *pinned = nullptr; size_t pinnedSize = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -1063,6 +1075,7 @@ static int upload(ptc_ctx *ctx, const T *src, size_t count, const T **dst, std::
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     CUDA_TRY(ctx, cudaMalloc(&p, bytes));
     track.push_back(p);
+    if (&track == &ctx->allocations) { ctx->allocationBytes.push_back(bytes); }
     if (count) { CUDA_TRY(ctx, cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice)); }
     *dst = (const T *)p;
     return PTC_OK;
@@ -1115,9 +1128,13 @@ void ptc_destroy(ptc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void *p : ctx->allocations) { cudaFree(p); }
+    ctx->allocations.clear(); ctx->allocationBytes.clear();
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
-    cudaFree(ctx->framebuffer); cudaFree(ctx->gatherOut); cudaFree(ctx->gatherStage);
+    cudaFree(ctx->framebuffer); cudaFree(ctx->gatherStage);
+    for (float *snapshot : ctx->snapshots) { cudaFree(snapshot); }
+    for (auto &g : ctx->gathers) { cudaFree(g.device); if (g.pinned) { cudaFreeHost(g.pinned); } if (g.done) { cudaEventDestroy(g.done); } }
+    if (ctx->gatherRead) { cudaEventDestroy(ctx->gatherRead); }
     cudaFree(ctx->volumeOut); cudaFree(ctx->volumeCursor);
     if (ctx->framebufferReady) { cudaEventDestroy(ctx->framebufferReady); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
@@ -1463,8 +1480,8 @@ int ptc_commit(ptc_ctx *ctx)
             if (ctx->bvhBuilder == 1) {
                 DeviceWideBVH built;
                 buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built);
-                if (built.nodes) { A.push_back(built.nodes); }
-                if (built.triangles) { A.push_back(built.triangles); }
+                if (built.nodes) { A.push_back(built.nodes); ctx->allocationBytes.push_back((size_t)built.nNodes * sizeof(WideNode)); }
+                if (built.triangles) { A.push_back(built.triangles); ctx->allocationBytes.push_back((size_t)built.nTriangles * sizeof(LeafTriangle)); }
                 s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
                 ctx->bvhPlocIterations = built.plocIterations;
                 // host copy for the scalar counting traversal (ptc_count_traversal) and the statistics
@@ -1583,6 +1600,7 @@ int ptc_commit(ptc_ctx *ctx)
     if ((rc = upload(ctx, (const uint2 *)primIds2.data(), primIds2.size() / 2, &s.primIds, A))) { return rc; }
     if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
     if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }
+    ctx->deviceMaterials = dm;
     if ((rc = upload(ctx, lights.data(), lights.size(), &s.lights, A))) { return rc; }
     s.nLights = ctx->nLights;
 
@@ -1653,6 +1671,72 @@ int ptc_commit(ptc_ctx *ctx)
 
 #define NEED_COMMIT(ctx) do { if (!(ctx)) { return PTC_ERR_INVALID; } if (!(ctx)->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "scene not committed"); } } while (0)
 
+// the scene is parsed, fed and its BVH built ONCE; every further GPU of the spp split gets a copy of the finished
+// device data over NVLink (cudaMemcpyPeer) instead of a second feed + build.  Everything ptc_commit uploaded is position-independent
+// except the pointers of DScene and the texel pointers inside the material table, which are rebased here.
+static void forEachScenePointer(DScene &s, const std::function<void(const void **)> &f)
+{
+    const void **fields[] = {(const void **)&s.bvh.nodes, (const void **)&s.bvh.triangles, (const void **)&s.bvh.spheres, (const void **)&s.bvh.primEvent,
+                             (const void **)&s.bvh.sphereEvent, (const void **)&s.bvh.placements, (const void **)&s.positions, (const void **)&s.normals,
+                             (const void **)&s.uvs, (const void **)&s.prims, (const void **)&s.primIds, (const void **)&s.instIds, (const void **)&s.sphereIds,
+                             (const void **)&s.triShade, (const void **)&s.materials, (const void **)&s.lights, (const void **)&s.envRgba,
+                             (const void **)&s.envThetaCdf, (const void **)&s.envPhiCdf, (const void **)&s.envPhiEmpty, (const void **)&s.envThetaGuide,
+                             (const void **)&s.envPhiGuide, (const void **)&s.media, (const void **)&s.geomMedium};
+    for (const void **field : fields) { f(field); }
+}
+
+int ptc_replicate(ptc_ctx *src, int device, ptc_ctx **out)
+{
+    if (!out) { return PTC_ERR_INVALID; }
+    *out = nullptr;
+    NEED_COMMIT(src);
+    ptc_ctx *dst = nullptr;
+    int rc = ptc_create(device, &dst);
+    if (rc) { CTX_FAIL(src, rc, "cannot create a context on device %d", device); }
+    // host-side state the calls after ptc_commit consult (the staged geometry itself is not needed any more)
+    dst->materials = src->materials; dst->media = src->media; dst->geometries = src->geometries; dst->scenes = src->scenes; dst->rootGeometry = src->rootGeometry;
+    dst->integrator = src->integrator; dst->hasEnv = src->hasEnv; dst->hasCamera = src->hasCamera;
+    dst->envW = src->envW; dst->envH = src->envH; dst->envScale = src->envScale;
+    memcpy(dst->envM2W, src->envM2W, sizeof(dst->envM2W)); memcpy(dst->envW2M, src->envW2M, sizeof(dst->envW2M));
+    memcpy(dst->camToWorld, src->camToWorld, sizeof(dst->camToWorld)); dst->vfov = src->vfov; dst->width = src->width; dst->height = src->height;
+    dst->bvh = src->bvh; dst->nLights = src->nLights; dst->classMask = src->classMask;
+    dst->pathsPerWave = src->pathsPerWave; dst->stageTiming = src->stageTiming; dst->countTraversal = src->countTraversal;
+    dst->bvhBuilder = src->bvhBuilder; dst->bvhBuildMs = 0.f; dst->bvhPlocIterations = src->bvhPlocIterations;
+    dst->deviceMaterials = src->deviceMaterials;
+    dst->scene = src->scene;
+    auto fail = [&](const char *what) { src->error = std::string("ptc_replicate: ") + what + ": " + cudaGetErrorString(cudaGetLastError()); ptc_destroy(dst); return PTC_ERR_CUDA; };
+    if (cudaSetDevice(device) != cudaSuccess) { return fail("cudaSetDevice"); }
+    for (size_t i = 0; i < src->allocations.size(); i++) {
+        void *copy = nullptr;
+        if (cudaMalloc(&copy, src->allocationBytes[i]) != cudaSuccess) { return fail("cudaMalloc"); }
+        dst->allocations.push_back(copy); dst->allocationBytes.push_back(src->allocationBytes[i]);
+        if (cudaMemcpyPeerAsync(copy, device, src->allocations[i], src->device, src->allocationBytes[i], dst->stream) != cudaSuccess) { return fail("cudaMemcpyPeerAsync"); }
+    }
+    bool rebased = true;
+    auto rebase = [&](const void **field) {
+        if (!*field) { return; }
+        for (size_t i = 0; i < src->allocations.size(); i++) { if (src->allocations[i] == *field) { *field = dst->allocations[i]; return; } }
+        rebased = false;
+    };
+    forEachScenePointer(dst->scene, rebase);
+    for (DMaterial &m : dst->deviceMaterials) { rebase((const void **)&m.texels); }
+    if (!rebased) { src->error = "ptc_replicate: a scene pointer does not start one of the context's allocations"; ptc_destroy(dst); return PTC_ERR_STATE; }
+    if (!dst->deviceMaterials.empty() &&
+        cudaMemcpyAsync((void *)dst->scene.materials, dst->deviceMaterials.data(), dst->deviceMaterials.size() * sizeof(DMaterial), cudaMemcpyHostToDevice, dst->stream) != cudaSuccess) {
+        return fail("material table");
+    }
+    {
+        float gamma[256];
+        for (int c = 0; c < 256; c++) { gamma[c] = powf(c / 255.f, 2.2f); }
+        if (cudaMemcpyToSymbolAsync(c_gammaTable, gamma, sizeof(gamma), 0, cudaMemcpyHostToDevice, dst->stream) != cudaSuccess) { return fail("gamma table"); }
+    }
+    // the source's data must be complete before it is read (ptc_commit is synchronous, so it is) and the copies before `dst` is used
+    if (cudaStreamSynchronize(dst->stream) != cudaSuccess) { return fail("copy"); }
+    dst->committed = true;
+    *out = dst;
+    return PTC_OK;
+}
+
 static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
 {
     if (capacity <= ctx->pathCapacity) { return PTC_OK; }
@@ -1678,8 +1762,26 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
     return PTC_OK;
 }
 
+// Which checkpoints the resolve of one wave (global samples F .. F + S - 1 of a render call) snapshots, and after how many of the wave's
+// samples: those that fall inside it, plus -- in the first / last wave of the call -- those before / after the call's samples (copies of
+// the sums as they were / as they end up: the spp split gives every GPU a block of samples, and a checkpoint is the sum over all GPUs)
+struct Checkpoints { const uint32_t *counts = nullptr; uint32_t n = 0; float *const *dst = nullptr; };
+static CheckpointPlan planFor(const Checkpoints &cp, uint32_t F, uint32_t S, bool isFirst, bool isLast)
+{
+    CheckpointPlan plan; plan.n = 0;
+    for (uint32_t i = 0; i < cp.n; i++) {
+        const uint32_t c = cp.counts[i]; // sample count: the checkpoint holds samples 0 .. c - 1
+        const bool inside = c > F && c <= F + S;
+        if (!(inside || (isFirst && c <= F) || (isLast && c > F + S))) { continue; }
+        plan.at[plan.n] = c <= F ? 0u : std::min(c - F, S);
+        plan.dst[plan.n] = cp.dst[i];
+        plan.n++;
+    }
+    return plan;
+}
+
 // one wave = fixed launch sequence; all queue sizes stay on the device
-static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream)
+static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream, const CheckpointPlan &plan)
 {
     const DScene &s = ctx->scene;
     PathBuffers pb = ctx->paths; // by value: the current / next buffers swap after every bounce
@@ -1729,7 +1831,7 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     }
     {
         StageTimer t(ctx, stream, STAGE_OTHER);
-        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height);
+        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
         tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
     }
     ctx->launches += 2;
@@ -1739,7 +1841,8 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
 }
 
 // VolumePathTracer waves: one volumePathKernel launch over pixels x sppWave paths, then the same in-order accumulation
-static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, uint32_t sppWave, int start, int last, float *accumDevice, cudaStream_t stream)
+static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, uint32_t sppWave, int start, int last, float *accumDevice, cudaStream_t stream,
+                        const Checkpoints &checkpoints)
 {
     const DScene &s = ctx->scene;
     const uint32_t nPixels = (uint32_t)s.width * (uint32_t)s.height;
@@ -1763,7 +1866,8 @@ static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint3
         }
         {
             StageTimer t(ctx, stream, STAGE_OTHER);
-            accumulateKernel<<<std::min<uint32_t>((nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height);
+            const CheckpointPlan plan = planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp);
+            accumulateKernel<<<std::min<uint32_t>((nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
         }
         ctx->launches += 2;
         CUDA_TRY(ctx, cudaGetLastError());
@@ -1773,21 +1877,22 @@ static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint3
     return PTC_OK;
 }
 
-static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accumDevice, cudaStream_t stream)
+static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, float *accumDevice, cudaStream_t stream,
+                          const Checkpoints &checkpoints = Checkpoints())
 {
     if (start < 0 || (last != -1 && start > last)) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bad bounce window [%d, %d]", start, last); }
     if (last == -1 || last > PTC_MAX_BOUNCES) { last = PTC_MAX_BOUNCES; }
     const uint32_t nPixels = (uint32_t)ctx->scene.width * (uint32_t)ctx->scene.height;
     uint32_t sppWave = (uint32_t)std::max<int64_t>(1, ctx->pathsPerWave / (int64_t)nPixels);
     sppWave = std::min(sppWave, std::max(nSpp, 1u));
-    if (ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { return renderVolume(ctx, seed, firstSample, nSpp, sppWave, start, last, accumDevice, stream); }
+    if (ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { return renderVolume(ctx, seed, firstSample, nSpp, sppWave, start, last, accumDevice, stream, checkpoints); }
     int rc = ensurePathBuffers(ctx, nPixels * sppWave);
     if (rc) { return rc; }
     for (uint32_t done = 0; done < nSpp; done += sppWave) {
         WaveParams wp;
         wp.seed = seed; wp.firstSample = firstSample + done; wp.sppWave = std::min(sppWave, nSpp - done); wp.nPixels = nPixels;
         wp.startBounce = start; wp.lastBounce = last;
-        if ((rc = launchWave(ctx, wp, accumDevice, stream))) { return rc; }
+        if ((rc = launchWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
     }
     ctx->samples += (uint64_t)nPixels * nSpp;
     return PTC_OK;
@@ -1832,9 +1937,8 @@ static int ensureFramebuffer(ptc_ctx *ctx)
 {
     const size_t n = (size_t)3 * ctx->scene.width * ctx->scene.height;
     if (ctx->framebufferSize == n) { return PTC_OK; }
-    cudaFree(ctx->framebuffer); cudaFree(ctx->gatherOut); ctx->framebuffer = ctx->gatherOut = nullptr; ctx->framebufferSize = 0;
+    cudaFree(ctx->framebuffer); ctx->framebuffer = nullptr; ctx->framebufferSize = 0;
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->framebuffer, n * sizeof(float)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->gatherOut, n * sizeof(float)));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->framebuffer, 0, n * sizeof(float), ctx->stream));
     if (!ctx->framebufferReady) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->framebufferReady, cudaEventDisableTiming)); }
     ctx->framebufferSize = n;
@@ -1853,27 +1957,46 @@ int ptc_framebuffer_clear(ptc_ctx *ctx)
 
 int ptc_framebuffer_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last)
 {
-    NEED_COMMIT(ctx);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const int rc = ensureFramebuffer(ctx);
-    if (rc) { return rc; }
-    return renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->framebuffer, ctx->stream);
+    return ptc_framebuffer_render_checkpoints(ctx, seed, firstSample, nSpp, start, last, nullptr, 0);
 }
 
-int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers, uint32_t divisor, float *out)
+int ptc_framebuffer_render_checkpoints(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp, int start, int last, const uint32_t *sampleCounts, uint32_t nCounts)
+{
+    NEED_COMMIT(ctx);
+    if (nCounts > PTC_MAX_CHECKPOINTS || (nCounts && !sampleCounts)) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bad checkpoint list (at most %d)", PTC_MAX_CHECKPOINTS); }
+    for (uint32_t i = 1; i < nCounts; i++) { if (sampleCounts[i] <= sampleCounts[i - 1]) { CTX_FAIL(ctx, PTC_ERR_INVALID, "checkpoint sample counts must ascend"); } }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = ensureFramebuffer(ctx);
+    if (rc) { return rc; }
+    while (ctx->snapshots.size() < nCounts) {
+        float *buffer = nullptr;
+        CUDA_TRY(ctx, cudaMalloc((void **)&buffer, ctx->framebufferSize * sizeof(float)));
+        ctx->snapshots.push_back(buffer);
+    }
+    if (nSpp == 0) { // no samples for this context in the wave: every snapshot is the framebuffer as it stands
+        for (uint32_t i = 0; i < nCounts; i++) { CUDA_TRY(ctx, cudaMemcpyAsync(ctx->snapshots[i], ctx->framebuffer, ctx->framebufferSize * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream)); }
+        return PTC_OK;
+    }
+    Checkpoints cp; cp.counts = sampleCounts; cp.n = nCounts; cp.dst = ctx->snapshots.data();
+    return renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->framebuffer, ctx->stream, cp);
+}
+
+int ptc_framebuffer_gather_begin(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers, int snapshot, uint32_t divisor, uint32_t *ticketOut)
 {
     NEED_COMMIT(root);
-    if (!out || !divisor || (nPeers && !peers) || nPeers > PTC_MAX_PEERS) { CTX_FAIL(root, PTC_ERR_INVALID, "bad gather arguments"); }
+    if (!ticketOut || !divisor || (nPeers && !peers) || nPeers > PTC_MAX_PEERS) { CTX_FAIL(root, PTC_ERR_INVALID, "bad gather arguments"); }
     CUDA_TRY(root, cudaSetDevice(root->device));
     int rc = ensureFramebuffer(root);
     if (rc) { return rc; }
     const size_t n = root->framebufferSize;
+    auto source = [&](ptc_ctx *c) -> const float * { return snapshot < 0 ? c->framebuffer : (size_t)snapshot < c->snapshots.size() ? c->snapshots[snapshot] : nullptr; };
+    if (!source(root)) { CTX_FAIL(root, PTC_ERR_STATE, "no snapshot %d was rendered", snapshot); }
     FramebufferSet set;
-    set.fb[0] = root->framebuffer; set.count = 1;
+    set.fb[0] = source(root); set.count = 1;
     size_t staged = 0;
     for (uint32_t g = 0; g < nPeers; g++) {
         ptc_ctx *peer = peers[g];
-        if (!peer || !peer->committed || peer->framebufferSize != n) { CTX_FAIL(root, PTC_ERR_STATE, "peer %u has no framebuffer of the same size", g); }
+        if (!peer || !peer->committed || peer->framebufferSize != n || !source(peer)) { CTX_FAIL(root, PTC_ERR_STATE, "peer %u has no framebuffer (or snapshot) of the same size", g); }
         // order the gather after the peer's pending renders
         CUDA_TRY(root, cudaSetDevice(peer->device));
         CUDA_TRY(root, cudaEventRecord(peer->framebufferReady, peer->stream));
@@ -1881,10 +2004,10 @@ int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers
         CUDA_TRY(root, cudaStreamWaitEvent(root->stream, peer->framebufferReady, 0));
         int canAccess = 0;
         if (peer->device != root->device) { cudaDeviceCanAccessPeer(&canAccess, root->device, peer->device); }
-        if (peer->device == root->device) { set.fb[set.count++] = peer->framebuffer; continue; }
+        if (peer->device == root->device) { set.fb[set.count++] = source(peer); continue; }
         if (canAccess) {
             const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
-            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); set.fb[set.count++] = peer->framebuffer; continue; }
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); set.fb[set.count++] = source(peer); continue; }
             cudaGetLastError();
         }
         // no peer mapping: stage the peer's framebuffer into local memory first
@@ -1895,21 +2018,51 @@ int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers
             root->gatherStageSize = (size_t)nPeers * n;
         }
         float *slot = root->gatherStage + staged * n; staged++;
-        CUDA_TRY(root, cudaMemcpyPeerAsync(slot, root->device, peer->framebuffer, peer->device, n * sizeof(float), root->stream));
+        CUDA_TRY(root, cudaMemcpyPeerAsync(slot, root->device, source(peer), peer->device, n * sizeof(float), root->stream));
         set.fb[set.count++] = slot;
     }
-    if (root->pinnedSize < n) {
-        if (root->pinned) { cudaFreeHost(root->pinned); root->pinned = nullptr; }
-        CUDA_TRY(root, cudaMallocHost((void **)&root->pinned, n * sizeof(float)));
-        root->pinnedSize = n;
+    // a free result slot (device buffer + pinned host buffer + event)
+    uint32_t ticket = 0;
+    while (ticket < root->gathers.size() && root->gathers[ticket].busy) { ticket++; }
+    if (ticket == root->gathers.size()) { root->gathers.push_back(ptc_ctx::Gather()); }
+    ptc_ctx::Gather &slot = root->gathers[ticket];
+    if (!slot.device) {
+        CUDA_TRY(root, cudaMalloc((void **)&slot.device, n * sizeof(float)));
+        CUDA_TRY(root, cudaMallocHost((void **)&slot.pinned, n * sizeof(float)));
+        CUDA_TRY(root, cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
     }
-    gatherResolveKernel<<<std::min<uint32_t>((uint32_t)((n / 4 + 255) / 256) + 1, (uint32_t)root->gridSimple * 4), 256, 0, root->stream>>>(set, root->gatherOut, (uint32_t)n, divisor);
+    gatherResolveKernel<<<std::min<uint32_t>((uint32_t)((n / 4 + 255) / 256) + 1, (uint32_t)root->gridSimple * 4), 256, 0, root->stream>>>(set, slot.device, (uint32_t)n, divisor);
     root->launches++;
     CUDA_TRY(root, cudaGetLastError());
-    CUDA_TRY(root, cudaMemcpyAsync(root->pinned, root->gatherOut, n * sizeof(float), cudaMemcpyDeviceToHost, root->stream));
-    CUDA_TRY(root, cudaStreamSynchronize(root->stream));
-    memcpy(out, root->pinned, n * sizeof(float));
+    // renders that follow on any of the contexts must not overwrite what this kernel reads
+    if (!root->gatherRead) { CUDA_TRY(root, cudaEventCreateWithFlags(&root->gatherRead, cudaEventDisableTiming)); }
+    CUDA_TRY(root, cudaEventRecord(root->gatherRead, root->stream));
+    for (uint32_t g = 0; g < nPeers; g++) { CUDA_TRY(root, cudaStreamWaitEvent(peers[g]->stream, root->gatherRead, 0)); }
+    CUDA_TRY(root, cudaMemcpyAsync(slot.pinned, slot.device, n * sizeof(float), cudaMemcpyDeviceToHost, root->stream));
+    CUDA_TRY(root, cudaEventRecord(slot.done, root->stream));
+    slot.busy = true;
+    *ticketOut = ticket;
     return PTC_OK;
+}
+
+int ptc_framebuffer_gather_end(ptc_ctx *root, uint32_t ticket, float *out)
+{
+    NEED_COMMIT(root);
+    if (!out || ticket >= root->gathers.size() || !root->gathers[ticket].busy) { CTX_FAIL(root, PTC_ERR_INVALID, "no gather in flight under ticket %u", ticket); }
+    CUDA_TRY(root, cudaSetDevice(root->device));
+    ptc_ctx::Gather &slot = root->gathers[ticket];
+    CUDA_TRY(root, cudaEventSynchronize(slot.done));
+    memcpy(out, slot.pinned, root->framebufferSize * sizeof(float));
+    slot.busy = false;
+    return PTC_OK;
+}
+
+int ptc_framebuffer_gather(ptc_ctx *root, ptc_ctx *const *peers, uint32_t nPeers, uint32_t divisor, float *out)
+{
+    if (!out) { return PTC_ERR_INVALID; }
+    uint32_t ticket = 0;
+    const int rc = ptc_framebuffer_gather_begin(root, peers, nPeers, -1, divisor, &ticket);
+    return rc ? rc : ptc_framebuffer_gather_end(root, ticket, out);
 }
 
 int ptc_resolve_device(ptc_ctx *ctx, const float *accum, float *out, uint32_t spp, void *stream)

@@ -7,7 +7,10 @@
 
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <fstream>
+#include <thread>
+#include <vector>
 
 namespace pathed {
 
@@ -24,6 +27,21 @@ void Image::set(int row, int col, float r, float g, float b)
     m_data[index + 0] = (unsigned char)(fminf(powf(r, 1 / 2.2), 1.f) * 255);
     m_data[index + 1] = (unsigned char)(fminf(powf(g, 1 / 2.2), 1.f) * 255);
     m_data[index + 2] = (unsigned char)(fminf(powf(b, 1 / 2.2), 1.f) * 255);
+}
+
+void Image::setAll(const float *rgb)
+{
+    const int threads = std::max(1, std::min(m_height, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        pool.emplace_back([this, rgb, t, threads]() {
+            for (int row = t; row < m_height; row += threads) {
+                const float *line = rgb + 3 * (size_t)row * m_width;
+                for (int col = 0; col < m_width; col++) { set(row, col, line[3 * col], line[3 * col + 1], line[3 * col + 2]); }
+            }
+        });
+    }
+    for (std::thread &t : pool) { t.join(); }
 }
 
 void Image::save(const std::string &filestem) { save(filestem, false); }

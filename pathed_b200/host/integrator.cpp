@@ -56,20 +56,26 @@ double now()
 // ------------------------------------------------------------------------------------------------ Scene
 Scene::Scene(const SceneDescription &description, int gpus) : m_width(description.camera.width), m_height(description.camera.height)
 {
-    for (int device = 0; device < std::max(1, gpus); device++) {
-        ptc_ctx *ctx = nullptr;
-        if (ptc_create(device, &ctx) != PTC_OK || !ctx) {
-            for (ptc_ctx *c : m_contexts) { ptc_destroy(c); }
-            throw std::runtime_error("Failed to create device " + std::to_string(device) + " (no CUDA device? there is no CPU path)");
-        }
-        m_contexts.push_back(ctx);
-        const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium, sinkBeginInstance, sinkEndInstance, sinkAddInstance};
-        const int status = feedScene(description, sink);
-        if (status != PTC_OK) {
+    // device 0 is fed and builds the BVH; the other devices of the spp split receive copies of the finished device data
+    ptc_ctx *ctx = nullptr;
+    if (ptc_create(0, &ctx) != PTC_OK || !ctx) { throw std::runtime_error("Failed to create device 0 (no CUDA device? there is no CPU path)"); }
+    m_contexts.push_back(ctx);
+    const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium, sinkBeginInstance, sinkEndInstance, sinkAddInstance};
+    const int status = feedScene(description, sink);
+    if (status != PTC_OK) {
+        const std::string message = ptc_last_error(ctx);
+        ptc_destroy(ctx); m_contexts.clear();
+        throw std::runtime_error("scene upload failed: " + message);
+    }
+    for (int device = 1; device < std::max(1, gpus); device++) {
+        ptc_ctx *copy = nullptr;
+        if (ptc_replicate(ctx, device, &copy) != PTC_OK || !copy) {
             const std::string message = ptc_last_error(ctx);
             for (ptc_ctx *c : m_contexts) { ptc_destroy(c); }
-            throw std::runtime_error("scene upload failed: " + message);
+            m_contexts.clear();
+            throw std::runtime_error("Failed to replicate the scene to device " + std::to_string(device) + ": " + message);
         }
+        m_contexts.push_back(copy);
     }
 }
 
@@ -176,10 +182,12 @@ void CudaPathTracer::sampleImage(std::vector<float> &radianceLookup, Scene &scen
     m_samples += (uint64_t)scene.width() * scene.height();
 }
 
-// Waves end at every power of two (the reference checkpoints there, src/integrator.cpp:87-92) and after at most
-// wave_spp samples; inside a wave the samples are split over the GPUs in contiguous blocks of global sample indices,
-// each GPU accumulating into its own device framebuffer.  At a wave boundary ONE kernel on GPU 0 sums all framebuffers
-// through peer (NVLink) loads and divides by the sample count (K7 resolve), and the result is copied to the host once.
+// A wave covers up to wave_spp samples per GPU, split over the GPUs in contiguous blocks of global sample indices, each GPU
+// accumulating into its own device framebuffer.  The images the reference checkpoints (after 1, 2, 4, ... samples,
+// src/integrator.cpp:87-92) that fall inside a wave are snapshots the resolve kernel keeps on the way (ptc_framebuffer_render_
+// checkpoints): waves do not end there.  After a wave ONE kernel on GPU 0 per image sums the framebuffers (or snapshots) through peer
+// (NVLink) loads and divides by the sample count (K7 resolve); the copies to the host are asynchronous, and the next wave is
+// enqueued before the host converts, reports and saves this one -- GPU and host work overlap.
 void CudaPathTracer::run(Image &image, Scene &scene, std::function<void(RenderStatus)> callback, bool *quit)
 {
     const int width = g_job->width(), height = g_job->height(), primarySamples = g_job->spp();
@@ -197,49 +205,64 @@ void CudaPathTracer::run(Image &image, Scene &scene, std::function<void(RenderSt
     }
     std::vector<ptc_ctx *> peers;
     for (int g = 1; g < gpus; g++) { peers.push_back(scene.context(g)); }
+    ptc_ctx *root = scene.context(0);
     std::vector<float> resolved((size_t)3 * width * height);
 
-    int done = 0;
-    while (done < primarySamples) {
-        const double begin = now();
-        int nextPowerOfTwo = 1;
-        while (nextPowerOfTwo <= done) { nextPowerOfTwo <<= 1; }
-        const int target = std::min(std::min(nextPowerOfTwo, done + m_waveSpp * gpus), primarySamples);
-        const int waveSamples = target - done;
-        // contiguous blocks: GPU g takes samples [done + g*per, ...); any split gives the same sums up to fp32 order
-        const int per = (waveSamples + gpus - 1) / gpus;
+    struct Pending { int spp; uint32_t ticket; bool checkpoint; };
+    struct Wave { int first = 0, end = 0; std::vector<Pending> images; double enqueued = 0.0; };
+    // enqueue the wave that starts at sample `first`: renders on every GPU, then one gather per image wanted from it
+    auto enqueue = [&](int first) {
+        Wave wave;
+        wave.first = first; wave.end = std::min(first + m_waveSpp * gpus, primarySamples);
+        wave.enqueued = now();
+        std::vector<uint32_t> counts; // power-of-two sample counts inside the wave, the wave's end excluded (that is the live framebuffer)
+        for (int c = 1; c < wave.end; c <<= 1) { if (c > first) { counts.push_back((uint32_t)c); } }
+        if (counts.size() > PTC_MAX_CHECKPOINTS) { counts.resize(PTC_MAX_CHECKPOINTS); }
+        // contiguous blocks: GPU g takes samples [first + g*per, ...); any split gives the same sums up to fp32 order
+        const int per = (wave.end - first + gpus - 1) / gpus;
         for (int g = 0; g < gpus; g++) {
-            const int first = done + g * per, count = std::min(per, target - first);
-            if (count <= 0) { continue; }
-            check(scene.context(g), ptc_framebuffer_render(scene.context(g), m_seed, (uint32_t)first, (uint32_t)count, start, last), "render");
+            const int from = std::min(first + g * per, wave.end), count = std::min(per, wave.end - from);
+            // a GPU without samples in this wave still snapshots its sums: a checkpoint is the sum over all GPUs
+            check(scene.context(g), ptc_framebuffer_render_checkpoints(scene.context(g), m_seed, (uint32_t)from, (uint32_t)count, start, last,
+                                                                       counts.data(), (uint32_t)counts.size()), "render");
         }
-        done = target;
-        check(scene.context(0), ptc_framebuffer_gather(scene.context(0), peers.data(), (uint32_t)peers.size(), (uint32_t)done, resolved.data()),
-              "framebuffer gather");
-        const double end = now();
-        m_renderSeconds += end - begin;
-        m_samples += (uint64_t)waveSamples * width * height;
-        m_nextSample = (uint32_t)done;
-        postwave(scene, done);
+        for (size_t i = 0; i < counts.size(); i++) {
+            Pending p; p.spp = (int)counts[i]; p.checkpoint = true;
+            check(root, ptc_framebuffer_gather_begin(root, peers.data(), (uint32_t)peers.size(), (int)i, counts[i], &p.ticket), "checkpoint gather");
+            wave.images.push_back(p);
+        }
+        Pending p; p.spp = wave.end; p.checkpoint = (wave.end & (wave.end - 1)) == 0;
+        check(root, ptc_framebuffer_gather_begin(root, peers.data(), (uint32_t)peers.size(), -1, (uint32_t)wave.end, &p.ticket), "framebuffer gather");
+        wave.images.push_back(p);
+        return wave;
+    };
 
-        RenderStatus status;
-        status.setSample(done);
-        callback(status);
-        {
+    const double loopBegin = now();
+    Wave current = enqueue(0);
+    while (current.first < primarySamples) {
+        Wave next;
+        const bool more = current.end < primarySamples && !*quit;
+        if (more) { next = enqueue(current.end); } // the GPUs go on while the host handles the images of `current`
+        for (const Pending &p : current.images) {
+            check(root, ptc_framebuffer_gather_end(root, p.ticket, resolved.data()), "framebuffer gather");
             std::lock_guard<std::mutex> guard(image.getLock());
-            image.setSpp(done);
-            for (int row = 0; row < height; row++) {
-                for (int col = 0; col < width; col++) {
-                    const size_t index = 3 * ((size_t)row * width + col);
-                    image.set(row, col, resolved[index], resolved[index + 1], resolved[index + 2]);
-                }
-            }
-            if ((done & (done - 1)) == 0) { image.saveCheckpoint("auto"); }
+            image.setSpp(p.spp);
+            image.setAll(resolved.data());
+            if (p.checkpoint) { image.saveCheckpoint("auto"); }
         }
+        const double end = now();
+        m_samples += (uint64_t)(current.end - current.first) * width * height;
+        m_nextSample = (uint32_t)current.end;
+        m_renderSeconds = end - loopBegin;
+        postwave(scene, current.end);
+        RenderStatus status;
+        status.setSample(current.end);
+        callback(status);
         std::ostringstream line;
-        line << "sample: " << done << "/" << primarySamples << std::fixed << std::setprecision(1) << " (" << (end - begin) << "s elapsed)";
+        line << "sample: " << current.end << "/" << primarySamples << std::fixed << std::setprecision(1) << " (" << (end - current.enqueued) << "s elapsed)";
         Logger::line(line.str());
-        if (*quit) { return; }
+        if (!more) { break; }
+        current = next;
     }
 }
 

@@ -100,6 +100,7 @@ class Image {
 public:
     Image(int width, int height);
     void set(int row, int col, float r, float g, float b); // row 0 = bottom scanline (Q14)
+    void setAll(const float *rgb);                         // set(row, col, ...) for every pixel of a row-major 3*W*H buffer, on all host threads
     void save(const std::string &filestem);           // <outdir>/<stem>.exr
     void saveCheckpoint(const std::string &filestem); // + <outdir>/<stem>-%05dspp.exr
     void write(const std::string &filename);          // 24-bit BMP of the 8-bit preview

@@ -34,7 +34,8 @@ def test_cli_renders_a_job_like_the_reference_binary(tmp_path):
     assert json.load(open(os.path.join(out, "report.json")))["scene"] == job["scene"]
     assert "sample: 8/8" in r.stdout and "PATHED_RESULT" in r.stdout
     ctx = load_scene(job["scene"], job["width"], job["height"])
-    for spp in (1, 8):
+    assert r.stdout.count("sample: ") == 1  # ONE wave of 8 spp: the checkpoints inside it are snapshots, not wave ends
+    for spp in (1, 2, 4, 8):
         want = (ctx.render(0x5EED, 0, spp, 0, 10) / np.float32(spp))[::-1].astype(np.float16).astype(np.float32)
         got = read_exr(os.path.join(out, "auto-%05dspp.exr" % spp))[..., :3]
         assert np.array_equal(got, want), spp  # same Philox streams, same accumulation order: bit-exact after HALF
@@ -101,6 +102,54 @@ def test_framebuffer_gather_sums_contexts_and_resolves():
     assert np.array_equal(sums, load_scene("scenes/cornell-glass.json", 40, 40).render(5, 0, 4, 0, 10))
     a.framebuffer_clear()
     assert not a.framebuffer_gather([], divisor=1).any()
+
+
+def test_checkpoint_snapshots_equal_renders_that_stopped_there():
+    """ptc_framebuffer_render_checkpoints: the K7 resolve keeps the running sums after 1, 2, 4, 8 of a 12-sample wave -- the very
+    floats of renders that ended there (src/integrator.cpp:87-92 without ending waves at the checkpoints); with the samples split
+    over two contexts a checkpoint is the sum of both contexts' snapshots, also where it lies outside a context's block"""
+    fresh = lambda: load_scene("scenes/cornell-glass.json", 40, 40)
+    counts = [1, 2, 4, 8]
+    a = fresh()
+    a.framebuffer_clear()
+    a.framebuffer_render_checkpoints(5, 0, 12, 0, 10, counts)
+    tickets = [a.framebuffer_gather_begin([], snapshot=i, divisor=1) for i in range(len(counts))] + [a.framebuffer_gather_begin([], divisor=1)]
+    images = [a.framebuffer_gather_end(t) for t in tickets]  # all in flight at once, collected afterwards
+    for c, image in zip(counts + [12], images):
+        assert np.array_equal(image, fresh().render(5, 0, c, 0, 10)), c
+    # a second wave on top: snapshots before / inside / after the wave's samples
+    a.framebuffer_render_checkpoints(5, 12, 6, 0, 10, [8, 16, 32])
+    got = [a.framebuffer_gather_end(a.framebuffer_gather_begin([], snapshot=i, divisor=1)) for i in range(3)]
+    assert np.array_equal(got[0], images[-1]) and np.array_equal(got[1], fresh().render(5, 0, 16, 0, 10)) and np.array_equal(got[2], fresh().render(5, 0, 18, 0, 10))
+    # two contexts, blocks [0, 6) and [6, 12): checkpoint 4 lies before b's block, 8 inside it, 16 behind both
+    a, b = fresh(), fresh()
+    a.framebuffer_clear(); b.framebuffer_clear()
+    a.framebuffer_render_checkpoints(5, 0, 6, 0, 10, [4, 8, 16])
+    b.framebuffer_render_checkpoints(5, 6, 6, 0, 10, [4, 8, 16])
+    four, eight, sixteen = [a.framebuffer_gather_end(a.framebuffer_gather_begin([b], snapshot=i, divisor=1)) for i in range(3)]
+    assert np.array_equal(four, fresh().render(5, 0, 4, 0, 10))
+    assert np.allclose(eight, fresh().render(5, 0, 8, 0, 10), rtol=2e-6, atol=1e-7)
+    assert np.array_equal(sixteen, a.framebuffer_gather([b], divisor=1))
+    b.framebuffer_render_checkpoints(5, 12, 0, 0, 10, [4])  # no samples in this wave: the snapshot is the framebuffer as it stands
+    assert np.array_equal(b.framebuffer_gather_end(b.framebuffer_gather_begin([], snapshot=0, divisor=1)), b.framebuffer_gather([], divisor=1))
+
+
+@pytest.mark.parametrize("scene", ["scenes/cornell-glass.json", "scenes/textured.json", "test_scenes/environment_map_sampling.json", "scenes/instanced.json", "scenes/cornell-medium.json"])
+def test_replicated_context_renders_what_the_original_renders(scene):
+    """ptc_replicate (build once, broadcast): the copy -- on the last device of the box, which is the same device on a
+    one-GPU box -- owns rebased copies of BVH, shading records, textures, environment tables and media, and renders bit-identically"""
+    import torch
+    from pathed_b200._binding import VOLUME_PATH_TRACER
+    if not os.path.exists(os.path.join(REPO_ROOT, scene)):
+        pytest.skip(scene + " not generated")
+    volume = "medium" in scene
+    a = load_scene(scene, 48, 40, integrator=VOLUME_PATH_TRACER if volume else 0)
+    b = a.replicate(torch.cuda.device_count() - 1)
+    want = a.render(3, 0, 4, 0, 6)
+    a.close()  # the copy does not depend on the original's memory
+    assert b.num_lights() > 0 and np.array_equal(b.render(3, 0, 4, 0, 6), want) and want.mean() > 0
+    cam = b.camera_rays(np.array([[20.0, 24.0]], np.float32))
+    assert b.intersect_full(cam)["hit"][0] == 1
 
 
 def test_multi_gpu_job_matches_single_gpu(tmp_path):
