@@ -310,11 +310,14 @@ def main():
     # the multi-rank image is checked, not only timed: rank 0's reduced image = mean radiance of every rank's samples
     image_check = None
     if distributed:
-        mean_local = torch.tensor([float(local.double().mean())], device="cuda", dtype=torch.float64)
+        # a sample can be NaN exactly where the reference's is (teapot, 1920x1080, seed 0x5EED: sample 5318 of pixel (402, 922) is NaN in the
+        # oracle too -- tools/nan_hunt.py), so the check runs over the finite pixels and reports the others
+        mean_local = torch.tensor([float(torch.nan_to_num(local.double(), nan=0.0, posinf=0.0, neginf=0.0).mean())], device="cuda", dtype=torch.float64)
         dist.all_reduce(mean_local, op=dist.ReduceOp.SUM)
         if rank == 0:
-            got, want = float(staging.double().mean()), float(mean_local.item())
-            image_check = {"reduced_mean": got, "sum_of_rank_means": want, "spp": (args.steps + args.warmup) * total_spp}
+            got, want = float(torch.nan_to_num(staging.double(), nan=0.0, posinf=0.0, neginf=0.0).mean()), float(mean_local.item())
+            image_check = {"reduced_mean": got, "sum_of_rank_means": want, "spp": (args.steps + args.warmup) * total_spp,
+                           "non_finite_values": int((~torch.isfinite(staging)).sum().item())}
             assert abs(got - want) <= 1e-4 * abs(want) + 1e-9, image_check
 
     # ---- e2e: the reference-facing call with a HOST radianceLookup (accumulated, not overwritten: upload, add, download).

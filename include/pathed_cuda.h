@@ -249,6 +249,14 @@ int ptc_framebuffer_gather_begin(ptc_ctx *root, ptc_ctx *const *peers, uint32_t 
                                  uint32_t *ticket);
 int ptc_framebuffer_gather_end(ptc_ctx *root, uint32_t ticket, float *out_rgb_host);
 
+/* ---- the random streams on their own (known-answer tests; need no scene) ---------------------- */
+/* Philox4x32-10, the generator that replaces RandomGenerator (src/random_generator.cpp:4-11) and std::rand (src/camera.cpp:51-52)
+ * on the device: out[4i..4i+3] = philox(counter = counters[4i..4i+3], key = keys[2i..2i+1]) */
+int ptc_philox4x32_10(ptc_ctx *ctx, const uint32_t *counters, const uint32_t *keys, uint32_t n, uint32_t *out);
+/* the first `draws` uniform floats in [0, 1) a path draws at a vertex: stream i = (pixel, sample, bounce) = streams[3i..3i+2] under
+ * `seed`, out[i * draws + d] = draw d (counter = (pixel, sample, bounce, d / 4), lane d % 4, top 24 bits) */
+int ptc_uniforms(ptc_ctx *ctx, uint64_t seed, const uint32_t *streams, uint32_t n_streams, uint32_t draws, float *out);
+
 /* ---- ray queries (keep Scene::testIntersect / testOcclusion alive for CPU integrators; parity) */
 int ptc_intersect(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_hit *hits);        /* rtcIntersect1 */
 int ptc_intersect_full(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, ptc_isect *out);  /* Scene::testIntersect */

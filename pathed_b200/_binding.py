@@ -256,6 +256,19 @@ class Api:
         self._call("framebuffer_gather_end", ctypes.c_uint32(ticket), _ptr(out))
         return out
 
+    # ---- random streams (known-answer tests)
+    def philox(self, counters, keys):
+        counters = np.ascontiguousarray(counters, np.uint32).reshape(-1, 4); keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 2)
+        out = np.zeros_like(counters)
+        self._call("philox4x32_10", _ptr(counters), _ptr(keys), ctypes.c_uint32(len(counters)), _ptr(out))
+        return out
+
+    def uniforms(self, seed, streams, draws):
+        streams = np.ascontiguousarray(streams, np.uint32).reshape(-1, 3)
+        out = np.zeros((len(streams), draws), np.float32)
+        self._call("uniforms", ctypes.c_uint64(seed), _ptr(streams), ctypes.c_uint32(len(streams)), ctypes.c_uint32(draws), _ptr(out))
+        return out
+
     # ---- queries
     def intersect(self, rays):
         hits = np.zeros(len(rays), HIT_DTYPE)

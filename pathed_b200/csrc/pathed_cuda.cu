@@ -956,6 +956,25 @@ __global__ void volumeReplayKernel(const __grid_constant__ DScene scene, const p
     }
 }
 
+// the counter-based generator on its own (known-answer tests: Random123's philox4x32-10 vectors, the draw order of a path vertex)
+__global__ void philoxKernel(const uint32_t *counters, const uint32_t *keys, uint32_t n, uint32_t *out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t block[4];
+        philox4x32_10(counters[4 * i], counters[4 * i + 1], counters[4 * i + 2], counters[4 * i + 3], keys[2 * i], keys[2 * i + 1], block);
+        for (int c = 0; c < 4; c++) { out[4 * i + c] = block[c]; }
+    }
+}
+__global__ void uniformsKernel(uint64_t seed, const uint32_t *streams, uint32_t nStreams, uint32_t draws, float *out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nStreams; i += gridDim.x * blockDim.x) {
+        Rng rng;
+        rng.initPhilox(seed, streams[3 * i], streams[3 * i + 1]);
+        rng.beginVertex(streams[3 * i + 2]);
+        for (uint32_t d = 0; d < draws; d++) { out[(size_t)i * draws + d] = rng.next(); }
+    }
+}
+
 // ================================================================================================ host context
 struct HostGeometry {
     int32_t medium = -1; // Surface::m_internalMedium of every surface of the geometry
@@ -2197,6 +2216,23 @@ int ptc_camera_rays(ptc_ctx *ctx, const float *rowCol, uint32_t n, ptc_ray *rays
 {
     NEED_COMMIT(ctx);
     return roundTrip(ctx, rowCol, (size_t)2 * n, rays, n, [&](float *d, ptc_ray *o) { cameraRaysKernel<<<gridFor(ctx, n), 128, 0, ctx->stream>>>(ctx->scene, d, n, o); });
+}
+int ptc_philox4x32_10(ptc_ctx *ctx, const uint32_t *counters, const uint32_t *keys, uint32_t n, uint32_t *out)
+{
+    if (!ctx || (n && (!counters || !keys || !out))) { return PTC_ERR_INVALID; }
+    uint32_t *dKeys = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc((void **)&dKeys, std::max<size_t>(n, 1) * 2 * sizeof(uint32_t)));
+    cudaMemcpyAsync(dKeys, keys, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    const int rc = roundTrip(ctx, counters, (size_t)4 * n, out, (size_t)4 * n, [&](uint32_t *d, uint32_t *o) { philoxKernel<<<std::max(1u, (n + 127) / 128), 128, 0, ctx->stream>>>(d, dKeys, n, o); });
+    cudaFree(dKeys);
+    return rc;
+}
+int ptc_uniforms(ptc_ctx *ctx, uint64_t seed, const uint32_t *streams, uint32_t nStreams, uint32_t draws, float *out)
+{
+    if (!ctx || (nStreams && draws && (!streams || !out))) { return PTC_ERR_INVALID; }
+    return roundTrip(ctx, streams, (size_t)3 * nStreams, out, (size_t)nStreams * draws,
+                     [&](uint32_t *d, float *o) { uniformsKernel<<<std::max(1u, (nStreams + 127) / 128), 128, 0, ctx->stream>>>(seed, d, nStreams, draws, o); });
 }
 int ptc_bsdf_eval(ptc_ctx *ctx, uint32_t material, const ptc_isect *isects, const float *wi, uint32_t n, float *f, float *pdf)
 {

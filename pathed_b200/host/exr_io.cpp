@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace pathed {
 
@@ -381,8 +382,7 @@ void loadEXR(const std::string &path, std::vector<float> &rgba, int &width, int 
     }
 }
 
-void saveEXR(const std::string &path, int width, int height, const std::vector<std::string> &names,
-             const std::vector<const float *> &planes, bool asHalf)
+std::vector<unsigned char> encodeEXR(int width, int height, const std::vector<std::string> &names, const std::vector<const float *> &planes, bool asHalf)
 {
     std::vector<unsigned char> out;
     auto i32 = [&](int32_t v) { unsigned char b[4]; memcpy(b, &v, 4); out.insert(out.end(), b, b + 4); };
@@ -405,25 +405,46 @@ void saveEXR(const std::string &path, int width, int height, const std::vector<s
     attr("screenWindowWidth", "float", 4); f32(1.f);
     out.push_back(0);
 
-    const size_t bytesPerLine = names.size() * (size_t)width * (asHalf ? 2 : 4);
-    const size_t tableStart = out.size();
-    out.resize(out.size() + 8 * (size_t)height);
-    for (int y = 0; y < height; y++) {
-        const uint64_t offset = out.size();
-        memcpy(&out[tableStart + 8 * (size_t)y], &offset, 8);
-        i32(y); i32((int32_t)bytesPerLine);
-        for (size_t c = 0; c < names.size(); c++) {
-            const float *row = planes[c] + (size_t)y * width;
-            for (int x = 0; x < width; x++) {
-                if (asHalf) { const unsigned short h = floatToHalf(row[x]); unsigned char b[2]; memcpy(b, &h, 2); out.insert(out.end(), b, b + 2); }
-                else { f32(row[x]); }
+    // offset table, then one block per scanline (y, byte count, the channels' rows one after the other): sizes are known up front,
+    // so the scanlines are converted in place by all host threads
+    const size_t bytesPerLine = names.size() * (size_t)width * (asHalf ? 2 : 4), blockBytes = 8 + bytesPerLine;
+    const size_t tableStart = out.size(), dataStart = tableStart + 8 * (size_t)height;
+    out.resize(dataStart + blockBytes * (size_t)height);
+    unsigned char *base = out.data();
+    const int threads = std::max(1, std::min(height, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) {
+        pool.emplace_back([&, t]() {
+            for (int y = t; y < height; y += threads) {
+                const uint64_t offset = dataStart + blockBytes * (size_t)y;
+                memcpy(base + tableStart + 8 * (size_t)y, &offset, 8);
+                unsigned char *p = base + offset;
+                const int32_t line = y, count = (int32_t)bytesPerLine;
+                memcpy(p, &line, 4); memcpy(p + 4, &count, 4); p += 8;
+                for (size_t c = 0; c < names.size(); c++) {
+                    const float *row = planes[c] + (size_t)y * width;
+                    if (asHalf) { for (int x = 0; x < width; x++) { const unsigned short h = floatToHalf(row[x]); memcpy(p, &h, 2); p += 2; } }
+                    else { memcpy(p, row, (size_t)width * 4); p += (size_t)width * 4; }
+                }
             }
-        }
+        });
     }
+    for (std::thread &t : pool) { t.join(); }
+    return out;
+}
+
+void writeFileBytes(const std::string &path, const std::vector<unsigned char> &bytes)
+{
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) { throw std::runtime_error("exr: cannot write " + path); }
-    fwrite(out.data(), 1, out.size(), f);
+    fwrite(bytes.data(), 1, bytes.size(), f);
     fclose(f);
+}
+
+void saveEXR(const std::string &path, int width, int height, const std::vector<std::string> &names,
+             const std::vector<const float *> &planes, bool asHalf)
+{
+    writeFileBytes(path, encodeEXR(width, height, names, planes, asHalf));
 }
 
 } // namespace pathed

@@ -17,6 +17,10 @@ void loadEXR(const std::string &path, std::vector<float> &rgba, int &width, int 
 void saveEXR(const std::string &path, int width, int height, const std::vector<std::string> &channelNames,
              const std::vector<const float *> &channels, bool asHalf);
 
+// the same file as bytes (a checkpoint is written under two names), and a plain whole-file write
+std::vector<unsigned char> encodeEXR(int width, int height, const std::vector<std::string> &channelNames, const std::vector<const float *> &channels, bool asHalf);
+void writeFileBytes(const std::string &path, const std::vector<unsigned char> &bytes);
+
 unsigned short floatToHalf(float value);
 float halfToFloat(unsigned short bits);
 

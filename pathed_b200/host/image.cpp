@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <fstream>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -47,6 +48,9 @@ void Image::setAll(const float *rgb)
 void Image::save(const std::string &filestem) { save(filestem, false); }
 void Image::saveCheckpoint(const std::string &filestem) { save(filestem, true); }
 
+// The files are what the reference writes (src/image.cpp:80-154: <stem>.exr, and <stem>-%05dspp.exr for a checkpoint -- the same
+// bytes twice); the image is encoded here and now, the bytes go to disk on a writer thread, in the order of the calls (auto.exr is
+// rewritten by every checkpoint), so that the render loop does not wait for the file system.  flush() / the destructor wait.
 void Image::save(const std::string &filestem, bool checkpoint)
 {
     const size_t n = (size_t)m_width * m_height;
@@ -54,21 +58,31 @@ void Image::save(const std::string &filestem, bool checkpoint)
     for (int c = 0; c < 3; c++) { planes[c].resize(n); }
     for (size_t i = 0; i < n; i++) { for (int c = 0; c < 3; c++) { planes[c][i] = m_raw[3 * i + c]; } }
     const std::string directory = g_job ? g_job->outputDirectory() : std::string();
-    const std::string outputExr = directory + filestem + ".exr";
-    char suffix[32];
-    snprintf(suffix, sizeof(suffix), "-%05dspp.exr", m_spp);
-    const std::string outputSppExr = directory + filestem + suffix;
-    try {
-        saveEXR(outputExr, m_width, m_height, {"B", "G", "R"}, {planes[2].data(), planes[1].data(), planes[0].data()}, true);
-        printf("Saved exr file. [ %s ] \n", outputExr.c_str());
-        if (checkpoint) {
-            saveEXR(outputSppExr, m_width, m_height, {"B", "G", "R"}, {planes[2].data(), planes[1].data(), planes[0].data()}, true);
-            printf("Saved exr file. [ %s ] \n", outputSppExr.c_str());
-        }
-    } catch (const std::exception &e) {
-        fprintf(stderr, "Save EXR err: %s\n", e.what());
+    std::vector<std::string> paths = {directory + filestem + ".exr"};
+    if (checkpoint) {
+        char suffix[32];
+        snprintf(suffix, sizeof(suffix), "-%05dspp.exr", m_spp);
+        paths.push_back(directory + filestem + suffix);
     }
+    auto bytes = std::make_shared<std::vector<unsigned char>>(encodeEXR(m_width, m_height, {"B", "G", "R"}, {planes[2].data(), planes[1].data(), planes[0].data()}, true));
+    std::shared_future<void> previous = m_lastWrite;
+    m_lastWrite = std::async(std::launch::async, [previous, bytes, paths]() {
+        if (previous.valid()) { previous.wait(); }
+        for (const std::string &path : paths) {
+            try {
+                writeFileBytes(path, *bytes);
+                printf("Saved exr file. [ %s ] \n", path.c_str());
+            } catch (const std::exception &e) { fprintf(stderr, "Save EXR err: %s\n", e.what()); }
+        }
+    }).share();
 }
+
+void Image::flush()
+{
+    if (m_lastWrite.valid()) { m_lastWrite.wait(); }
+}
+
+Image::~Image() { flush(); }
 
 void Image::write(const std::string &filename)
 {

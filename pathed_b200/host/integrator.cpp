@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <future>
 #include <cstdio>
 #include <iomanip>
 #include <sstream>
@@ -54,11 +55,11 @@ double now()
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ Scene
-Scene::Scene(const SceneDescription &description, int gpus) : m_width(description.camera.width), m_height(description.camera.height)
+Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first) : m_width(description.camera.width), m_height(description.camera.height)
 {
     // device 0 is fed and builds the BVH; the other devices of the spp split receive copies of the finished device data
-    ptc_ctx *ctx = nullptr;
-    if (ptc_create(0, &ctx) != PTC_OK || !ctx) { throw std::runtime_error("Failed to create device 0 (no CUDA device? there is no CPU path)"); }
+    ptc_ctx *ctx = first;
+    if (!ctx && (ptc_create(0, &ctx) != PTC_OK || !ctx)) { throw std::runtime_error("Failed to create device 0 (no CUDA device? there is no CPU path)"); }
     m_contexts.push_back(ctx);
     const SceneSink sink = {ctx, sinkMaterial, sinkMesh, sinkSphere, sinkEnvironment, sinkCamera, sinkCommit, sinkTexture, sinkMedium, sinkInternalMedium, sinkBeginInstance, sinkEndInstance, sinkAddInstance};
     const int status = feedScene(description, sink);
@@ -121,8 +122,20 @@ uint32_t Scene::lightCount() const
 
 std::unique_ptr<Scene> parseSceneForJob(const Job &job, const std::string &rootDirectory)
 {
-    const SceneDescription description = parseScene(job.scene(), rootDirectory, job.width(), job.height());
-    return std::unique_ptr<Scene>(new Scene(description, job.gpus()));
+    // the CUDA runtime comes up (driver initialisation, module load: seconds on a multi-GPU box) while the host parses the scene files
+    std::future<ptc_ctx *> device = std::async(std::launch::async, []() { ptc_ctx *ctx = nullptr; ptc_create(0, &ctx); return ctx; });
+    const double begin = now();
+    SceneDescription description;
+    try { description = parseScene(job.scene(), rootDirectory, job.width(), job.height()); }
+    catch (...) { if (ptc_ctx *ctx = device.get()) { ptc_destroy(ctx); } throw; }
+    const double parsed = now();
+    ptc_ctx *first = device.get();
+    if (!first) { throw std::runtime_error("Failed to create device 0 (no CUDA device? there is no CPU path)"); }
+    const double ready = now();
+    std::unique_ptr<Scene> scene(new Scene(description, job.gpus(), first));
+    printf("Scene: %0.2fs parsing, %0.2fs more until the device was up, %0.2fs upload + BVH build + copies to %d more GPU(s)\n",
+           parsed - begin, ready - parsed, now() - ready, job.gpus() - 1);
+    return scene;
 }
 
 // ------------------------------------------------------------------------------------------------ Integrator

@@ -17,6 +17,7 @@
 #include "scene_description.hpp"
 
 #include <functional>
+#include <future>
 #include <istream>
 #include <memory>
 #include <mutex>
@@ -99,6 +100,8 @@ private:
 class Image {
 public:
     Image(int width, int height);
+    ~Image();
+    void flush();                                          // waits until every file handed to the writer thread is on disk
     void set(int row, int col, float r, float g, float b); // row 0 = bottom scanline (Q14)
     void setAll(const float *rgb);                         // set(row, col, ...) for every pixel of a row-major 3*W*H buffer, on all host threads
     void save(const std::string &filestem);           // <outdir>/<stem>.exr
@@ -117,6 +120,7 @@ private:
     std::vector<unsigned char> m_data;
     std::vector<float> m_raw;
     std::mutex m_lock;
+    std::shared_future<void> m_lastWrite; // files are written in call order by a background task chain
 };
 
 struct Ray {
@@ -135,7 +139,8 @@ struct Intersection {
 // The committed scene on one or more GPUs (one ptc_ctx per device, scene replicated).
 class Scene {
 public:
-    Scene(const SceneDescription &description, int gpus = 1);
+    // `first`: an already created context for device 0 (ownership passes to the Scene); null = create one
+    Scene(const SceneDescription &description, int gpus = 1, ptc_ctx *first = nullptr);
     ~Scene();
     Scene(const Scene &) = delete;
     Scene &operator=(const Scene &) = delete;

@@ -444,3 +444,30 @@ def test_scene_without_lights_renders_black():
         assert ctx.num_lights() == 0
         imgs.append(ctx.render(3, 0, 4, 0, 5))
     assert np.isfinite(imgs[0]).all() and (imgs[0] == 0).all() and np.array_equal(imgs[0], imgs[1])
+
+
+def test_philox_known_answers_on_the_device():
+    """Random123's kat_vectors for philox4x32-10 through the DEVICE generator (ptc_philox4x32_10), and the uniform streams of path
+    vertices (ptc_uniforms: counter = (pixel, sample, bounce, draw / 4), lane draw % 4, top 24 bits) bit for bit against the oracle's"""
+    import ctypes
+    from oracle_binding import oracle_lib
+    ctx = gpu_context()
+    counters = [(0, 0, 0, 0), (0xffffffff,) * 4, (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)]
+    keys = [(0, 0), (0xffffffff,) * 2, (0xa4093822, 0x299f31d0)]
+    want = [(0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)]
+    assert np.array_equal(ctx.philox(counters, keys), np.array(want, np.uint32))
+    rng = np.random.default_rng(5)
+    big_c = rng.integers(0, 2 ** 32, (4096, 4), dtype=np.uint64).astype(np.uint32); big_k = rng.integers(0, 2 ** 32, (4096, 2), dtype=np.uint64).astype(np.uint32)
+    got = ctx.philox(big_c, big_k)
+    lib = oracle_lib()
+    out = (ctypes.c_uint32 * 4)()
+    for i in range(0, 4096, 37):
+        lib.orc_philox4x32_10((ctypes.c_uint32 * 4)(*big_c[i].tolist()), (ctypes.c_uint32 * 2)(*big_k[i].tolist()), out)
+        assert tuple(out) == tuple(got[i].tolist())
+    streams = np.array([(0, 0, 0), (3, 5, 1), (1048575, 4095, 64), (0xFFFFFFFF, 0xFFFFFFFF, 7)], np.uint32)
+    seed = 0x5EED0123456789AB
+    u = ctx.uniforms(seed, streams, 64)
+    assert (u >= 0).all() and (u < 1).all()
+    for s, (pixel, sample, bounce) in enumerate(streams.tolist()):
+        ref = np.array([lib.orc_uniform(ctypes.c_uint64(seed), pixel, sample, bounce, d) for d in range(64)], np.float32)
+        assert np.array_equal(u[s], ref)
