@@ -23,7 +23,7 @@ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y +
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ V3 operator*(V3 a, float t) { return mk(a.x * t, a.y * t, a.z * t); }
 __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ V3 operator/(V3 a, float t) { return mk(a.x / t, a.y / t, a.z / t); }
+__device__ __forceinline__ V3 operator/(V3 a, float t) { return mk(divIeee(a.x, t), divIeee(a.y, t), divIeee(a.z, t)); } // IEEE division, zero numerators answered directly
 __device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }            // src/vector.cpp:18-21
 __device__ __forceinline__ float length(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }          // :28-35
@@ -263,7 +263,7 @@ __device__ __forceinline__ void makeIsect(const DScene &s, V3 O, V3 D, const Ray
 __device__ __forceinline__ float tfCos2(V3 v) { return v.y * v.y; }
 __device__ __forceinline__ float tfSin(V3 v) { return sqrtIeee(fmaxf(0.f, 1.f - tfCos2(v))); }
 __device__ __forceinline__ float tfSin2(V3 v) { return 1.f - tfCos2(v); }
-__device__ __forceinline__ float tfTan(V3 v) { return tfSin(v) / v.y; }
+__device__ __forceinline__ float tfTan(V3 v) { return divIeee(tfSin(v), v.y); }
 __device__ __forceinline__ float tfTan2(V3 v) { return divIeee(tfSin2(v), tfCos2(v)); }
 __device__ __forceinline__ float tfCosPhi(V3 v) // :69-76
 {
@@ -353,7 +353,7 @@ __device__ __forceinline__ float mfD(const DMaterial &m, V3 wh) // src/beckmann.
         const float cp = tfCosPhi(wh), sp = tfSinPhi(wh);
         const float num = expHost(-tan2 * (divIeee(cp * cp, alpha2) + divIeee(sp * sp, alpha2)));
         const float den = (float)(PTC_PI_D * (double)alpha2 * (double)cos4);
-        return num / den;
+        return divIeee(num, den); // num underflows to 0 for directions far off a narrow lobe
     }
     const float sum = alpha2 + tan2;
     const float den = (float)(PTC_PI_D * (double)cos4 * (double)sum * (double)sum);
@@ -416,13 +416,13 @@ __device__ __forceinline__ V3 microfacetF(const DMaterial &m, const Isect &i, V3
     const V3 wo = normalize(toLocal(i, i.wo)), wi = normalize(toLocal(i, wiW));
     const float cosO = fabsf(wo.y), cosI = fabsf(wi.y);
     const V3 wh = normalize(wo + wi);
-    pdf = mfPdf(m, wh) / (4.f * dot(wo, wh));
+    pdf = divIeee(mfPdf(m, wh), 4.f * dot(wo, wh));
     if (cosO == 0.f || cosI == 0.f) { return mk(0.f, 0.f, 0.f); }
     if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) { return mk(0.f, 0.f, 0.f); }
     const float F = fresnelDielectric(clampf(dot(wi, wh), 0.f, 1.f), 1.f, 1.5f); // Fresnel fixed at 1 -> 1.5 (Q10)
     const float D = mfD(m, wh);
     const float G = mfG(m, wo, wi);
-    const float val = ((1.f * D) * G * F) / (4 * cosI * cosO);
+    const float val = divIeee((1.f * D) * G * F, 4 * cosI * cosO);
     return mk(val, val, val);
 }
 
@@ -471,7 +471,7 @@ __device__ __forceinline__ void microfacetSample(const DMaterial &m, const Isect
     const V3 wo = toLocal(i, i.wo);
     const V3 wh = mfSampleWh(m, r);
     s.wi = toWorld(i, reflect(wo, wh));
-    s.pdf = mfPdf(m, wh) / (4.f * dot(wo, wh));
+    s.pdf = divIeee(mfPdf(m, wh), 4.f * dot(wo, wh));
     s.thr = microfacetF(m, i, s.wi, unused); s.delta = false;
 }
 
@@ -525,16 +525,27 @@ __device__ __forceinline__ void bsdfSample(const DMaterial &m, const Isect &i, R
         return;
     }
     default: { // PTC_PLASTIC, src/plastic.cpp:37-66: xi > 0.5 -> diffuse lobe
+        // The two branches of the reference differ only in how wi and the sampled lobe's pdf come about; both then evaluate BOTH lobes for
+        // wi (the sampled lobe inside its own sample(), the other one for the sum).  Only the first part is divergent here: the
+        // evaluations run once, for the whole warp (same functions, same arguments, same floats).
         const float xi = r.next();
-        if (xi > 0.5f) {
-            lambertSample(m, i, r, s);
-            float pm; const V3 fm = microfacetF(m, i, s.wi, pm);
-            s.pdf = (s.pdf + pm) / 2.f; s.thr = s.thr + fm;
-        } else {
-            microfacetSample(m, i, r, s);
-            float pl; const V3 fl = lambertF(m, i, s.wi, pl);
-            s.pdf = (s.pdf + pl) / 2.f; s.thr = s.thr + fl;
+        const bool diffuse = xi > 0.5f;
+        float sampledPdf;
+        if (diffuse) { // Lambertian::sample, src/lambertian.cpp:43-58
+            const V3 l = cosineSample(r);
+            s.wi = toWorld(i, l); sampledPdf = l.y * PTC_INV_PI;
+        } else {       // Microfacet::sample, src/microfacet.cpp:60-78
+            const V3 wo = toLocal(i, i.wo);
+            const V3 wh = mfSampleWh(m, r);
+            s.wi = toWorld(i, reflect(wo, wh));
+            sampledPdf = divIeee(mfPdf(m, wh), 4.f * dot(wo, wh));
         }
+        float pl, pm;
+        const V3 fl = lambertF(m, i, s.wi, pl);
+        const V3 fm = microfacetF(m, i, s.wi, pm);
+        s.pdf = (sampledPdf + (diffuse ? pm : pl)) / 2.f;
+        s.thr = fl + fm; // diffuse: lambertF + microfacetF, specular: microfacetF + lambertF -- the same sums
+        s.delta = false;
         return;
     }
     }

@@ -39,10 +39,17 @@ PTC_HD float u2f(uint32_t u)
 // IEEE-rounded division / square root regardless of compiler flags: hit records must match Embree's, and unit vectors feed
 // 1 - cos^2 terms whose cancellation multiplies every ulp (a fast-math build was measured: Beckmann alpha = 0.005 eval and
 // sample fixtures miss the 1e-5 gate), so the library is built with the precise forms throughout.
+// On the device an exactly zero numerator is answered without dividing: the division sequence (MUFU.RCP + FFMA refinement) guards itself
+// with FCHK, which sends every operand with a zero exponent field -- 0.0 included -- to a ~150-instruction slow path that the whole warp
+// waits for.  Zeros are common here (axis-aligned normals, black colour channels, a Beckmann D that underflowed): measured 9 slow-path calls
+// per Lambertian vertex on the dragon workload's floor, 15 % of the Plastic kernel's instructions.  0 / b = +-0 (NaN for b = 0 or NaN).
 PTC_HD float divIeee(float a, float b)
 {
 #if defined(__CUDA_ARCH__)
-    return __fdiv_rn(a, b);
+    const bool zero = a == 0.f;
+    const float q = __fdiv_rn(zero ? 1.f : a, b);
+    const float z = (b == 0.f || b != b) ? __int_as_float(0x7FFFFFFF) : __uint_as_float((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u);
+    return zero ? z : q;
 #else
     return a / b;
 #endif

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# Profiles of one wave of the dragon workload (run under gpurun, one GPU).  usage: tools/gpu_profile.sh <tag>
+#  1. per-launch metrics of every kernel of a 64-spp wave (gpu time, DRAM / L2 bytes, issue utilisation, lanes, hit rates, occupancy)
+#  2. --set full with sources of the first stage launches of a 16-spp wave (bounces 0 and 1 of every stage)
+set -u
+cd "$(dirname "$0")/.."
+tag=${1:-r02}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/p_build.log 2>&1
+M=dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,l1tex__t_sector_hit_rate.pct,lts__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,l1tex__t_bytes.sum
+timeout 900 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${tag}_wave_metrics.csv python tools/profile_wave.py dragon 64 gpurun_out/${tag}_wave_counts.json > gpurun_out/${tag}_wave.log 2>&1
+tail -1 gpurun_out/${tag}_wave.log
+timeout 1200 ncu --set full --import-source on --clock-control none -k 'regex:materialKernel|logicKernel|traverseKernel' -c 9 \
+  -f -o gpurun_out/${tag}_stages python tools/profile_wave.py dragon 16 gpurun_out/${tag}_wave16_counts.json > gpurun_out/${tag}_stages.log 2>&1
+ls -la gpurun_out/${tag}_stages.ncu-rep
