@@ -445,33 +445,42 @@ __device__ __forceinline__ void finishPath(const PathBuffers &pb, uint32_t origi
     streamStore(pb.out + origin, make_float4(c.x + result.x, c.y + result.y, c.z + result.z, 0.f));
 }
 
-__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask)
+// `bounce` = k of every path of the launch (ray k leaves vertex k), so which records a path needs is known before any of them
+// arrives: hit, result, (modulation | throughput) and the occlusion byte are requested together, the pending NEE term as soon as the
+// flags are there.  The class of the surface (material type, emitter bit) comes from one byte per primitive (DScene::primClass)
+// instead of the index record and the material table one after the other.
+__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask, int bounce)
 {
     const uint32_t n = bc->extendCount;
+    const int k = bounce;
+    const uint32_t lane = threadIdx.x & 31u;
     // uniform cost per path: static warp-strided assignment (whole warps stay in the loop together for the ballots below);
     // slot p of the current buffers = item p of this bounce's ray list, so every load below is a dense, coalesced one
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t p = base + (threadIdx.x & 31u);
+        const uint32_t p = base + lane;
         int cls = -1;
         if (p < n) {
             const float4 h4 = streamLoad(pb.hit + p);
             const float4 res4 = streamLoad(pb.result + p);
+            Rec32 mt; mt.a = mt.b = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint8_t occluded = 0;
+            if (k > 0) { mt = loadRec(pb.modThr, p); occluded = pb.occluded[p]; }
             const uint32_t flags = __float_as_uint(res4.w);
-            const int k = (int)(flags & FLAG_BOUNCE_MASK);
+            float4 ne = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k > 0 && (flags & FLAG_NEE)) { ne = streamLoad(pb.nee + 2 * (size_t)p); }
             const uint32_t prim = __float_as_uint(h4.w);
             const bool isHit = prim != PTC_MISS;
-            uint32_t material = 0;
-            bool emitter = false;
-            if (isHit) {
-                material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w);
-                emitter = __ldg(&scene.materials[material].emitter) != 0;
-            }
+            uint32_t surface = 0; // material type | emitter << 3
+            if (isHit) { surface = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereClass + (prim & ~PTC_SPHERE_FLAG)) : __ldg(scene.primClass + prim); }
+            const bool emitter = (surface & 8u) != 0;
             V3 result = mk(res4.x, res4.y, res4.z);
             bool alive = true;
             // the ray (origin, direction) is only needed for environment misses and emitter hits: a surviving ordinary hit never reads it
             const bool needRay = PTC_LAZY_DIRECTION ? (!isHit || emitter) : true;
             Rec32 ray;
             if (needRay) { ray = loadRec(pb.ray, p); }
+            uint32_t material = 0;
+            if (isHit && emitter) { material = (prim & PTC_SPHERE_FLAG) ? __ldg(scene.sphereIds + (prim & ~PTC_SPHERE_FLAG)).y : __ldg(&scene.prims[prim].w); }
             if (k == 0) {
                 // SampleIntegrator::samplePixel, src/sample_integrator.cpp:18-59; bounce 0: slot = origin slot
                 if (!isHit) {
@@ -489,10 +498,9 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                     }
                 }
             } else {
-                const Rec32 mt = loadRec(pb.modThr, p);
                 if (flags & FLAG_DIRECT) { // direct() of vertex k, src/path_tracer.cpp:79-111
                     V3 Ld = mk(0.f, 0.f, 0.f);
-                    if ((flags & FLAG_NEE) && !pb.occluded[p]) { const float4 ne = streamLoad(pb.nee + 2 * (size_t)p); Ld = Ld + mk(ne.x, ne.y, ne.z); }
+                    if ((flags & FLAG_NEE) && !occluded) { Ld = Ld + mk(ne.x, ne.y, ne.z); }
                     if (!isHit || emitter) { // directSampleBSDF contributes only for emitter hits and environment misses
                         const V3 O = mk(ray.a.x, ray.a.y, ray.a.z), D = mk(ray.b.x, ray.b.y, ray.b.z);
                         Isect bi;
@@ -509,14 +517,26 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
                     finishPath(pb, origin, flags, result);
                 }
             }
-            if (alive) { cls = __ldg(&scene.materials[material].type); }
+            if (alive) { cls = (int)(surface & 7u); }
         }
+        // survivors join the queue of their material class: the warp's counts of all classes are added with atomics issued back to
+        // back by one lane (one round trip for all of them), then every survivor takes its place behind the lanes before it
+        uint32_t masks[PTC_MATERIAL_CLASSES], starts[PTC_MATERIAL_CLASSES];
+#pragma unroll
+        for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
+            masks[t] = 0u; starts[t] = 0u;
+            if (!(classMask & (1u << t))) { continue; }
+            masks[t] = __ballot_sync(0xFFFFFFFFu, cls == t);
+            if (lane == 0 && masks[t]) { starts[t] = atomicAdd(&bc->classCount[t], __popc(masks[t])); }
+        }
+        uint32_t mine = 0, myBase = 0;
 #pragma unroll
         for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
             if (!(classMask & (1u << t))) { continue; }
-            const uint32_t slot = warpAppend(&bc->classCount[t], cls == t);
-            if (cls == t) { streamStore(pb.classQueue[t] + slot, p); }
+            const uint32_t start = __shfl_sync(0xFFFFFFFFu, starts[t], 0);
+            if (cls == t) { mine = masks[t]; myBase = start; }
         }
+        if (cls >= 0) { streamStore(pb.classQueue[cls] + myBase + __popc(mine & ((1u << lane) - 1u)), p); }
     }
 }
 
@@ -1627,6 +1647,13 @@ int ptc_commit(ptc_ctx *ctx)
     if ((rc = upload(ctx, (const uint2 *)sphereIds2.data(), sphereIds2.size() / 2, &s.sphereIds, A))) { return rc; }
     if ((rc = upload(ctx, dm.data(), dm.size(), &s.materials, A))) { return rc; }
     ctx->deviceMaterials = dm;
+    { // one byte per primitive / sphere for the logic stage: material type | emitter << 3
+        std::vector<uint8_t> primClass(nPrims), sphereClass(sphereIds2.size() / 2);
+        for (uint32_t p = 0; p < nPrims; p++) { const DMaterial &m = dm[prims4[4 * (size_t)p + 3]]; primClass[p] = (uint8_t)(m.type | (m.emitter ? 8 : 0)); }
+        for (size_t i = 0; i < sphereClass.size(); i++) { const DMaterial &m = dm[sphereIds2[2 * i + 1]]; sphereClass[i] = (uint8_t)(m.type | (m.emitter ? 8 : 0)); }
+        if ((rc = upload(ctx, primClass.data(), primClass.size(), &s.primClass, A))) { return rc; }
+        if ((rc = upload(ctx, sphereClass.data(), sphereClass.size(), &s.sphereClass, A))) { return rc; }
+    }
     if ((rc = upload(ctx, lights.data(), lights.size(), &s.lights, A))) { return rc; }
     s.nLights = ctx->nLights;
 
@@ -1707,7 +1734,8 @@ static void forEachScenePointer(DScene &s, const std::function<void(const void *
                              (const void **)&s.uvs, (const void **)&s.prims, (const void **)&s.primIds, (const void **)&s.instIds, (const void **)&s.sphereIds,
                              (const void **)&s.triShade, (const void **)&s.materials, (const void **)&s.lights, (const void **)&s.envRgba,
                              (const void **)&s.envThetaCdf, (const void **)&s.envPhiCdf, (const void **)&s.envPhiEmpty, (const void **)&s.envThetaGuide,
-                             (const void **)&s.envPhiGuide, (const void **)&s.media, (const void **)&s.geomMedium};
+                             (const void **)&s.envPhiGuide, (const void **)&s.media, (const void **)&s.geomMedium, (const void **)&s.primClass,
+                             (const void **)&s.sphereClass};
     for (const void **field : fields) { f(field); }
 }
 
@@ -1840,7 +1868,7 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
-            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask);
+            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, k);
             if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
             const int g = ctx->gridShade;
             if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }

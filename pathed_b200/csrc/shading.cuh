@@ -91,6 +91,7 @@ struct DScene {
     const uint2 *primIds;    // per triangle: geomID, primID (inside the scene the mesh is attached to)
     const uint2 *instIds;    // per triangle: RTCHit::instID[0..1] of the placement it was flattened from; null without instances (N4)
     const uint2 *sphereIds;  // per sphere: geomID, material
+    const uint8_t *primClass, *sphereClass; // per triangle / sphere: material type | emitter << 3 (all the logic stage needs of a surface)
     // per triangle, everything Scene::testIntersect's post-processing needs in one 80-byte record (5 float4): unnormalised Ng as the
     // traversal computes it + material | n0.xyz n1.x | n1.yz n2.xy | n2.z uv0.xy uv1.x | uv1.y uv2.xy.  Ten scattered sectors
     // (index record, 3 positions, 3 normals, 3 uvs) become three contiguous ones; built at ptc_commit with the same arithmetic.
