@@ -385,8 +385,10 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
 // ------------------------------------------------------------------------------------------------ K5-K6 logic
 // Handles the result of the ray that left vertex k (k = 0: the camera ray): everything in PathTracer::L between two
 // BSDF samples.  Cheap per path (the Intersection is only built for emitter hits); survivors go to the class queues.
-// 78-86 registers -> 3 CTAs of 256 (logic) / 6 CTAs of 128 (material) per SM.  Forcing 64 registers (4 / 8 CTAs) spills and was
-// measured equal (shade 42.7 ms per 4 steps either way), so the compiler's allocation stands.
+// Registers / occupancy (profiles/r02_sweep_shade_occupancy.txt, dragon workload, shade ms per 4 steps): the material kernels at 64
+// registers -> 8 CTAs of 128 per SM, with ~170 bytes of spills: 117.2; 80 registers / 6 CTAs 120.7; 96-100 / 5 CTAs 123.4; 10, 12, 16 CTAs
+// 125.8, 135.4, 136.0 -- they wait on dependent loads and fixed-latency arithmetic, so more resident warps pay until the spills take
+// over.  The logic kernel stays at the compiler's 76 registers (3 CTAs of 256): 64 / 48 registers measured 124.5 / 125.3 against 123.4.
 // SampleIntegrator::samplePixel's container branch (src/sample_integrator.cpp:35-51): the camera ray hit a Passthrough surface;
 // adds what lies behind it, attenuated by the medium.
 __device__ __forceinline__ void cameraContainerTerm(const DScene &scene, float ox, float oy, float oz, float dx, float dy, float dz, float *rgb)
@@ -449,7 +451,10 @@ __device__ __forceinline__ void finishPath(const PathBuffers &pb, uint32_t origi
 // arrives: hit, result, (modulation | throughput) and the occlusion byte are requested together, the pending NEE term as soon as the
 // flags are there.  The class of the surface (material type, emitter bit) comes from one byte per primitive (DScene::primClass)
 // instead of the index record and the material table one after the other.
-__global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask, int bounce)
+#ifndef PTC_LOGIC_MIN_BLOCKS
+#define PTC_LOGIC_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, PTC_LOGIC_MIN_BLOCKS) logicKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, uint32_t classMask, int bounce)
 {
     const uint32_t n = bc->extendCount;
     const int k = bounce;
@@ -543,7 +548,10 @@ __global__ void __launch_bounds__(256) logicKernel(DScene scene, PathBuffers pb,
 // ------------------------------------------------------------------------------------------------ K4 material
 // Vertex k + 1 of every surviving path whose hit surface has material class TYPE: Intersection, BSDF sample, NEE set-up.
 template <int TYPE>
-__global__ void __launch_bounds__(128) materialKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, BounceCounters *next)
+#ifndef PTC_MATERIAL_MIN_BLOCKS
+#define PTC_MATERIAL_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, PTC_MATERIAL_MIN_BLOCKS) materialKernel(DScene scene, PathBuffers pb, WaveParams wp, BounceCounters *bc, BounceCounters *next)
 {
     const uint32_t n = bc->classCount[TYPE];
     const uint32_t *queue = pb.classQueue[TYPE];
