@@ -115,6 +115,10 @@ echo "g++ $PFLAGS -c $HERE/shims/ptex_local_stub.cpp -o $B/obj/pathed_ptex_local
 for h in headless_main probe_main; do
   echo "g++ $PFLAGS -c $HERE/$h.cpp -o $B/obj/harness_$h.o" >> "$CMDS"
 done
+# the reference bound to libpathed_cuda: same reference objects, the Embree API served by a recording shim
+REPO=$(cd "$HERE/../.." && pwd)
+echo "g++ $PFLAGS -I$REPO/include -c $HERE/cuda_main.cpp -o $B/obj/harness_cuda_main.o" >> "$CMDS"
+echo "g++ -std=c++17 -O2 -fPIC -w -I$E/include -c $HERE/embree_shim.cpp -o $B/obj/harness_embree_shim.o" >> "$CMDS"
 
 echo "compiling $(wc -l < "$CMDS") translation units with $JOBS jobs"
 xargs -P "$JOBS" -I{} bash -c '{} || { echo "FAILED: {}" >&2; exit 255; }' < "$CMDS"
@@ -124,4 +128,11 @@ PATHED_OBJS=$(ls "$B"/obj/pathed_*.o)
 LINK="-fopenmp -Wl,--start-group $B/libembree_all.a -Wl,--end-group -lpthread -ldl"
 g++ -o "$OUT/pathed_ref_headless" "$B/obj/harness_headless_main.o" $PATHED_OBJS $LINK
 g++ -shared -o "$OUT/libpathed_ref_probe.so" "$B/obj/harness_probe_main.o" $PATHED_OBJS $LINK
+if [ -f "$REPO/pathed_b200/libpathed_cuda.so" ]; then
+  g++ -o "$OUT/pathed_ref_cuda" "$B/obj/harness_cuda_main.o" "$B/obj/harness_embree_shim.o" $PATHED_OBJS -fopenmp \
+      -L"$REPO/pathed_b200" -lpathed_cuda -Wl,-rpath,'$ORIGIN/../../pathed_b200' -lpthread -ldl
+  echo "built $OUT/pathed_ref_cuda"
+else
+  echo "pathed_b200/libpathed_cuda.so is not built yet: skipping $OUT/pathed_ref_cuda"
+fi
 echo "built $OUT/pathed_ref_headless and $OUT/libpathed_ref_probe.so"

@@ -11,26 +11,28 @@
 
 namespace pathed {
 
+// tinyexr's float_to_half_full (vendor/tinyexr.h:7164-7199), which SaveEXRImageToFile applies to every HALF channel the reference
+// writes: the mantissa is truncated and then incremented when the highest dropped bit is set (ties go up, not to even), floats with a zero
+// exponent field become signed zeros.  The files of this writer equal the reference's byte for byte (tests/test_gpu_host.py).
 unsigned short floatToHalf(float value)
 {
     uint32_t x; memcpy(&x, &value, 4);
     const uint32_t sign = (x >> 16) & 0x8000u;
-    const int32_t exponent = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
-    uint32_t mantissa = x & 0x7FFFFFu;
-    if (((x >> 23) & 0xFF) == 0xFF) { return (unsigned short)(sign | 0x7C00u | (mantissa ? 0x200u : 0u)); }
+    const uint32_t biased = (x >> 23) & 0xFFu;
+    const uint32_t mantissa = x & 0x7FFFFFu;
+    if (biased == 0) { return (unsigned short)sign; }
+    if (biased == 0xFF) { return (unsigned short)(sign | 0x7C00u | (mantissa ? 0x200u : 0u)); }
+    const int32_t exponent = (int32_t)biased - 127 + 15;
     if (exponent >= 31) { return (unsigned short)(sign | 0x7C00u); }
     if (exponent <= 0) {
-        if (exponent < -10) { return (unsigned short)sign; }
-        mantissa |= 0x800000u;
-        const int shift = 14 - exponent;
-        uint32_t half = mantissa >> shift;
-        const uint32_t rem = mantissa & ((1u << shift) - 1), halfway = 1u << (shift - 1);
-        if (rem > halfway || (rem == halfway && (half & 1))) { half++; }
+        if (14 - exponent > 24) { return (unsigned short)sign; }
+        const uint32_t full = mantissa | 0x800000u;
+        uint32_t half = full >> (14 - exponent);
+        if ((full >> (13 - exponent)) & 1u) { half++; }
         return (unsigned short)(sign | half);
     }
     uint32_t half = ((uint32_t)exponent << 10) | (mantissa >> 13);
-    const uint32_t rem = mantissa & 0x1FFFu;
-    if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) { half++; }
+    if (mantissa & 0x1000u) { half++; } // may carry into the exponent, up to infinity
     return (unsigned short)(sign | half);
 }
 

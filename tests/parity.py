@@ -94,3 +94,21 @@ def check_container_known_answer(api):
     occ, ne, et, em = api.occluded_volumetric(rays, np.array([7.0], np.float32))
     assert occ[0] == 1 and ne[0] == 0                                              # the glass sphere occludes
     assert api.occluded(rays, np.array([6.0], np.float32))[0] == 0               # Scene::testOcclusion skips the container too
+
+
+def half_like_reference(x):
+    """float32 -> float16 the way the reference's EXR writer does it (tinyexr float_to_half_full, vendor/tinyexr.h:7164-7199): truncate the
+    mantissa, add one when the highest dropped bit is set (ties go up), flush float denormals; returned as float32 like read_exr gives"""
+    x = np.ascontiguousarray(x, np.float32)
+    bits = x.view(np.uint32).astype(np.int64)
+    sign = (bits >> 16) & 0x8000
+    biased = (bits >> 23) & 0xFF
+    mant = bits & 0x7FFFFF
+    exp = biased - 127 + 15
+    normal = (exp << 10 | (mant >> 13)) + ((mant >> 12) & 1)
+    full = mant | 0x800000
+    shift = np.clip(14 - exp, 0, 40)
+    under = np.where(shift <= 24, (full >> shift) + ((full >> np.clip(shift - 1, 0, 40)) & 1), 0)
+    half = np.where(exp >= 31, 0x7C00, np.where(exp <= 0, under, normal))
+    half = np.where(biased == 0, 0, np.where(biased == 0xFF, 0x7C00 | np.where(mant != 0, 0x200, 0), half))
+    return (sign | half).astype(np.uint16).view(np.float16).astype(np.float32).reshape(x.shape)

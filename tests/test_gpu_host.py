@@ -7,6 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from parity import half_like_reference
+
 from pathed_b200 import SceneFile, load_scene, read_exr, scene_query
 from pathed_b200._binding import PKG_DIR, REPO_ROOT, rays_array
 
@@ -36,7 +38,7 @@ def test_cli_renders_a_job_like_the_reference_binary(tmp_path):
     ctx = load_scene(job["scene"], job["width"], job["height"])
     assert r.stdout.count("sample: ") == 1  # ONE wave of 8 spp: the checkpoints inside it are snapshots, not wave ends
     for spp in (1, 2, 4, 8):
-        want = (ctx.render(0x5EED, 0, spp, 0, 10) / np.float32(spp))[::-1].astype(np.float16).astype(np.float32)
+        want = half_like_reference((ctx.render(0x5EED, 0, spp, 0, 10) / np.float32(spp))[::-1])
         got = read_exr(os.path.join(out, "auto-%05dspp.exr" % spp))[..., :3]
         assert np.array_equal(got, want), spp  # same Philox streams, same accumulation order: bit-exact after HALF
     assert np.array_equal(read_exr(os.path.join(out, "final.exr")), read_exr(os.path.join(out, "auto.exr")))
@@ -49,7 +51,7 @@ def test_cli_wave_size_and_seed_keys(tmp_path):
     assert a.stdout.count("sample: ") == 6  # one wave per spp, like the reference
     got = read_exr(str(tmp_path / "out" / "final.exr"))[..., :3]
     ctx = load_scene("scenes/cornell.json", 48, 40)
-    want = (ctx.render(7, 0, 6, 0, 10) / np.float32(6))[::-1].astype(np.float16).astype(np.float32)
+    want = half_like_reference((ctx.render(7, 0, 6, 0, 10) / np.float32(6))[::-1])
     assert np.array_equal(got, want)
 
 
@@ -67,7 +69,7 @@ def test_cli_volume_path_tracer_job(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     got = read_exr(str(tmp_path / "out" / "final.exr"))[..., :3]
     ctx = load_scene(job["scene"], job["width"], job["height"], integrator=VOLUME_PATH_TRACER)
-    want = (ctx.render(0x5EED, 0, 4, 0, 10) / np.float32(4))[::-1].astype(np.float16).astype(np.float32)
+    want = half_like_reference((ctx.render(0x5EED, 0, 4, 0, 10) / np.float32(4))[::-1])
     assert np.array_equal(got, want)
     assert want.mean() > 0.01
 
@@ -161,3 +163,35 @@ def test_multi_gpu_job_matches_single_gpu(tmp_path):
     assert one.returncode == 0 and two.returncode == 0, two.stdout
     x = read_exr(str(tmp_path / "a" / "out" / "final.exr")); y = read_exr(str(tmp_path / "b" / "out" / "final.exr"))
     assert np.allclose(x, y, rtol=2e-3, atol=1e-4)  # HALF output of sums that differ in the last fp32 bit
+
+
+REF_CUDA = os.path.join(REPO_ROOT, "oracle", "_ref", "pathed_ref_cuda")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CUDA), reason="oracle/_ref/pathed_ref_cuda is built where /root/reference is mounted (oracle/ref/build_ref.sh)")
+@pytest.mark.parametrize("scene,integrator,width,height", [
+    ("scenes/cornell.json", "PathTracer", 48, 40), ("scenes/cornell-glass.json", "PathTracer", 48, 40), ("scenes/mis-pbrt.json", "PathTracer", 60, 40),
+    ("scenes/teapot.json", "PathTracer", 64, 36), ("scenes/textured.json", "PathTracer", 48, 40), ("scenes/instanced.json", "PathTracer", 48, 36),
+    ("test_scenes/environment_map_sampling.json", "PathTracer", 48, 36), ("scenes/cornell-medium.json", "VolumePathTracer", 40, 40)])
+def test_reference_tree_bound_to_the_cuda_library_renders_the_same_image(tmp_path, scene, integrator, width, height):
+    """INTEGRATION.md as a binary: the UNMODIFIED reference (its Job, scene / OBJ parsers, Image, Integrator::run) linked against the
+    Embree-API shim + libpathed_cuda (oracle/ref/cuda_main.cpp) and the repository's own host layer must feed the same geometry,
+    materials, lights and camera -- the final images are equal bit for bit (same Philox streams), and so are the checkpoint files"""
+    if not os.path.exists(os.path.join(REPO_ROOT, scene)):
+        pytest.skip(scene + " not generated")
+    job, ours = _run_job(tmp_path / "ours", scene=scene, integrator=integrator, width=width, height=height, spp=4, wave_spp=1)
+    assert ours.returncode == 0, ours.stdout + ours.stderr
+    job["output_directory"] = str(tmp_path / "ref" / "out")
+    os.makedirs(str(tmp_path / "ref"), exist_ok=True)
+    path = str(tmp_path / "ref" / "job.json")
+    json.dump(job, open(path, "w"))
+    raw = str(tmp_path / "ref" / "image.f32")
+    r = subprocess.run([REF_CUDA, "--root", REPO_ROOT, path, "--raw", raw], capture_output=True, text=True)
+    assert r.returncode == 0 and "REF_CUDA_RESULT" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    got = np.fromfile(raw, np.float32).reshape(height, width, 3)          # Image::m_raw of the reference's Image, top scanline first
+    ctx = load_scene(scene, width, height, integrator=1 if integrator == "VolumePathTracer" else 0)
+    want = (ctx.render(0x5EED, 0, 4, 0, 10) / np.float32(4))[::-1]         # the repository's host layer + the same library
+    assert want.mean() > 0 and np.array_equal(got, want)
+    for name in ("final.exr", "auto-00004spp.exr"):                         # the reference's tinyexr writer against this repository's
+        a = read_exr(str(tmp_path / "ref" / "out" / name)); b = read_exr(str(tmp_path / "ours" / "out" / name))
+        assert np.array_equal(a, b), name

@@ -7,6 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from parity import half_like_reference
+
 from pathed_b200 import PathedError, bounce_controller, image_save, job_describe, read_exr
 from pathed_b200._binding import PKG_DIR, REPO_ROOT
 
@@ -71,7 +73,7 @@ def test_image_layout_exr_and_preview(tmp_path):
     for name in ("auto.exr", "auto-00008spp.exr"):
         exr = read_exr(os.path.join(out, name))
         assert exr.shape == (6, 5, 4)
-        want = rgb[::-1].astype(np.float16).astype(np.float32)  # top scanline first, HALF
+        want = half_like_reference(rgb[::-1])  # top scanline first, HALF as the reference rounds it
         assert np.array_equal(exr[..., :3], want)
     want8 = (np.minimum(np.power(rgb, np.float32(1 / 2.2), dtype=np.float32), 1.0) * 255).astype(np.uint8)
     assert np.abs(preview.astype(int) - want8.astype(int)).max() <= 1
@@ -145,7 +147,7 @@ def test_exr_reader_decodes_every_codec(codec, kind):
     """files written by OpenEXR itself (cv2.imwrite, tests/golden/exr); PIZ is what the reference's test_scenes/1_pixel_test.exr uses"""
     want = np.load(os.path.join(EXR_DIR, "pixels_rgb_f32.npy"))
     if kind == "f16":
-        want = want.astype(np.float16).astype(np.float32)
+        want = half_like_reference(want)
     got = read_exr(os.path.join(EXR_DIR, "%s_%s.exr" % (codec, kind)))
     assert got.shape == want.shape[:2] + (4,)
     assert np.array_equal(got[..., :3], want) and (got[..., 3] == 1).all()
@@ -200,3 +202,18 @@ def test_exr_reader_rejects_malformed_blocks(tmp_path):
         read_exr(path)
     except PathedError:
         pass
+
+
+def test_exr_half_rounding_is_the_reference_writers(tmp_path):
+    """the reference writes HALF through tinyexr's float_to_half_full (vendor/tinyexr.h:7164-7199): ties round UP (1 + 2^-11 -> 1 + 2^-10,
+    where round-to-nearest-even gives 1), float denormals flush to zero, the carry may run into the exponent"""
+    rgb = np.zeros((4, 8, 3), np.float32)
+    special = [1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 2.0 - 2.0 ** -11, 65519.0, 65520.0, 1e-40, 6e-8, 3e-8, 5.96e-8, 6.1e-5, 0.1, 0.3333333, 1e6, 2.0 ** -14 * (1 + 2.0 ** -11)]
+    flat = rgb.reshape(-1)
+    flat[:len(special)] = special
+    flat[len(special):] = np.random.default_rng(3).random(flat.size - len(special), np.float32) * 4
+    image_save(str(tmp_path) + "/", "tie", rgb, 1)
+    got = read_exr(str(tmp_path / "tie.exr"))[..., :3][::-1]
+    assert np.array_equal(got, half_like_reference(rgb))
+    assert got.reshape(-1)[0] == np.float32(1.0 + 2.0 ** -10) and np.float32(special[0]).astype(np.float16) == np.float16(1.0)
+    assert got.reshape(-1)[2] == 2.0 and np.isinf(got.reshape(-1)[4]) and got.reshape(-1)[5] == 0.0
