@@ -400,6 +400,9 @@ def main():
         stages = {"volume_kernel_ms": tst.shade_ms, "other_ms": tst.other_ms, "grays_per_s": n_rays / max(tst.shade_ms, 1e-9) * 1e-6}
     elif rank == 0:
         peak, peak_note = measured_peak()
+        # per-stage times are taken with the stages one after the other (in the timed region above the shadow rays of a bounce are traced
+        # on a second stream, concurrently with its extend rays, and the stage times would overlap)
+        ctx.set_option("overlap_shadow", 0)
         ctx.set_option("stage_timing", 1)
         ctx.reset_stats()
         for i in range(args.steps):
@@ -413,6 +416,7 @@ def main():
             ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         cst = ctx.stats()
         ctx.set_option("count_traversal", 0)
+        ctx.set_option("overlap_shadow", 1)
         # algorithmic bytes per extend ray: 32 B ray + 16 B hit record + 80 B per inner node + 48 B per triangle test
         per_ray = 32 + 16 + (80.0 * cst.extend_inner_visits + 48.0 * cst.extend_triangle_tests) / max(cst.closest_rays, 1)
         extend_rays_per_launch = tst.closest_rays / max(tst.extend_launches, 1)

@@ -1075,6 +1075,10 @@ struct ptc_ctx {
     int64_t pathsPerWave = 1 << 26; // 67 M paths x 156 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
                                     // keep 148 SMs busy; measured 648 vs 613 Msamples/s against 2^24 on the dragon workload, 653 with 2^27
     bool stageTiming = false, countTraversal = false;
+    // the shadow rays of a bounce are traced on a second stream, concurrently with the bounce's extend rays: both grids fill the GPU, so
+    // the shadow CTAs become resident as the extend kernel drains -- the tail of one launch is filled with the head of the other
+    bool overlapShadow = true;
+    cudaStream_t shadowStream = nullptr; cudaEvent_t shadeDone = nullptr, shadowDone = nullptr;
     int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
     float bvhBuildMs = 0.f; uint32_t bvhPlocIterations = 0;
     uint64_t samples = 0, launches = 0;
@@ -1155,6 +1159,8 @@ int ptc_create(int device, ptc_ctx **out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { ctx->numSMs = prop.multiProcessorCount; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->shadowStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->shadeDone, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->shadowDone, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess ||
         cudaMalloc((void **)&ctx->counters, CNT_STRIDE * sizeof(BounceCounters)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->totals, 6 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -1193,6 +1199,9 @@ void ptc_destroy(ptc_ctx *ctx)
     if (ctx->framebufferReady) { cudaEventDestroy(ctx->framebufferReady); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
+    if (ctx->shadowStream) { cudaStreamDestroy(ctx->shadowStream); }
+    if (ctx->shadeDone) { cudaEventDestroy(ctx->shadeDone); }
+    if (ctx->shadowDone) { cudaEventDestroy(ctx->shadowDone); }
     if (ctx->evStart) { cudaEventDestroy(ctx->evStart); }
     if (ctx->evStop) { cudaEventDestroy(ctx->evStop); }
     collectTimings(ctx);
@@ -1860,6 +1869,13 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
     // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
     for (int k = 0; k <= wp.lastBounce; k++) {
         BounceCounters *bc = cnt + k;
+        // shadow rays cast at vertex k (queued by material(k - 1)) go to the second stream, behind everything enqueued so far
+        const bool overlap = ctx->overlapShadow && k > 0;
+        cudaStream_t shadowOn = overlap ? ctx->shadowStream : stream;
+        if (overlap) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->shadeDone, stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->shadowStream, ctx->shadeDone, 0));
+        }
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
             // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
@@ -1868,11 +1884,15 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
             else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
         }
         if (k > 0) {
-            StageTimer t(ctx, stream, STAGE_SHADOW);
-            if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            StageTimer t(ctx, shadowOn, STAGE_SHADOW);
+            if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+        }
+        if (overlap) { // the logic stage reads the occlusion bytes
+            CUDA_TRY(ctx, cudaEventRecord(ctx->shadowDone, ctx->shadowStream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->shadowDone, 0));
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
@@ -2397,6 +2417,7 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
         ctx->pathsPerWave = value; return PTC_OK;
     }
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
+    if (!strcmp(name, "overlap_shadow")) { ctx->overlapShadow = value != 0; return PTC_OK; }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
     if (!strcmp(name, "bvh_builder")) { // before ptc_commit; 1 = device (default), 0 = host binned SAH
         if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "bvh_builder must be set before ptc_commit"); }
