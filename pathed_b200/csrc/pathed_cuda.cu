@@ -232,6 +232,9 @@ __device__ __forceinline__ void flushCounters(const TraverseCounters &c, unsigne
 #ifndef PTC_TRI_ROUNDS
 #define PTC_TRI_ROUNDS 2 /* sweep on the dragon workload: 1000 (while-while) 560, 1: 602, 2: 607, 3: 590 Msamples/s */
 #endif
+#ifndef PTC_TRI_ROUNDS_ANY
+#define PTC_TRI_ROUNDS_ANY 1 /* shadow rays stop at the first hit: one round per node phase measured 47.6 against 49.2 ms per 4 steps */
+#endif
 template <bool ANY>
 __device__ __forceinline__ bool coopTriangles(const BvhView &bvh, TraversalState &st, bool eligible, uint8_t *ownerOf)
 {
@@ -358,7 +361,7 @@ __global__ void PTC_TRAVERSE_BOUNDS traverseKernel(DScene scene, PathBuffers pb,
             bool done = false; // this ray needs no further BVH work
             if (PTC_COOP_TRI && !COUNT && !FILTER && !INSTANCES) { done = coopTriangles<ANY>(scene.bvh, st, busy, ownerOf); }
             else {
-                for (int round = 0; round < PTC_TRI_ROUNDS; round++) { // triangle rounds, warp-uniform control flow
+                for (int round = 0; round < (ANY ? PTC_TRI_ROUNDS_ANY : PTC_TRI_ROUNDS); round++) { // triangle rounds, warp-uniform control flow
                     bool pending = busy && !done && st.tgroup.y != 0u;
                     const uint32_t want = __ballot_sync(0xFFFFFFFFu, pending);
                     if (want == 0u) { break; }
