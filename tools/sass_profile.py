@@ -19,8 +19,13 @@ def main():
             kernels[-1][1] = r
         elif kernels and kernels[-1][1] and len(r) == len(kernels[-1][1]):
             kernels[-1][2].append(r)
+    seen = set()
     for name, hdr, data in kernels:
         ix = {h: i for i, h in enumerate(hdr)}
+        key = (name, len(data), sum(float(r[ix["Instructions Executed"]] or 0) for r in data))
+        if key in seen:  # ncu prints every launch twice (SASS view of the source page and of the PTX page)
+            continue
+        seen.add(key)
         f = lambda r, k: float(r[ix[k]] or 0)
         ti = sum(f(r, "Instructions Executed") for r in data)
         tt = sum(f(r, "Thread Instructions Executed") for r in data)
