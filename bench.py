@@ -18,7 +18,7 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
             `traffic` = DRAM bytes per launch of the same kernel from the ncu capture of THIS build (profiles/traffic.json carries
             the hash of the CUDA sources it was taken from; a capture of another build is reported as null, never scaled)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
-L2: every wave streams its path state (67.1 M paths x 156 B = 10.5 GB incl. queues) through each stage, far more than the
+L2: every wave streams its path state (67.1 M paths x 237 B = 15.9 GB incl. queues) through each stage, far more than the
 126 MB L2, so no stage finds its inputs cached from the previous one; the BVH itself (~55 MB) is meant to be L2-resident.
 
 Multi-GPU (torchrun, one rank per GPU): samples-per-pixel are split across ranks (each rank renders its own sample
@@ -50,6 +50,8 @@ WORKLOADS = {
     # participating medium in a Passthrough container, VolumePathTracer (one-thread-per-path kernel)
     "cornell-medium": dict(scene="scenes/cornell-medium.json", width=512, height=512, last_bounce=10, integrator="VolumePathTracer"),
 }
+PATH_STATE_BYTES = 237  # per path: 5 x 32 B records (ray and modulation|throughput, current + next; NEE), 4 x 16 B (hit, result x 2, out), 1 B occlusion,
+                        # 4 B shadow queue, 4 B per material class queue (2 classes in the dragon scene)
 SPP_PER_STEP = 64  # one wave of 2^26 paths at 1024^2: the late bounces' queues stay long enough to fill 148 SMs (profiles/README.md)
 REF_SPP_PER_STEP = 1  # the CPU reference does ~0.5 Msamples/s: one spp of 1024^2 is ~2 s
 STRONG_JOB_SPP = {"dragon": 256, "teapot": 1024}  # --scaling strong: one step = the whole job BASELINE.json names for the scene
@@ -143,7 +145,7 @@ def workload_config(args, world):
         parallelism = "single GPU"
     return {"workload": "%s %dx%d %s lastBounce %d" % (w["scene"], w["width"], w["height"], w.get("integrator", "PathTracer"), w["last_bounce"]),
             "spp_per_step": step_spp(args, world), "spp_per_rank_and_step": spp_rank, "scaling": args.scaling, "parallelism": parallelism,
-            "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d wave(s) per step" % (min(n_pix * spp_rank, ppw) * 156 / 1e6, waves)}
+            "l2": "inputs larger than L2: %.0f MB of path state streamed per wave, %d wave(s) per step" % (min(n_pix * spp_rank, ppw) * PATH_STATE_BYTES / 1e6, waves)}
 
 
 def rank_spp(args, world):

@@ -68,15 +68,23 @@ Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first) : m_
         ptc_destroy(ctx); m_contexts.clear();
         throw std::runtime_error("scene upload failed: " + message);
     }
-    for (int device = 1; device < std::max(1, gpus); device++) {
-        ptc_ctx *copy = nullptr;
-        if (ptc_replicate(ctx, device, &copy) != PTC_OK || !copy) {
+    // one thread per further device: creating a CUDA context takes a few hundred milliseconds, the copies run over NVLink side by side
+    const int devices = std::max(1, gpus);
+    std::vector<ptc_ctx *> copies((size_t)devices, nullptr);
+    std::vector<int> status((size_t)devices, PTC_OK);
+    std::vector<std::thread> workers;
+    for (int device = 1; device < devices; device++) {
+        workers.emplace_back([&, device]() { status[(size_t)device] = ptc_replicate(ctx, device, &copies[(size_t)device]); });
+    }
+    for (std::thread &worker : workers) { worker.join(); }
+    for (int device = 1; device < devices; device++) {
+        if (status[(size_t)device] != PTC_OK || !copies[(size_t)device]) {
             const std::string message = ptc_last_error(ctx);
-            for (ptc_ctx *c : m_contexts) { ptc_destroy(c); }
-            m_contexts.clear();
+            for (ptc_ctx *c : copies) { if (c) { ptc_destroy(c); } }
+            ptc_destroy(ctx); m_contexts.clear();
             throw std::runtime_error("Failed to replicate the scene to device " + std::to_string(device) + ": " + message);
         }
-        m_contexts.push_back(copy);
+        m_contexts.push_back(copies[(size_t)device]);
     }
 }
 
