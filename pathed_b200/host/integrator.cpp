@@ -71,14 +71,14 @@ Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first) : m_
     // one thread per further device: creating a CUDA context takes a few hundred milliseconds, the copies run over NVLink side by side
     const int devices = std::max(1, gpus);
     std::vector<ptc_ctx *> copies((size_t)devices, nullptr);
-    std::vector<int> status((size_t)devices, PTC_OK);
+    std::vector<int> outcome((size_t)devices, PTC_OK);
     std::vector<std::thread> workers;
     for (int device = 1; device < devices; device++) {
-        workers.emplace_back([&, device]() { status[(size_t)device] = ptc_replicate(ctx, device, &copies[(size_t)device]); });
+        workers.emplace_back([&, device]() { outcome[(size_t)device] = ptc_replicate(ctx, device, &copies[(size_t)device]); });
     }
     for (std::thread &worker : workers) { worker.join(); }
     for (int device = 1; device < devices; device++) {
-        if (status[(size_t)device] != PTC_OK || !copies[(size_t)device]) {
+        if (outcome[(size_t)device] != PTC_OK || !copies[(size_t)device]) {
             const std::string message = ptc_last_error(ctx);
             for (ptc_ctx *c : copies) { if (c) { ptc_destroy(c); } }
             ptc_destroy(ctx); m_contexts.clear();
