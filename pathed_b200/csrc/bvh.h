@@ -57,7 +57,10 @@ struct DeviceWideBVH {
     uint32_t nNodes = 0, nTriangles = 0, maxDepth = 0, plocIterations = 0;
     float buildMs[4] = {0, 0, 0, 0}; // boxes + sort, clustering, emission, total (host clock around synchronised phases)
 };
-void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t nPrims, cudaStream_t stream, DeviceWideBVH &out);
+// workspaceOut (optional): the build's working set (one allocation, ~480 B per primitive) is handed to the caller instead of being
+// released -- cudaFree of a few hundred MB that kernels have just written was measured at 37 ms, five times the build itself; the
+// caller frees it when nothing waits for it (ptc_destroy).
+void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t nPrims, cudaStream_t stream, DeviceWideBVH &out, void **workspaceOut = nullptr);
 // The device builder's per-element code run serially on the host (ptc_bvh_selfcheck_builder: CPU tests of the algorithm).
 // Never used by ptc_commit.
 void buildWideBVHEmulated(const float *positions4, const uint32_t *indices4, uint32_t nPrims, WideBVH &out);

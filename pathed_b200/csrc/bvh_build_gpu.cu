@@ -554,21 +554,41 @@ struct DeviceExec {
     {
         if (e != cudaSuccess) { throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e)); }
     }
+    // The working set (436 B per primitive in ~25 arrays) comes out of ONE allocation: every cudaMalloc / cudaFree is a driver call
+    // of 0.1-0.5 ms that synchronises the device, which cost as much as the sort.  Requests that do not fit fall back to cudaMalloc.
+    char *arena = nullptr; size_t arenaBytes = 0, arenaUsed = 0;
+    void reserve(size_t bytes)
+    {
+        if (arena || cudaMalloc((void **)&arena, bytes) != cudaSuccess) { cudaGetLastError(); return; }
+        arenaBytes = bytes; arenaUsed = 0;
+    }
     template <class T> T *alloc(size_t n)
     {
+        const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255u) & ~(size_t)255u;
+        if (arena && arenaUsed + bytes <= arenaBytes) { void *p = arena + arenaUsed; arenaUsed += bytes; return (T *)p; }
         void *p = nullptr;
-        check(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)), "cudaMalloc (BVH build)");
+        check(cudaMalloc(&p, bytes), "cudaMalloc (BVH build)");
         owned.push_back(p);
         return (T *)p;
     }
-    void releaseAll() { for (void *p : owned) { cudaFree(p); } owned.clear(); if (scratch) { cudaFree(scratch); scratch = nullptr; } }
+    void releaseAll()
+    {
+        for (void *p : owned) { cudaFree(p); }
+        owned.clear();
+        if (scratch) { cudaFree(scratch); scratch = nullptr; }
+        if (arena) { cudaFree(arena); arena = nullptr; arenaBytes = arenaUsed = 0; }
+    }
     void needScratch(size_t bytes)
     {
         if (bytes <= scratchBytes) { return; }
+        const size_t rounded = (bytes + 255u) & ~(size_t)255u;
+        if (arena && arenaUsed + rounded <= arenaBytes) { scratchFromArena = true; scratchPtr = arena + arenaUsed; arenaUsed += rounded; scratchBytes = bytes; return; }
         if (scratch) { cudaFree(scratch); }
         check(cudaMalloc(&scratch, bytes), "cudaMalloc (scan scratch)");
+        scratchPtr = scratch; scratchFromArena = false;
         scratchBytes = bytes;
     }
+    void *scratchPtr = nullptr; bool scratchFromArena = false;
     template <class Op> void forEach(uint32_t n, const Op &op)
     {
         if (!n) { return; }
@@ -592,7 +612,7 @@ struct DeviceExec {
         size_t bytes = 0;
         check(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, values, (int)a.nPrims, 0, 63, stream), "radix sort size");
         needScratch(bytes);
-        check(cub::DeviceRadixSort::SortPairs(scratch, bytes, keys, values, (int)a.nPrims, 0, 63, stream), "radix sort");
+        check(cub::DeviceRadixSort::SortPairs(scratchPtr, bytes, keys, values, (int)a.nPrims, 0, 63, stream), "radix sort");
         return values.selector;
     }
     // exclusive sum of packed counters; returns the total (sum of all n inputs)
@@ -601,7 +621,7 @@ struct DeviceExec {
         size_t bytes = 0;
         check(cub::DeviceScan::ExclusiveSum(nullptr, bytes, a.scanIn, a.scanOut, (int)n, stream), "scan size");
         needScratch(bytes);
-        check(cub::DeviceScan::ExclusiveSum(scratch, bytes, a.scanIn, a.scanOut, (int)n, stream), "scan");
+        check(cub::DeviceScan::ExclusiveSum(scratchPtr, bytes, a.scanIn, a.scanOut, (int)n, stream), "scan");
         uint64_t tail[2];
         check(cudaMemcpyAsync(&tail[0], a.scanIn + (n - 1), 8, cudaMemcpyDeviceToHost, stream), "scan tail");
         check(cudaMemcpyAsync(&tail[1], a.scanOut + (n - 1), 8, cudaMemcpyDeviceToHost, stream), "scan tail");
@@ -745,20 +765,29 @@ BuildResult runBuild(Exec &exec, BuildArrays &a)
 } // namespace
 
 // ---- public entry points ---------------------------------------------------------------------------------------------
-void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t nPrims, cudaStream_t stream, DeviceWideBVH &out)
+void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t nPrims, cudaStream_t stream, DeviceWideBVH &out, void **workspaceOut)
 {
+    if (workspaceOut) { *workspaceOut = nullptr; }
     out = DeviceWideBVH();
     if (nPrims == 0) { return; }
     DeviceExec exec; exec.stream = stream;
+    const bool timing = getenv("PTC_BUILD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto msBetween = [](auto x, auto y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+    const auto c0 = now();
+    exec.reserve((size_t)nPrims * 480u + (8u << 20)); // 436 B per primitive + radix-sort scratch (~24 B per primitive) + alignment
+    const auto c1 = now();
     BuildArrays a;
     memset(&a, 0, sizeof(a));
     a.positions = dPositions; a.prims = dPrims; a.nPrims = nPrims;
     try {
         const BuildResult r = runBuild(exec, a);
-        // exact-size copies of the result; the build's working set (about 300 B per primitive) is released
+        const auto c2 = now();
+        // exact-size copies of the result; the build's working set (about 440 B per primitive) is released
         float4 *nodes = nullptr, *tris = nullptr;
         DeviceExec::check(cudaMalloc((void **)&nodes, (size_t)r.nNodes * sizeof(WideNode)), "cudaMalloc (BVH nodes)");
         if (cudaMalloc((void **)&tris, (size_t)r.nTriangles * sizeof(LeafTriangle)) != cudaSuccess) { cudaFree(nodes); throw std::runtime_error("cudaMalloc (BVH triangles)"); }
+        const auto c2b = now();
         cudaMemcpyAsync(nodes, a.wideNodes, (size_t)r.nNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(tris, a.leafTriangles, (size_t)r.nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToDevice, stream);
         const cudaError_t e = cudaStreamSynchronize(stream);
@@ -766,11 +795,17 @@ void buildWideBVHDevice(const float4 *dPositions, const uint4 *dPrims, uint32_t 
         out.nodes = nodes; out.triangles = tris; out.nNodes = r.nNodes; out.nTriangles = r.nTriangles; out.maxDepth = r.maxDepth;
         out.plocIterations = r.plocIterations;
         for (int k = 0; k < 4; k++) { out.buildMs[k] = (float)r.ms[k]; }
+        const auto c3 = now();
+        if (workspaceOut && exec.arena) { *workspaceOut = exec.arena; exec.arena = nullptr; }
+        exec.releaseAll();
+        if (timing) {
+            fprintf(stderr, "buildWideBVHDevice: reserve %.2f ms, build %.2f ms, exact-size allocations %.2f ms + copies %.2f ms, release %.2f ms\n", msBetween(c0, c1),
+                    msBetween(c1, c2), msBetween(c2, c2b), msBetween(c2b, c3), msBetween(c3, now()));
+        }
     } catch (...) {
         exec.releaseAll();
         throw;
     }
-    exec.releaseAll();
 }
 
 void buildWideBVHEmulated(const float *positions4, const uint32_t *indices4, uint32_t nPrims, WideBVH &out)

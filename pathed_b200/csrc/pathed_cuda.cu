@@ -111,7 +111,10 @@ struct BounceCounters {
     uint32_t extendCount, shadowCount;           // rays leaving vertex k / NEE shadow rays cast at vertex k
     uint32_t classCount[PTC_MATERIAL_CLASSES];   // survivors of logic(k) per material class
     uint32_t extendCursor, shadowCursor;         // work cursors of the two traversal launches (lane refill)
-    uint32_t pad[21];
+    // VolumePathTracer wavefront (volume_wavefront.cuh): paths in the slot list of bounce k (there extendCount is the length of the
+    // merged-ray queue, a subset of the slots), scatter-point shadow rays and their cursor
+    uint32_t slotCount, scatterCount, scatterCursor;
+    uint32_t pad[18];
 };
 static_assert(sizeof(BounceCounters) == 128, "one cache line per bounce");
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
@@ -688,6 +691,8 @@ __global__ void __launch_bounds__(128, PTC_VOLUME_MIN_BLOCKS) volumePathKernel(c
     }
 }
 
+#include "volume_wavefront.cuh"
+
 __global__ void resolveKernel(const float *accum, float *out, uint32_t n, uint32_t spp) // src/integrator.cpp:74-85
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = accum[i] / (int)spp; }
@@ -735,7 +740,7 @@ __global__ void tallyKernel(const BounceCounters *counters, unsigned long long *
 {
     if (threadIdx.x == 0) {
         unsigned long long closest = 0, shadow = 0;
-        for (int b = 0; b < CNT_STRIDE; b++) { closest += counters[b].extendCount; shadow += counters[b].shadowCount; }
+        for (int b = 0; b < CNT_STRIDE; b++) { closest += counters[b].extendCount; shadow += counters[b].shadowCount + counters[b].scatterCount; }
         totals[0] += closest; totals[1] += shadow;
     }
 }
@@ -1049,6 +1054,10 @@ struct ptc_ctx {
     int integrator = PTC_INTEGRATOR_PATH_TRACER;
     float4 *volumeOut = nullptr; uint32_t volumeCapacity = 0; uint32_t *volumeCursor = nullptr;
     int gridVolume = 0;
+    // VolumePathTracer as wavefront stages (volume_wavefront.cuh); volumeMegakernel = 1 keeps the one-thread-per-path kernel
+    bool volumeMegakernel = false;
+    VolumeBuffers volumeBuffers = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; uint32_t volumeBufferCapacity = 0; std::vector<void *> volumeAllocations;
+    int gridVolumeTraverse = 0, gridVolumeLogic = 0, gridVolumeShade = 0;
     bool hasEnv = false, hasCamera = false;
     std::vector<float> envRgba; int envW = 0, envH = 0; float envScale = 1.f; float envM2W[16], envW2M[16];
     float camToWorld[12]; float vfov = 0.f; int width = 0, height = 0;
@@ -1070,6 +1079,10 @@ struct ptc_ctx {
     std::vector<Gather> gathers;                         // results of ptc_framebuffer_gather_begin in flight
     cudaEvent_t gatherRead = nullptr;                    // the last gather kernel of this (root) context finished reading the framebuffers
     float *pinned = nullptr; size_t pinnedSize = 0;
+    // ptc_render: the caller's radianceLookup is uploaded on its own stream while the wave's kernels run; only the first
+    // accumulation waits for it (beforeAccumulate is called once, after the wave's other launches have been issued)
+    cudaStream_t copyStream = nullptr; cudaEvent_t uploadDone = nullptr;
+    std::function<int()> beforeAccumulate;
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int numSMs = 148;
@@ -1084,6 +1097,10 @@ struct ptc_ctx {
     cudaStream_t shadowStream = nullptr; cudaEvent_t shadeDone = nullptr, shadowDone = nullptr;
     int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
     float bvhBuildMs = 0.f; uint32_t bvhPlocIterations = 0;
+    // the device builder leaves nodes and leaf triangles in HBM; the host copy (only ptc_count_traversal walks it) is fetched on demand
+    uint32_t bvhNodeCount = 0, bvhTriangleCount = 0;
+    bool hostBvhFetched = true;
+    void *buildWorkspace = nullptr; // the device builder's working set, released with the context (bvh.h: buildWideBVHDevice)
     uint64_t samples = 0, launches = 0;
     float lastRenderMs = 0.f;
     // stage timing: CUDA events on the launching stream around every launch, summed per kernel class
@@ -1163,6 +1180,7 @@ int ptc_create(int device, ptc_ctx **out)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { ctx->numSMs = prop.multiProcessorCount; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->shadowStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->uploadDone, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->shadeDone, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->shadowDone, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess ||
         cudaMalloc((void **)&ctx->counters, CNT_STRIDE * sizeof(BounceCounters)) != cudaSuccess ||
@@ -1180,6 +1198,12 @@ int ptc_create(int device, ptc_ctx **out)
     ctx->gridShade = ctx->numSMs * std::max(perSM, 1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumePathKernel<false>, 128, 0);
     ctx->gridVolume = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (volumeTraverseKernel<VOL_EXTEND, false>), 128, 0);
+    ctx->gridVolumeTraverse = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumeLogicKernel, 256, 0);
+    ctx->gridVolumeLogic = ctx->numSMs * std::max(perSM, 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumeMaterialKernel<PTC_PLASTIC>, 128, 0);
+    ctx->gridVolumeShade = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
     *out = ctx;
     return PTC_OK;
@@ -1199,10 +1223,14 @@ void ptc_destroy(ptc_ctx *ctx)
     for (auto &g : ctx->gathers) { cudaFree(g.device); if (g.pinned) { cudaFreeHost(g.pinned); } if (g.done) { cudaEventDestroy(g.done); } }
     if (ctx->gatherRead) { cudaEventDestroy(ctx->gatherRead); }
     cudaFree(ctx->volumeOut); cudaFree(ctx->volumeCursor);
+    for (void *p : ctx->volumeAllocations) { cudaFree(p); }
+    cudaFree(ctx->buildWorkspace);
     if (ctx->framebufferReady) { cudaEventDestroy(ctx->framebufferReady); }
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); }
     if (ctx->stream) { cudaStreamDestroy(ctx->stream); }
     if (ctx->shadowStream) { cudaStreamDestroy(ctx->shadowStream); }
+    if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); }
+    if (ctx->uploadDone) { cudaEventDestroy(ctx->uploadDone); }
     if (ctx->shadeDone) { cudaEventDestroy(ctx->shadeDone); }
     if (ctx->shadowDone) { cudaEventDestroy(ctx->shadowDone); }
     if (ctx->evStart) { cudaEventDestroy(ctx->evStart); }
@@ -1545,35 +1573,35 @@ int ptc_commit(ptc_ctx *ctx)
         try {
             if (ctx->bvhBuilder == 1) {
                 DeviceWideBVH built;
-                buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built);
+                if (ctx->buildWorkspace) { cudaFree(ctx->buildWorkspace); ctx->buildWorkspace = nullptr; }
+                buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built, &ctx->buildWorkspace);
                 if (built.nodes) { A.push_back(built.nodes); ctx->allocationBytes.push_back((size_t)built.nNodes * sizeof(WideNode)); }
                 if (built.triangles) { A.push_back(built.triangles); ctx->allocationBytes.push_back((size_t)built.nTriangles * sizeof(LeafTriangle)); }
                 s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
                 ctx->bvhPlocIterations = built.plocIterations;
-                // host copy for the scalar counting traversal (ptc_count_traversal) and the statistics
-                ctx->bvh.nodes.resize(built.nNodes); ctx->bvh.triangles.resize(built.nTriangles); ctx->bvh.maxDepth = built.maxDepth;
-                if (built.nNodes) {
-                    CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.nodes.data(), built.nodes, (size_t)built.nNodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
-                    CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.triangles.data(), built.triangles, (size_t)built.nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
-                }
+                // no host copy here (49 MB through pageable memory cost more than the build): fetchHostBvh brings it when
+                // the scalar counting traversal asks for it
+                ctx->bvh.nodes.clear(); ctx->bvh.triangles.clear(); ctx->bvh.maxDepth = built.maxDepth;
+                ctx->bvhNodeCount = built.nNodes; ctx->bvhTriangleCount = built.nTriangles; ctx->hostBvhFetched = false;
             } else {
                 buildWideBVH(hostBuildPositions.data(), hostBuildPrims.data(), nPrims, ctx->bvh);
                 if ((rc = upload(ctx, (const float4 *)ctx->bvh.nodes.data(), ctx->bvh.nodes.size() * 5, &s.bvh.nodes, A))) { return rc; }
                 if ((rc = upload(ctx, (const float4 *)ctx->bvh.triangles.data(), ctx->bvh.triangles.size() * 3, &s.bvh.triangles, A))) { return rc; }
                 s.bvh.nNodes = (uint32_t)ctx->bvh.nodes.size();
+                ctx->bvhNodeCount = (uint32_t)ctx->bvh.nodes.size(); ctx->bvhTriangleCount = (uint32_t)ctx->bvh.triangles.size(); ctx->hostBvhFetched = true;
             }
         } catch (const std::exception &e) { CTX_FAIL(ctx, PTC_ERR_INVALID, "BVH build failed: %s", e.what()); }
         s.bvh.placements = nullptr;
         ctx->bvh.placements = placements;
-        if (!placements.empty() && !ctx->bvh.triangles.empty()) {
+        if (!placements.empty() && ctx->bvhTriangleCount) {
             const uint32_t *tags = nullptr;
             if ((rc = upload(ctx, flatTag.data(), flatTag.size(), &tags, A))) { return rc; }
             if ((rc = upload(ctx, (const float4 *)placements.data(), placements.size() / 4, &s.bvh.placements, A))) { return rc; }
-            const uint32_t nTriangles = (uint32_t)ctx->bvh.triangles.size();
+            const uint32_t nTriangles = ctx->bvhTriangleCount;
             LeafTriangle *leaves = (LeafTriangle *)s.bvh.triangles;
             localizeLeavesKernel<<<(nTriangles + 255) / 256, 256, 0, ctx->stream>>>(leaves, nTriangles, s.positions, s.prims, tags);
-            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bvh.triangles.data(), leaves, (size_t)nTriangles * sizeof(LeafTriangle), cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->bvh.nodes.clear(); ctx->bvh.triangles.clear(); ctx->hostBvhFetched = false; // the leaves changed on the device
         }
         ctx->bvhBuildMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - buildStart).count();
     }
@@ -1773,8 +1801,11 @@ int ptc_replicate(ptc_ctx *src, int device, ptc_ctx **out)
     dst->envW = src->envW; dst->envH = src->envH; dst->envScale = src->envScale;
     memcpy(dst->envM2W, src->envM2W, sizeof(dst->envM2W)); memcpy(dst->envW2M, src->envW2M, sizeof(dst->envW2M));
     memcpy(dst->camToWorld, src->camToWorld, sizeof(dst->camToWorld)); dst->vfov = src->vfov; dst->width = src->width; dst->height = src->height;
-    dst->bvh = src->bvh; dst->nLights = src->nLights; dst->classMask = src->classMask;
-    dst->pathsPerWave = src->pathsPerWave; dst->stageTiming = src->stageTiming; dst->countTraversal = src->countTraversal;
+    dst->bvh.placements = src->bvh.placements; dst->bvh.maxDepth = src->bvh.maxDepth; // nodes / triangles: fetchHostBvh, from this GPU's copy
+    memcpy(dst->bvh.sceneLo, src->bvh.sceneLo, sizeof(dst->bvh.sceneLo)); memcpy(dst->bvh.sceneHi, src->bvh.sceneHi, sizeof(dst->bvh.sceneHi));
+    dst->bvhNodeCount = src->bvhNodeCount; dst->bvhTriangleCount = src->bvhTriangleCount; dst->hostBvhFetched = false;
+    dst->nLights = src->nLights; dst->classMask = src->classMask;
+    dst->pathsPerWave = src->pathsPerWave; dst->stageTiming = src->stageTiming; dst->countTraversal = src->countTraversal; dst->volumeMegakernel = src->volumeMegakernel;
     dst->bvhBuilder = src->bvhBuilder; dst->bvhBuildMs = 0.f; dst->bvhPlocIterations = src->bvhPlocIterations;
     dst->deviceMaterials = src->deviceMaterials;
     dst->scene = src->scene;
@@ -1854,6 +1885,15 @@ static CheckpointPlan planFor(const Checkpoints &cp, uint32_t F, uint32_t S, boo
     return plan;
 }
 
+// ptc_render: the upload of the caller's sums, issued behind the launches of the first wave (ptc_ctx::beforeAccumulate)
+static int runBeforeAccumulate(ptc_ctx *ctx)
+{
+    if (!ctx->beforeAccumulate) { return PTC_OK; }
+    const std::function<int()> f = ctx->beforeAccumulate;
+    ctx->beforeAccumulate = nullptr;
+    return f();
+}
+
 // one wave = fixed launch sequence; all queue sizes stay on the device
 static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream, const CheckpointPlan &plan)
 {
@@ -1914,6 +1954,98 @@ static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cu
         // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
         std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
     }
+    { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
+    {
+        StageTimer t(ctx, stream, STAGE_OTHER);
+        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
+        tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+    }
+    ctx->launches += 2;
+    if (ctx->pending.size() > 4096) { collectTimings(ctx); }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return PTC_OK;
+}
+
+// VolumePathTracer, wavefront form (volume_wavefront.cuh): the launch sequence of one wave
+static int ensureVolumeBuffers(ptc_ctx *ctx, uint32_t capacity)
+{
+    if (capacity <= ctx->volumeBufferCapacity) { return PTC_OK; }
+    for (void *p : ctx->volumeAllocations) { cudaFree(p); }
+    ctx->volumeAllocations.clear(); ctx->volumeBufferCapacity = 0;
+    VolumeBuffers &vb = ctx->volumeBuffers;
+    struct { void **slot; size_t bytesPerPath; } arrays[] = {
+        {(void **)&vb.probeHit, 16}, {(void **)&vb.shadowTr, 16}, {(void **)&vb.scatter, 48}, {(void **)&vb.scatterTr, 16}, {(void **)&vb.extendQueue, 4}, {(void **)&vb.scatterQueue, 4}};
+    for (auto &a : arrays) {
+        CUDA_TRY(ctx, cudaMalloc(a.slot, (size_t)capacity * a.bytesPerPath));
+        ctx->volumeAllocations.push_back(*a.slot);
+    }
+    ctx->volumeBufferCapacity = capacity;
+    return PTC_OK;
+}
+
+#define LAUNCH_VOLUME_MATERIAL(TYPE) \
+    if (ctx->classMask & (1u << TYPE)) { volumeMaterialKernel<TYPE><<<ctx->gridVolumeShade, 128, 0, stream>>>(s, pb, vb, wp, bc, bc + 1); ctx->launches++; }
+
+static int launchVolumeWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream, const CheckpointPlan &plan)
+{
+    const DScene &s = ctx->scene;
+    PathBuffers pb = ctx->paths;
+    const VolumeBuffers &vb = ctx->volumeBuffers;
+    BounceCounters *cnt = ctx->counters;
+    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(BounceCounters), stream));
+    const uint32_t nPaths = wp.nPixels * wp.sppWave;
+    unsigned long long *work = ctx->totals + 2;
+    const bool count = ctx->countTraversal;
+    {
+        StageTimer t(ctx, stream, STAGE_OTHER);
+        generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    }
+    ctx->launches++;
+    for (int k = 0; k <= wp.lastBounce; k++) {
+        BounceCounters *bc = cnt + k;
+        {
+            StageTimer t(ctx, stream, STAGE_EXTEND);
+            if (k == 0) { // camera rays: Scene::testIntersect, every slot
+                if (count) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            } else if (s.hasFilter) { // probe + continuation ray in one traversal
+                if (count) { volumeTraverseKernel<VOL_EXTEND, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                else { volumeTraverseKernel<VOL_EXTEND, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+            } else {                  // no container surface: the two rules coincide
+                if (count) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+            }
+        }
+        ctx->launches++;
+        if (k > 0) {
+            StageTimer t(ctx, stream, STAGE_SHADOW);
+            if (count) {
+                volumeTraverseKernel<VOL_SHADOW, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+            } else {
+                volumeTraverseKernel<VOL_SHADOW, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+            }
+            ctx->launches += s.nMedia ? 2 : 1;
+        }
+        {
+            StageTimer t(ctx, stream, STAGE_SHADE);
+            if (k == 0) { // SampleIntegrator::samplePixel's own terms, as in the PathTracer wavefront
+                logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, 0);
+                if (s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
+            } else { volumeLogicKernel<<<ctx->gridVolumeLogic, 256, 0, stream>>>(s, pb, vb, wp, bc, ctx->classMask); }
+            ctx->launches++;
+            LAUNCH_VOLUME_MATERIAL(PTC_LAMBERTIAN)
+            LAUNCH_VOLUME_MATERIAL(PTC_OREN_NAYAR)
+            LAUNCH_VOLUME_MATERIAL(PTC_MIRROR)
+            LAUNCH_VOLUME_MATERIAL(PTC_GLASS)
+            LAUNCH_VOLUME_MATERIAL(PTC_MICROFACET)
+            LAUNCH_VOLUME_MATERIAL(PTC_PLASTIC)
+            LAUNCH_VOLUME_MATERIAL(PTC_PASSTHROUGH)
+        }
+        std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
+    }
+    { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
     {
         StageTimer t(ctx, stream, STAGE_OTHER);
         accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
@@ -1949,6 +2081,7 @@ static int renderVolume(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint3
             if (ctx->countTraversal) { volumePathKernel<true><<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals); }
             else { volumePathKernel<false><<<ctx->gridVolume, 128, 0, stream>>>(s, ctx->volumeOut, wp, ctx->volumeCursor, ctx->totals); }
         }
+        { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
         {
             StageTimer t(ctx, stream, STAGE_OTHER);
             const CheckpointPlan plan = planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp);
@@ -1970,13 +2103,20 @@ static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uin
     const uint32_t nPixels = (uint32_t)ctx->scene.width * (uint32_t)ctx->scene.height;
     uint32_t sppWave = (uint32_t)std::max<int64_t>(1, ctx->pathsPerWave / (int64_t)nPixels);
     sppWave = std::min(sppWave, std::max(nSpp, 1u));
-    if (ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER) { return renderVolume(ctx, seed, firstSample, nSpp, sppWave, start, last, accumDevice, stream, checkpoints); }
+    const bool volume = ctx->integrator == PTC_INTEGRATOR_VOLUME_PATH_TRACER;
+    // the one-thread-per-path kernel stays for instanced scenes (the volume traversal kernels test world-space leaves only) and as an option
+    if (volume && (ctx->volumeMegakernel || ctx->scene.bvh.placements)) { return renderVolume(ctx, seed, firstSample, nSpp, sppWave, start, last, accumDevice, stream, checkpoints); }
     int rc = ensurePathBuffers(ctx, nPixels * sppWave);
     if (rc) { return rc; }
+    if (volume && (rc = ensureVolumeBuffers(ctx, nPixels * sppWave))) { return rc; }
     for (uint32_t done = 0; done < nSpp; done += sppWave) {
         WaveParams wp;
         wp.seed = seed; wp.firstSample = firstSample + done; wp.sppWave = std::min(sppWave, nSpp - done); wp.nPixels = nPixels; wp.groupShift = groupShiftFor(wp.sppWave);
         wp.startBounce = start; wp.lastBounce = last;
+        if (volume) {
+            if ((rc = launchVolumeWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
+            continue;
+        }
         if ((rc = launchWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
     }
     ctx->samples += (uint64_t)nPixels * nSpp;
@@ -2004,11 +2144,20 @@ int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp,
         CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->pinned, n * sizeof(float)));
         ctx->accumScratchSize = ctx->pinnedSize = n;
     }
-    // radianceLookup is accumulated, not overwritten (src/sample_integrator.cpp:61-63): upload, add, download
-    memcpy(ctx->pinned, accum, n * sizeof(float));
+    // radianceLookup is accumulated, not overwritten (src/sample_integrator.cpp:61-63): upload, add, download.  The sums are first
+    // needed by the accumulation at the end of the first wave, so the host copy into pinned memory and the upload are issued on a second
+    // stream AFTER the wave's other launches (they are asynchronous) and run while the GPU traces the wave.
     CUDA_TRY(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->accumScratch, ctx->pinned, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->accumScratch, ctx->stream);
+    ctx->beforeAccumulate = [ctx, accum, n]() -> int {
+        memcpy(ctx->pinned, accum, n * sizeof(float));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->accumScratch, ctx->pinned, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->uploadDone, ctx->copyStream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->uploadDone, 0));
+        return PTC_OK;
+    };
+    int rc = renderInternal(ctx, seed, firstSample, nSpp, start, last, ctx->accumScratch, ctx->stream);
+    if (!rc) { rc = runBeforeAccumulate(ctx); } // no wave at all (zero samples): the sums pass through
+    ctx->beforeAccumulate = nullptr;
     if (rc) { return rc; }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->accumScratch, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
@@ -2377,8 +2526,8 @@ int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out)
     out->closest_rays = totals[0]; out->shadow_rays = totals[1]; out->samples = ctx->samples; out->kernel_launches = ctx->launches;
     out->extend_inner_visits = totals[2]; out->extend_triangle_tests = totals[3];
     out->shadow_inner_visits = totals[4]; out->shadow_triangle_tests = totals[5];
-    out->bvh_nodes = ctx->bvh.nodes.size(); out->bvh_triangles = ctx->bvh.triangles.size();
-    out->bvh_bytes = ctx->bvh.nodes.size() * sizeof(WideNode) + ctx->bvh.triangles.size() * sizeof(LeafTriangle);
+    out->bvh_nodes = ctx->bvhNodeCount; out->bvh_triangles = ctx->bvhTriangleCount;
+    out->bvh_bytes = (size_t)ctx->bvhNodeCount * sizeof(WideNode) + (size_t)ctx->bvhTriangleCount * sizeof(LeafTriangle);
     out->extend_launches = ctx->stageLaunches[STAGE_EXTEND]; out->shadow_launches = ctx->stageLaunches[STAGE_SHADOW];
     out->shade_launches = ctx->stageLaunches[STAGE_SHADE];
     out->extend_ms = (float)ctx->stageMs[STAGE_EXTEND]; out->shadow_ms = (float)ctx->stageMs[STAGE_SHADOW];
@@ -2422,6 +2571,7 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
     if (!strcmp(name, "overlap_shadow")) { ctx->overlapShadow = value != 0; return PTC_OK; }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
+    if (!strcmp(name, "volume_megakernel")) { ctx->volumeMegakernel = value != 0; return PTC_OK; }
     if (!strcmp(name, "bvh_builder")) { // before ptc_commit; 1 = device (default), 0 = host binned SAH
         if (ctx->committed) { CTX_FAIL(ctx, PTC_ERR_STATE, "bvh_builder must be set before ptc_commit"); }
         if (value != 0 && value != 1) { CTX_FAIL(ctx, PTC_ERR_INVALID, "bvh_builder must be 0 (host) or 1 (device)"); }
@@ -2430,9 +2580,24 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     CTX_FAIL(ctx, PTC_ERR_INVALID, "unknown option %s", name);
 }
 
+// host copy of the device-resident BVH for the scalar traversal below
+static int fetchHostBvh(ptc_ctx *ctx)
+{
+    if (ctx->hostBvhFetched) { return PTC_OK; }
+    cudaSetDevice(ctx->device);
+    ctx->bvh.nodes.resize(ctx->bvhNodeCount); ctx->bvh.triangles.resize(ctx->bvhTriangleCount);
+    if (ctx->bvhNodeCount) {
+        CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.nodes.data(), ctx->scene.bvh.nodes, (size_t)ctx->bvhNodeCount * sizeof(WideNode), cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->bvh.triangles.data(), ctx->scene.bvh.triangles, (size_t)ctx->bvhTriangleCount * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
+    }
+    ctx->hostBvhFetched = true;
+    return PTC_OK;
+}
+
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner, uint64_t *tris)
 {
     NEED_COMMIT(ctx);
+    { const int rc = fetchHostBvh(ctx); if (rc) { return rc; } }
     TraversalCounts c;
     for (uint32_t i = 0; i < n; i++) { traverseReference(ctx->bvh, rays[i].origin, rays[i].direction, PTC_TNEAR, PTC_TFAR, false, nullptr, nullptr, &c); }
     if (inner) { *inner = c.innerVisits; }

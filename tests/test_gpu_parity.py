@@ -173,6 +173,37 @@ def test_wavefront_render_matches_oracle_per_pixel(name):
     assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean() + 1e-7
 
 
+@pytest.mark.parametrize("name", ["cornell_medium", "medium_sphere", "cornell_glass", "mis"])
+def test_volume_wavefront_equals_the_one_thread_per_path_kernel(name):
+    """VolumePathTracer: the wavefront stages (one merged probe / continuation traversal, transmittance computed by the shadow
+    warps) against the kernel that follows whole paths with the oracle-pinned building blocks -- same samples, same control flow;
+    only the place of the transmittance factor in the light-sampling products differs (<= 2 ulp per term).  Scenes without media
+    take the plain extend kernel over the queue (no container surface: the two acceptance rules coincide)."""
+    from pathed_b200 import load_scene
+    from pathed_b200._binding import VOLUME_PATH_TRACER
+    cfg = SCENES[name]
+    w, h = cfg["width"] // 2, cfg["height"] // 2
+    ctx = load_scene(cfg["scene"], w, h, integrator=VOLUME_PATH_TRACER)
+    for (spp, start, last) in [(8, 0, cfg["last_bounce"]), (3, 0, 0), (4, 1, 1), (4, 2, 3), (2, 0, 1), (2, 0, -1)]:
+        ctx.set_option("volume_megakernel", 0)
+        before = ctx.stats()
+        a = ctx.render(77, 5, spp, start, last)
+        mid = ctx.stats()
+        ctx.set_option("volume_megakernel", 1)
+        b = ctx.render(77, 5, spp, start, last)
+        after = ctx.stats()
+        assert np.isfinite(a).all()
+        err = np.abs(a - b) / (np.abs(b) + 1e-6 * max(float(b.mean()), 1e-6))
+        print(name, spp, start, last, "max rel", float(err.max()), "rays", mid.closest_rays - before.closest_rays, after.closest_rays - mid.closest_rays)
+        assert err.max() <= 2e-5, (name, spp, start, last, float(err.max()))
+        # shadow rays: the wavefront skips those whose contribution is exactly black; closest-hit rays: never more than the path kernel
+        assert mid.closest_rays - before.closest_rays <= after.closest_rays - mid.closest_rays
+    ctx.set_option("volume_megakernel", 0)
+    one = ctx.render(3, 0, 6, 0, cfg["last_bounce"])
+    ctx.set_option("paths_per_wave", w * h * 2)  # three waves instead of one: same image, bit for bit
+    assert np.array_equal(one, ctx.render(3, 0, 6, 0, cfg["last_bounce"]))
+
+
 def test_render_is_deterministic_and_splits_over_samples():
     """bit-exact: same seed twice; and 8 spp in one call == samples 0-3 then 4-7 into the same buffer (what the
     spp split across GPUs relies on)"""
