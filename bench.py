@@ -334,7 +334,9 @@ def main():
     # N = 1: ptc_render.  N > 1: every rank renders its sample block into a cleared device buffer, one NCCL reduce brings the step's
     # sum to rank 0, which uploads the host accumulator from pinned memory, adds and downloads -- one H2D + one D2H of the
     # framebuffer per step on rank 0, nothing through the host on the other ranks
-    host_accum = np.zeros((height, width, 3), np.float32)
+    # the host radianceLookup lives in page-locked memory (what a binding gets with one cudaHostRegister of the reference's vector):
+    # ptc_render then copies from and to it directly instead of through its own staging buffer
+    host_accum = torch.zeros((height, width, 3), dtype=torch.float32).pin_memory().numpy()
     fb_bytes = n_pix * 3 * 4
     if distributed:
         stepbuf = torch.zeros_like(local)
@@ -387,6 +389,7 @@ def main():
         #             material 336 B (queue entry, ray, hit, result, modulation | throughput, 80 B triangle record; next ray, next
         #             modulation | throughput, next result, NEE record, queue entries)
         peak, peak_note = measured_peak()
+        ctx.set_option("overlap_shadow", 0)  # stage times are taken with the stages one after the other
         ctx.set_option("stage_timing", 1)
         ctx.reset_stats()
         for i in range(args.steps):
@@ -399,6 +402,7 @@ def main():
             ctx.render_device(seed, i * world * spp, spp, 0, last, local.data_ptr(), stream)
         cst = ctx.stats()
         ctx.set_option("count_traversal", 0)
+        ctx.set_option("overlap_shadow", 1)
         n_rays = max(cst.closest_rays + cst.shadow_rays, 1)
         extend_bytes = 64.0 * cst.closest_rays + 80.0 * cst.extend_inner_visits + 48.0 * cst.extend_triangle_tests
         shade_bytes = (148.0 + 336.0) * cst.closest_rays

@@ -202,9 +202,16 @@ int ptc_commit(ptc_ctx *ctx);
  * adds, for every pixel, the radiance of samples first_sample .. first_sample+n_spp-1 into
  * accum_rgb (HOST, 3*W*H floats, index 3*(row*W+col)+c, row 0 = bottom; `+=` like radianceLookup).
  * start_bounce / last_bounce = BounceController (src/bounce_controller.cpp:14-25; -1 = unbounded,
- * capped at PTC_MAX_BOUNCES).  seed keys the Philox streams (pixel, sample, bounce). */
+ * capped at PTC_MAX_BOUNCES).  seed keys the Philox streams (pixel, sample, bounce).
+ * The upload of accum_rgb overlaps the first wave of kernels.  A page-locked accum_rgb (cudaHostRegister of the vector the
+ * reference keeps for the whole render, or cudaHostAlloc) is copied from and to directly; pageable memory goes through a staging
+ * buffer of the context (two more host copies of the framebuffer per call). */
 int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
                int last_bounce, float *accum_rgb);
+/* optional: allocates the per-path state for waves of up to n_paths paths (clamped to "paths_per_wave") NOW instead of inside the
+ * first render call.  Needs no scene: a renderer knows resolution and sample count from its job file (src/job.cpp:25-60) and can call
+ * this -- from another thread -- while it parses the scene; 16 GB of cudaMalloc cost ~0.1 s of the first wave otherwise. */
+int ptc_reserve_paths(ptc_ctx *ctx, uint64_t n_paths);
 /* same, accumulating into a DEVICE buffer on `cuda_stream` (a cudaStream_t; NULL = default stream);
  * asynchronous: returns after enqueueing.  Used for multi-GPU (NCCL reduce of the buffer) */
 int ptc_render_device(ptc_ctx *ctx, uint64_t seed, uint32_t first_sample, uint32_t n_spp, int start_bounce,
@@ -304,7 +311,9 @@ int ptc_reset_stats(ptc_ctx *ctx);
  * NEE shadow rays cast at vertex k; up to `capacity` (<= PTC_MAX_BOUNCES + 2) entries each */
 int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend_counts, uint32_t *shadow_counts, uint32_t capacity);
 int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave",
-                                                                      "bvh_builder" (before ptc_commit: 1 device, 0 host) */
+                                                                      "overlap_shadow", "bvh_builder" (before ptc_commit: 1 device,
+                                                                      0 host), "volume_megakernel" (1: VolumePathTracer as one
+                                                                      thread per path instead of wavefront stages) */
 /* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
  * visits and triangle tests per ray (algorithmic bytes per ray) */
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);

@@ -373,6 +373,9 @@ class Api:
     def reset_stats(self):
         self._call("reset_stats")
 
+    def reserve_paths(self, n_paths):
+        self._call("reserve_paths", ctypes.c_uint64(n_paths))
+
     def set_option(self, name, value):
         self._call("set_option", name.encode(), ctypes.c_int64(value))
 

@@ -1068,6 +1068,7 @@ struct ptc_ctx {
     std::vector<DMaterial> deviceMaterials;                              // the device material table as uploaded (holds texel pointers)
     DScene scene;
     PathBuffers paths; uint32_t pathCapacity = 0; std::vector<void *> pathAllocations;
+    uint32_t classQueueCapacity = 0, classQueueMask = 0; std::vector<void *> classQueueAllocations;
     BounceCounters *counters = nullptr;
     uint32_t classMask = 0; // material classes present in the scene
     unsigned long long *totals = nullptr;
@@ -1217,6 +1218,7 @@ void ptc_destroy(ptc_ctx *ctx)
     for (void *p : ctx->allocations) { cudaFree(p); }
     ctx->allocations.clear(); ctx->allocationBytes.clear();
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
+    for (void *p : ctx->classQueueAllocations) { cudaFree(p); }
     cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
     cudaFree(ctx->framebuffer); cudaFree(ctx->gatherStage);
     for (float *snapshot : ctx->snapshots) { cudaFree(snapshot); }
@@ -1842,29 +1844,45 @@ int ptc_replicate(ptc_ctx *src, int device, ptc_ctx **out)
     return PTC_OK;
 }
 
-static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity)
+// Path state for waves of up to `capacity` paths.  The per-path arrays depend on nothing but the capacity (ptc_reserve_paths may ask
+// for them before the scene exists); the class queues follow the material classes the committed scene holds.
+static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity, bool withClassQueues = true)
 {
-    if (capacity <= ctx->pathCapacity) { return PTC_OK; }
-    for (void *p : ctx->pathAllocations) { cudaFree(p); }
-    ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
     PathBuffers &pb = ctx->paths;
-    CUDA_TRY(ctx, cudaMalloc((void **)&pb.out, (size_t)capacity * sizeof(float4)));
-    ctx->pathAllocations.push_back(pb.out);
-    struct { void **slot; size_t bytesPerPath; } arrays[] = {
-        {(void **)&pb.ray, 32}, {(void **)&pb.nRay, 32}, {(void **)&pb.modThr, 32}, {(void **)&pb.nModThr, 32}, {(void **)&pb.nee, 32},
-        {(void **)&pb.hit, 16}, {(void **)&pb.result, 16}, {(void **)&pb.nResult, 16}, {(void **)&pb.occluded, 1}, {(void **)&pb.shadowQueue, 4}};
-    for (auto &a : arrays) {
-        CUDA_TRY(ctx, cudaMalloc(a.slot, (size_t)capacity * a.bytesPerPath));
-        ctx->pathAllocations.push_back(*a.slot);
+    if (capacity > ctx->pathCapacity) {
+        for (void *p : ctx->pathAllocations) { cudaFree(p); }
+        ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
+        CUDA_TRY(ctx, cudaMalloc((void **)&pb.out, (size_t)capacity * sizeof(float4)));
+        ctx->pathAllocations.push_back(pb.out);
+        struct { void **slot; size_t bytesPerPath; } arrays[] = {
+            {(void **)&pb.ray, 32}, {(void **)&pb.nRay, 32}, {(void **)&pb.modThr, 32}, {(void **)&pb.nModThr, 32}, {(void **)&pb.nee, 32},
+            {(void **)&pb.hit, 16}, {(void **)&pb.result, 16}, {(void **)&pb.nResult, 16}, {(void **)&pb.occluded, 1}, {(void **)&pb.shadowQueue, 4}};
+        for (auto &a : arrays) {
+            CUDA_TRY(ctx, cudaMalloc(a.slot, (size_t)capacity * a.bytesPerPath));
+            ctx->pathAllocations.push_back(*a.slot);
+        }
+        ctx->pathCapacity = capacity;
     }
-    for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
-        pb.classQueue[t] = nullptr;
-        if (!(ctx->classMask & (1u << t))) { continue; }
-        CUDA_TRY(ctx, cudaMalloc((void **)&pb.classQueue[t], (size_t)capacity * sizeof(uint32_t)));
-        ctx->pathAllocations.push_back(pb.classQueue[t]);
+    if (withClassQueues && (ctx->pathCapacity > ctx->classQueueCapacity || ctx->classQueueMask != ctx->classMask)) {
+        for (void *p : ctx->classQueueAllocations) { cudaFree(p); }
+        ctx->classQueueAllocations.clear(); ctx->classQueueCapacity = 0;
+        for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) {
+            pb.classQueue[t] = nullptr;
+            if (!(ctx->classMask & (1u << t))) { continue; }
+            CUDA_TRY(ctx, cudaMalloc((void **)&pb.classQueue[t], (size_t)ctx->pathCapacity * sizeof(uint32_t)));
+            ctx->classQueueAllocations.push_back(pb.classQueue[t]);
+        }
+        ctx->classQueueCapacity = ctx->pathCapacity; ctx->classQueueMask = ctx->classMask;
     }
-    ctx->pathCapacity = capacity;
     return PTC_OK;
+}
+
+int ptc_reserve_paths(ptc_ctx *ctx, uint64_t nPaths)
+{
+    if (!ctx) { return PTC_ERR_INVALID; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t capacity = std::min<uint64_t>(std::max<uint64_t>(nPaths, 1), (uint64_t)ctx->pathsPerWave);
+    return ensurePathBuffers(ctx, (uint32_t)capacity, false);
 }
 
 // Which checkpoints the resolve of one wave (global samples F .. F + S - 1 of a render call) snapshots, and after how many of the wave's
@@ -2003,6 +2021,13 @@ static int launchVolumeWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevi
     ctx->launches++;
     for (int k = 0; k <= wp.lastBounce; k++) {
         BounceCounters *bc = cnt + k;
+        // both kinds of shadow rays of bounce k go to the second stream, next to the bounce's merged rays (as in launchWave)
+        const bool overlap = ctx->overlapShadow && k > 0;
+        cudaStream_t shadowOn = overlap ? ctx->shadowStream : stream;
+        if (overlap) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->shadeDone, stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->shadowStream, ctx->shadeDone, 0));
+        }
         {
             StageTimer t(ctx, stream, STAGE_EXTEND);
             if (k == 0) { // camera rays: Scene::testIntersect, every slot
@@ -2018,15 +2043,19 @@ static int launchVolumeWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevi
         }
         ctx->launches++;
         if (k > 0) {
-            StageTimer t(ctx, stream, STAGE_SHADOW);
+            StageTimer t(ctx, shadowOn, STAGE_SHADOW);
             if (count) {
-                volumeTraverseKernel<VOL_SHADOW, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
-                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+                volumeTraverseKernel<VOL_SHADOW, true><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, true><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
             } else {
-                volumeTraverseKernel<VOL_SHADOW, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
-                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+                volumeTraverseKernel<VOL_SHADOW, false><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, false><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
             }
             ctx->launches += s.nMedia ? 2 : 1;
+        }
+        if (overlap) { // the logic stage reads the shadow outcomes
+            CUDA_TRY(ctx, cudaEventRecord(ctx->shadowDone, ctx->shadowStream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->shadowDone, 0));
         }
         {
             StageTimer t(ctx, stream, STAGE_SHADE);
@@ -2144,13 +2173,19 @@ int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp,
         CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->pinned, n * sizeof(float)));
         ctx->accumScratchSize = ctx->pinnedSize = n;
     }
+    // A radianceLookup in page-locked memory (cudaHostAlloc / cudaHostRegister by the caller) is copied from and to directly; a pageable
+    // one goes through the context's pinned staging buffer (two host copies of the framebuffer more per call).
+    cudaPointerAttributes attr;
+    const bool callerPinned = cudaPointerGetAttributes(&attr, accum) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError(); // older drivers report unregistered host memory as an error
+    float *hostSide = callerPinned ? accum : ctx->pinned;
     // radianceLookup is accumulated, not overwritten (src/sample_integrator.cpp:61-63): upload, add, download.  The sums are first
     // needed by the accumulation at the end of the first wave, so the host copy into pinned memory and the upload are issued on a second
     // stream AFTER the wave's other launches (they are asynchronous) and run while the GPU traces the wave.
     CUDA_TRY(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    ctx->beforeAccumulate = [ctx, accum, n]() -> int {
-        memcpy(ctx->pinned, accum, n * sizeof(float));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->accumScratch, ctx->pinned, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
+    ctx->beforeAccumulate = [ctx, accum, hostSide, n]() -> int {
+        if (hostSide != accum) { memcpy(hostSide, accum, n * sizeof(float)); }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->accumScratch, hostSide, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copyStream));
         CUDA_TRY(ctx, cudaEventRecord(ctx->uploadDone, ctx->copyStream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->uploadDone, 0));
         return PTC_OK;
@@ -2159,11 +2194,11 @@ int ptc_render(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uint32_t nSpp,
     if (!rc) { rc = runBeforeAccumulate(ctx); } // no wave at all (zero samples): the sums pass through
     ctx->beforeAccumulate = nullptr;
     if (rc) { return rc; }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->accumScratch, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hostSide, ctx->accumScratch, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->lastRenderMs, ctx->evStart, ctx->evStop);
-    memcpy(accum, ctx->pinned, n * sizeof(float));
+    if (hostSide != accum) { memcpy(accum, hostSide, n * sizeof(float)); }
     return PTC_OK;
 }
 
@@ -2545,7 +2580,7 @@ int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend, uint32_t *shadow, uint32
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (cudaMemcpy(host.data(), ctx->counters, CNT_STRIDE * sizeof(BounceCounters), cudaMemcpyDeviceToHost) != cudaSuccess) { CTX_FAIL(ctx, PTC_ERR_CUDA, "cudaMemcpy failed"); }
-    for (uint32_t k = 0; k < capacity && k < CNT_STRIDE; k++) { extend[k] = host[k].extendCount; shadow[k] = host[k].shadowCount; }
+    for (uint32_t k = 0; k < capacity && k < CNT_STRIDE; k++) { extend[k] = host[k].extendCount; shadow[k] = host[k].shadowCount + host[k].scatterCount; }
     return PTC_OK;
 }
 

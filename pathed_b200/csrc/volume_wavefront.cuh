@@ -87,8 +87,14 @@ __device__ __forceinline__ V3 transmittanceBetween(const DScene &s, int32_t medi
 //  VOL_EXTEND  ray = the slot's (origin, direction); writes the plain closest hit to pb.hit and the filtered one to vb.probeHit
 //  VOL_SHADOW  ray = slot origin + the NEE record's direction / distance, medium = the one the path was in when Ld was evaluated
 //  VOL_SCATTER ray = the slot's scatter record
+// 64 registers -> 8 resident CTAs, as the PathTracer's traversal kernel has them (72-80 registers / 6 CTAs without the bound: merged
+// extend 55.5 -> 53.6 ms per 4 steps on cornell-medium)
+#ifndef PTC_VOLUME_TRAVERSE_MIN_BLOCKS
+#define PTC_VOLUME_TRAVERSE_MIN_BLOCKS 8
+#endif
+#define PTC_VOLUME_TRAVERSE_BOUNDS __launch_bounds__(128, PTC_VOLUME_TRAVERSE_MIN_BLOCKS)
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) volumeTraverseKernel(const __grid_constant__ DScene scene, PathBuffers pb, VolumeBuffers vb, const uint32_t *queue, const uint32_t *count,
+__global__ void PTC_VOLUME_TRAVERSE_BOUNDS volumeTraverseKernel(const __grid_constant__ DScene scene, PathBuffers pb, VolumeBuffers vb, const uint32_t *queue, const uint32_t *count,
                                                             uint32_t *cursor, unsigned long long *work)
 {
     constexpr bool ANY = MODE != VOL_EXTEND;
@@ -206,7 +212,10 @@ __global__ void __launch_bounds__(128) volumeTraverseKernel(const __grid_constan
 
 // Everything of VolumePathTracer::L that waits for the rays traced at bounce k >= 1 (they left vertex k): the in-scattered light of
 // the segment that arrived at vertex k (:54-55), Ld of vertex k (:36 -> DirectLightingHelper::Ld), and whether the path goes on (:52-53).
-__global__ void __launch_bounds__(256, PTC_LOGIC_MIN_BLOCKS) volumeLogicKernel(const __grid_constant__ DScene scene, PathBuffers pb, VolumeBuffers vb, WaveParams wp,
+#ifndef PTC_VOLUME_LOGIC_MIN_BLOCKS
+#define PTC_VOLUME_LOGIC_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, PTC_VOLUME_LOGIC_MIN_BLOCKS) volumeLogicKernel(const __grid_constant__ DScene scene, PathBuffers pb, VolumeBuffers vb, WaveParams wp,
                                                                                 BounceCounters *bc, uint32_t classMask)
 {
     const uint32_t n = bc->slotCount;
@@ -287,8 +296,11 @@ __global__ void __launch_bounds__(256, PTC_LOGIC_MIN_BLOCKS) volumeLogicKernel(c
 // Vertex b = k + 1 of every path whose continuation ray k hit a surface of material class TYPE: the rest of loop iteration k of
 // VolumePathTracer::L (:52-61: Intersection, modulation, scatter, transmittance, black test) and the head of iteration b (:33-50:
 // BSDF sample, Ld set-up, medium change).  k = 0: the camera hit (:21-31 are the same statements with modulation = 1).
+// Occupancy sweep on cornell-medium (profiles/r02_sweep_volume_wavefront.txt, Msamples/s): 8 CTAs of 128 per SM 333, 6 CTAs 342-345,
+// 5 CTAs 377, 4 CTAs 386-394, 3 CTAs 385, 2 CTAs 386 -- unlike the PathTracer's material kernels (best at 8 CTAs with ~170 B of
+// spills) this one carries the scatter record and the medium next to the BSDF state, and its spills cost more than the occupancy gives
 #ifndef PTC_VOLUME_MATERIAL_MIN_BLOCKS
-#define PTC_VOLUME_MATERIAL_MIN_BLOCKS 6
+#define PTC_VOLUME_MATERIAL_MIN_BLOCKS 4
 #endif
 template <int TYPE>
 __global__ void __launch_bounds__(128, PTC_VOLUME_MATERIAL_MIN_BLOCKS) volumeMaterialKernel(const __grid_constant__ DScene scene, PathBuffers pb, VolumeBuffers vb, WaveParams wp,

@@ -55,7 +55,7 @@ double now()
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ Scene
-Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first) : m_width(description.camera.width), m_height(description.camera.height)
+Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first, uint64_t reservePaths) : m_width(description.camera.width), m_height(description.camera.height)
 {
     // device 0 is fed and builds the BVH; the other devices of the spp split receive copies of the finished device data
     ptc_ctx *ctx = first;
@@ -74,7 +74,10 @@ Scene::Scene(const SceneDescription &description, int gpus, ptc_ctx *first) : m_
     std::vector<int> outcome((size_t)devices, PTC_OK);
     std::vector<std::thread> workers;
     for (int device = 1; device < devices; device++) {
-        workers.emplace_back([&, device]() { outcome[(size_t)device] = ptc_replicate(ctx, device, &copies[(size_t)device]); });
+        workers.emplace_back([&, device]() {
+            outcome[(size_t)device] = ptc_replicate(ctx, device, &copies[(size_t)device]);
+            if (outcome[(size_t)device] == PTC_OK && copies[(size_t)device] && reservePaths) { ptc_reserve_paths(copies[(size_t)device], reservePaths); }
+        });
     }
     for (std::thread &worker : workers) { worker.join(); }
     for (int device = 1; device < devices; device++) {
@@ -131,7 +134,14 @@ uint32_t Scene::lightCount() const
 std::unique_ptr<Scene> parseSceneForJob(const Job &job, const std::string &rootDirectory)
 {
     // the CUDA runtime comes up (driver initialisation, module load: seconds on a multi-GPU box) while the host parses the scene files
-    std::future<ptc_ctx *> device = std::async(std::launch::async, []() { ptc_ctx *ctx = nullptr; ptc_create(0, &ctx); return ctx; });
+    // ... and so does the path state of the first wave: resolution and sample count are the job's, not the scene's
+    const uint64_t wavePaths = (uint64_t)std::max(1, job.width()) * (uint64_t)std::max(1, job.height()) *
+                               (uint64_t)std::max(1, std::min(job.waveSpp(), (job.spp() + std::max(1, job.gpus()) - 1) / std::max(1, job.gpus())));
+    std::future<ptc_ctx *> device = std::async(std::launch::async, [wavePaths]() {
+        ptc_ctx *ctx = nullptr;
+        if (ptc_create(0, &ctx) == PTC_OK && ctx) { ptc_reserve_paths(ctx, wavePaths); } // best effort: the first render allocates what is missing
+        return ctx;
+    });
     const double begin = now();
     SceneDescription description;
     try { description = parseScene(job.scene(), rootDirectory, job.width(), job.height()); }
@@ -140,7 +150,7 @@ std::unique_ptr<Scene> parseSceneForJob(const Job &job, const std::string &rootD
     ptc_ctx *first = device.get();
     if (!first) { throw std::runtime_error("Failed to create device 0 (no CUDA device? there is no CPU path)"); }
     const double ready = now();
-    std::unique_ptr<Scene> scene(new Scene(description, job.gpus(), first));
+    std::unique_ptr<Scene> scene(new Scene(description, job.gpus(), first, wavePaths));
     printf("Scene: %0.2fs parsing, %0.2fs more until the device was up, %0.2fs upload + BVH build + copies to %d more GPU(s)\n",
            parsed - begin, ready - parsed, now() - ready, job.gpus() - 1);
     return scene;

@@ -140,7 +140,8 @@ struct Intersection {
 class Scene {
 public:
     // `first`: an already created context for device 0 (ownership passes to the Scene); null = create one
-    Scene(const SceneDescription &description, int gpus = 1, ptc_ctx *first = nullptr);
+    // reservePaths: path state the further devices allocate while they are set up (ptc_reserve_paths; the first one did it while the scene was parsed)
+    Scene(const SceneDescription &description, int gpus = 1, ptc_ctx *first = nullptr, uint64_t reservePaths = 0);
     ~Scene();
     Scene(const Scene &) = delete;
     Scene &operator=(const Scene &) = delete;

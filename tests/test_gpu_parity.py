@@ -219,6 +219,41 @@ def test_render_is_deterministic_and_splits_over_samples():
     assert np.array_equal(a, d)
 
 
+def test_render_into_page_locked_memory_equals_the_staged_copy():
+    """ptc_render copies from and to a page-locked radianceLookup directly, a pageable one through its staging buffer: same sums,
+    accumulated on top of what the buffer held (src/sample_integrator.cpp:61-63), also over several waves and for zero samples"""
+    import torch
+    ctx = gpu_scene("cornell", 64, 64)
+    pageable = ctx.render(7, 0, 6, 0, 5, accum=np.full((64, 64, 3), 0.5, np.float32))
+    pinned = torch.full((64, 64, 3), 0.5, dtype=torch.float32).pin_memory().numpy()
+    assert ctx.render(7, 0, 6, 0, 5, accum=pinned) is pinned
+    assert np.array_equal(pinned, pageable)
+    ctx.set_option("paths_per_wave", 64 * 64 * 2)  # three waves: the upload is waited for by the first accumulation only
+    again = torch.full((64, 64, 3), 0.5, dtype=torch.float32).pin_memory().numpy()
+    ctx.render(7, 0, 6, 0, 5, accum=again)
+    assert np.array_equal(again, pageable)
+    ctx.render(7, 0, 0, 0, 5, accum=again)         # no wave at all
+    assert np.array_equal(again, pageable)
+
+
+def test_path_state_reserved_before_the_scene_exists():
+    """ptc_reserve_paths: the per-path arrays allocated on a bare context (what the CLI does while it parses the scene) serve the
+    renders that follow, smaller and larger than the reservation; the images do not depend on it"""
+    images = []
+    for reserve in (0, 8 * 8 * 2, 1 << 20):
+        ctx = gpu_context()
+        if reserve:
+            ctx.reserve_paths(reserve)
+        _tiny_scene(ctx, [dict(type=0, diffuse=(0.7, 0.6, 0.5), emit=(3, 2, 1))])
+        images.append((ctx.render(11, 0, 2, 0, 4), ctx.render(11, 2, 6, 0, 4)))
+        ctx.close()
+    for a, b in images[1:]:
+        assert np.array_equal(a, images[0][0]) and np.array_equal(b, images[0][1])
+    import ctypes
+    from pathed_b200 import cuda_lib
+    assert cuda_lib().ptc_reserve_paths(None, ctypes.c_uint64(1)) != 0  # no context: refused with a status
+
+
 def test_bounce_window_matches_oracle():
     cfg = SCENES["cornell"]
     ctx = gpu_scene("cornell", 32, 32)

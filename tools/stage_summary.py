@@ -27,8 +27,12 @@ def main():
         per.setdefault(int(r[ix["ID"]]), {"name": r[ix["Kernel Name"]]})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     l2 = json.load(open(os.path.join(ROOT, "profiles", "l2_peak.json")))["l2_read_gbs"]
-    stage_of = lambda n: ("extend" if "traverseKernel<0" in n else "shadow" if "traverseKernel<1" in n else "logic" if "logicKernel" in n else
-                          "material" if "materialKernel" in n else "generate" if "generateKernel" in n else "resolve" if "accumulateKernel" in n else None)
+    # PathTracer stages and the VolumePathTracer's (volumeTraverseKernel<0 / 1 / 2>: merged extend / surface shadow / scatter shadow)
+    stage_of = lambda n: ("extend" if ("volumeTraverseKernel<0" in n or n.startswith("void traverseKernel<0")) else
+                          "shadow" if ("volumeTraverseKernel<" in n or n.startswith("void traverseKernel<1")) else
+                          "logic" if ("logicKernel" in n or "volumeLogicKernel" in n or "containerKernel" in n) else
+                          "material" if ("materialKernel" in n or "volumeMaterialKernel" in n) else "generate" if "generateKernel" in n else
+                          "resolve" if "accumulateKernel" in n else None)
     units = {"extend": sum(counts["extend_rays"]), "shadow": sum(counts["shadow_rays"]), "logic": sum(counts["extend_rays"]),
              "material": sum(counts["extend_rays"][1:]), "generate": counts["extend_rays"][0], "resolve": counts["extend_rays"][0]}
     unit_name = {"extend": "ray", "shadow": "ray", "logic": "path vertex", "material": "path vertex", "generate": "path", "resolve": "sample"}
