@@ -262,14 +262,6 @@ def main():
                      integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
     build_s = time.time() - t0
     tst0 = ctx.stats()
-    # the first build of a process also pays for CUDA's lazy module loading (every builder kernel, cub's sort and scan) and the first
-    # large allocations; a second scene in the same process shows the builder itself
-    warm_build_ms = None
-    if rank == 0 and not distributed:
-        again = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder},
-                           integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
-        warm_build_ms = again.stats().bvh_build_ms
-        again.close()
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
     n_pix = width * height
@@ -485,6 +477,16 @@ def main():
             cpu = {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": r["threads"], "kind": "reference",
                    "sample": "%d spp of %dx%d after 1 warm-up spp, unmodified reference + Embree 3.6.0, %d OpenMP threads, %.1f s"
                              % (r["spp"], width, height, r["threads"], r["render_wall_s"])}
+
+    # the first build of a process also pays for CUDA's lazy module loading (every builder kernel, cub's sort and scan) and the first
+    # large allocations; a second scene in the same process shows the builder itself.  Done after everything that is timed: earlier
+    # allocations and frees move later ones, and the throughput of the tiny scenes depends on where a handful of hot lines land.
+    warm_build_ms = None
+    if rank == 0 and not distributed:
+        again = load_scene(w["scene"], width, height, device=local_rank, options={"bvh_builder": args.bvh_builder},
+                           integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
+        warm_build_ms = again.stats().bvh_build_ms
+        again.close()
 
     if rank == 0:
         line = {

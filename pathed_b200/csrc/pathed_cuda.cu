@@ -1577,10 +1577,6 @@ int ptc_commit(ptc_ctx *ctx)
                 DeviceWideBVH built;
                 if (ctx->buildWorkspace) { cudaFree(ctx->buildWorkspace); ctx->buildWorkspace = nullptr; }
                 buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built, &ctx->buildWorkspace);
-                if (built.nodes) { A.push_back(built.nodes); ctx->allocationBytes.push_back((size_t)built.nNodes * sizeof(WideNode)); }
-                if (built.triangles) { A.push_back(built.triangles); ctx->allocationBytes.push_back((size_t)built.nTriangles * sizeof(LeafTriangle)); }
-                s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
-                ctx->bvhPlocIterations = built.plocIterations;
                 // no host copy here (49 MB through pageable memory cost more than the build): fetchHostBvh brings it when
                 // the scalar counting traversal asks for it
                 ctx->bvh.nodes.clear(); ctx->bvh.triangles.clear(); ctx->bvh.maxDepth = built.maxDepth;
@@ -1852,15 +1848,19 @@ static int ensurePathBuffers(ptc_ctx *ctx, uint32_t capacity, bool withClassQueu
     if (capacity > ctx->pathCapacity) {
         for (void *p : ctx->pathAllocations) { cudaFree(p); }
         ctx->pathAllocations.clear(); ctx->pathCapacity = 0;
-        CUDA_TRY(ctx, cudaMalloc((void **)&pb.out, (size_t)capacity * sizeof(float4)));
-        ctx->pathAllocations.push_back(pb.out);
         struct { void **slot; size_t bytesPerPath; } arrays[] = {
-            {(void **)&pb.ray, 32}, {(void **)&pb.nRay, 32}, {(void **)&pb.modThr, 32}, {(void **)&pb.nModThr, 32}, {(void **)&pb.nee, 32},
+            {(void **)&pb.out, 16}, {(void **)&pb.ray, 32}, {(void **)&pb.nRay, 32}, {(void **)&pb.modThr, 32}, {(void **)&pb.nModThr, 32}, {(void **)&pb.nee, 32},
             {(void **)&pb.hit, 16}, {(void **)&pb.result, 16}, {(void **)&pb.nResult, 16}, {(void **)&pb.occluded, 1}, {(void **)&pb.shadowQueue, 4}};
-        for (auto &a : arrays) {
-            CUDA_TRY(ctx, cudaMalloc(a.slot, (size_t)capacity * a.bytesPerPath));
-            ctx->pathAllocations.push_back(*a.slot);
-        }
+        // ONE allocation for all the arrays (one driver call instead of eleven; their relative placement no longer depends on what the
+        // process allocated and freed before).  Measured: neither the gaps between the arrays (0 ... 2 MB + 9 KB) nor slab vs separate
+        // allocations change the throughput (profiles/r02_path_state_layout.txt).
+        size_t total = 0;
+        for (auto &a : arrays) { total += ((size_t)capacity * a.bytesPerPath + 255u) & ~(size_t)255u; }
+        char *base = nullptr;
+        CUDA_TRY(ctx, cudaMalloc((void **)&base, total));
+        ctx->pathAllocations.push_back(base);
+        size_t offset = 0;
+        for (auto &a : arrays) { *a.slot = base + offset; offset += ((size_t)capacity * a.bytesPerPath + 255u) & ~(size_t)255u; }
         ctx->pathCapacity = capacity;
     }
     if (withClassQueues && (ctx->pathCapacity > ctx->classQueueCapacity || ctx->classQueueMask != ctx->classMask)) {

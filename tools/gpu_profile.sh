@@ -13,6 +13,9 @@ tail -1 gpurun_out/${tag}_wave.log
 timeout 1200 ncu --set full --import-source on --clock-control none -k 'regex:materialKernel|logicKernel|traverseKernel' -c 9 \
   -f -o gpurun_out/${tag}_stages python tools/profile_wave.py dragon 16 gpurun_out/${tag}_wave16_counts.json > gpurun_out/${tag}_stages.log 2>&1
 ls -la gpurun_out/${tag}_stages.ncu-rep
+# 2b. per-launch metrics of one VolumePathTracer wave (cornell-medium, 64 spp): the wavefront stages of volume_wavefront.cuh
+timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${tag}_volume_wave_metrics.csv python tools/profile_wave.py cornell-medium 64 gpurun_out/${tag}_volume_wave_counts.json > gpurun_out/${tag}_volume_wave.log 2>&1
+tail -1 gpurun_out/${tag}_volume_wave.log
 # 3. L2 -> SM read bandwidth ceiling (tools/l2_bandwidth.cu), for roofline.l2_frac
 if [ -f tools/l2_bandwidth.cu ]; then
   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/l2_bandwidth tools/l2_bandwidth.cu > gpurun_out/${tag}_l2_build.log 2>&1 && /tmp/l2_bandwidth > gpurun_out/${tag}_l2_peak.json 2> gpurun_out/${tag}_l2.err
