@@ -1577,6 +1577,10 @@ int ptc_commit(ptc_ctx *ctx)
                 DeviceWideBVH built;
                 if (ctx->buildWorkspace) { cudaFree(ctx->buildWorkspace); ctx->buildWorkspace = nullptr; }
                 buildWideBVHDevice(buildPositions, buildPrims, nPrims, ctx->stream, built, &ctx->buildWorkspace);
+                if (built.nodes) { A.push_back(built.nodes); ctx->allocationBytes.push_back((size_t)built.nNodes * sizeof(WideNode)); }
+                if (built.triangles) { A.push_back(built.triangles); ctx->allocationBytes.push_back((size_t)built.nTriangles * sizeof(LeafTriangle)); }
+                s.bvh.nodes = built.nodes; s.bvh.triangles = built.triangles; s.bvh.nNodes = built.nNodes;
+                ctx->bvhPlocIterations = built.plocIterations;
                 // no host copy here (49 MB through pageable memory cost more than the build): fetchHostBvh brings it when
                 // the scalar counting traversal asks for it
                 ctx->bvh.nodes.clear(); ctx->bvh.triangles.clear(); ctx->bvh.maxDepth = built.maxDepth;
