@@ -497,7 +497,8 @@ def main():
                       "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
                                     "ms": tst0.bvh_build_ms, "ms_second_build_in_process": warm_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},
             "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": fb_bytes,
+                    "wall_ms_per_step": e2e_wall_ms / args.steps, "device_ms_per_step": (e2e_device_ms / args.steps) if not distributed else None},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
         }
         if image_check:

@@ -103,6 +103,7 @@ struct BuildArrays {
     uint32_t *itemChildren; // 8 per item, slot order, kInvalid = empty
     WideNode *wideNodes;
     LeafTriangle *leafTriangles;
+    float costPrim; // cost of a triangle test relative to a node visit in the collapse (runBuild)
 };
 
 // ---- step 1: boxes ---------------------------------------------------------------------------------------------------
@@ -155,7 +156,7 @@ struct LeafOp {
         a.nodeLo[i] = make_float4(lo.x, lo.y, lo.z, u2f(p));
         a.nodeHi[i] = make_float4(hi.x, hi.y, hi.z, u2f(kInvalid));
         NodeDP d;
-        const float cost = halfArea(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) * kCostPrim;
+        const float cost = halfArea(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) * a.costPrim;
         for (int k = 0; k < 7; k++) { d.c[k] = cost; }
         d.info = 1u | (1u << 4);
         a.dp[i] = d;
@@ -200,7 +201,7 @@ struct MergeFlagOp {
 };
 
 // collapse table of a new inner node from its children's tables (Ylitie et al. 2017, section 3.1; the host builder's recurrences)
-PTC_HD NodeDP combineDP(const NodeDP &l, const NodeDP &r, float area)
+PTC_HD NodeDP combineDP(const NodeDP &l, const NodeDP &r, float area, float costPrim)
 {
     NodeDP d;
     float distribute[9];
@@ -218,7 +219,7 @@ PTC_HD NodeDP combineDP(const NodeDP &l, const NodeDP &r, float area)
     const uint32_t sum = dpPrimCount(l.info) + dpPrimCount(r.info);
     const uint32_t count = sum > 15u ? 15u : sum;
     const float internal = distribute[8] + area * kCostNode;
-    const float leaf = count <= kMaxLeaf ? area * (float)count * kCostPrim : kInf;
+    const float leaf = count <= kMaxLeaf ? area * (float)count * costPrim : kInf;
     const bool rootIsLeaf = leaf <= internal;
     d.c[0] = fminf(leaf, internal);
     for (int i = 2; i <= 7; i++) { d.c[i - 1] = fminf(distribute[i], d.c[i - 2]); }
@@ -246,7 +247,7 @@ struct MergeOp {
             hi = make_float4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), 0.f);
             a.nodeLo[node] = make_float4(lo.x, lo.y, lo.z, u2f(left));
             a.nodeHi[node] = make_float4(hi.x, hi.y, hi.z, u2f(right));
-            a.dp[node] = combineDP(a.dp[left], a.dp[right], halfArea(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z));
+            a.dp[node] = combineDP(a.dp[left], a.dp[right], halfArea(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z), a.costPrim);
             lo.w = u2f(node);
         }
         a.clusterLo[buffer ^ 1][slot] = lo;
@@ -277,7 +278,7 @@ struct TopDownOp {
                 const float4 l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), u2f(left));
                 const float4 h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), u2f(right));
                 a.nodeLo[nextNode] = l; a.nodeHi[nextNode] = h;
-                a.dp[nextNode] = combineDP(a.dp[left], a.dp[right], halfArea(l.x, l.y, l.z, h.x, h.y, h.z));
+                a.dp[nextNode] = combineDP(a.dp[left], a.dp[right], halfArea(l.x, l.y, l.z, h.x, h.y, h.z), a.costPrim);
                 results[rp++] = nextNode++;
                 sp--;
                 continue;
@@ -683,6 +684,8 @@ BuildResult runBuild(Exec &exec, BuildArrays &a)
     BuildResult result;
     const uint32_t n = a.nPrims;
     const auto t0 = std::chrono::steady_clock::now();
+    a.costPrim = kCostPrim;
+    if (const char *c = getenv("PTC_COST_PRIM")) { a.costPrim = (float)atof(c); } // tuning hook (tools/compare_builders.py)
     a.primLo = exec.template alloc<float4>(n); a.primHi = exec.template alloc<float4>(n);
     a.bounds = exec.template alloc<uint32_t>(6);
     for (int b = 0; b < 2; b++) {

@@ -118,6 +118,7 @@ struct BounceCounters {
 };
 static_assert(sizeof(BounceCounters) == 128, "one cache line per bounce");
 #define CNT_STRIDE (PTC_MAX_BOUNCES + 2)
+#define PTC_MAX_LANES 8
 
 // Path slot q of a wave -> pixel.  Slots are laid out in 8x4 pixel tiles so that the 32 camera rays of a warp (and the
 // secondary rays they spawn) stay spatially coherent; falls back to row-major when the image is not tileable.
@@ -1096,6 +1097,15 @@ struct ptc_ctx {
     // the shadow CTAs become resident as the extend kernel drains -- the tail of one launch is filled with the head of the other
     bool overlapShadow = true;
     cudaStream_t shadowStream = nullptr; cudaEvent_t shadeDone = nullptr, shadowDone = nullptr;
+    // A wave is traced as `lanes` interleaved part-waves (consecutive blocks of the wave's samples, each with its own share of the path
+    // state, its own counters and streams): while one lane's paths are in a shading stage (waiting on dependent loads, half of the issue
+    // slots idle) another lane's rays are in a traversal stage (issue-bound, hardly any DRAM traffic), and the SMs hold CTAs of both.
+    // Lane 0 runs on the caller's stream; the samples are still added to the image in sample order (launchWave), so the result does
+    // not depend on the number of lanes.
+    int lanes = 1;
+    struct Lane { cudaStream_t stream = nullptr, shadowStream = nullptr; cudaEvent_t shadeDone = nullptr, shadowDone = nullptr, done = nullptr; BounceCounters *counters = nullptr; };
+    std::vector<Lane> extraLanes; // lanes 1 ..
+    cudaEvent_t laneFork = nullptr;
     int bvhBuilder = 1; // 1: device builder (bvh_build_gpu.cu), 0: host binned-SAH builder (bvh_build.cu)
     float bvhBuildMs = 0.f; uint32_t bvhPlocIterations = 0;
     // the device builder leaves nodes and leaf triangles in HBM; the host copy (only ptc_count_traversal walks it) is fetched on demand
@@ -1206,6 +1216,11 @@ int ptc_create(int device, ptc_ctx **out)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumeMaterialKernel<PTC_PLASTIC>, 128, 0);
     ctx->gridVolumeShade = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
+    // tuning hooks (tools/sweep_lanes.sh): number of interleaved lanes and CTAs per SM of the persistent grids
+    if (const char *e = getenv("PTC_LANES")) { ctx->lanes = std::min(PTC_MAX_LANES, std::max(1, atoi(e))); }
+    if (const char *e = getenv("PTC_TRAVERSE_PER_SM")) { ctx->gridTraverse = ctx->numSMs * std::max(1, atoi(e)); }
+    if (const char *e = getenv("PTC_LOGIC_PER_SM")) { ctx->gridLogic = ctx->numSMs * std::max(1, atoi(e)); }
+    if (const char *e = getenv("PTC_SHADE_PER_SM")) { ctx->gridShade = ctx->numSMs * std::max(1, atoi(e)); }
     *out = ctx;
     return PTC_OK;
 }
@@ -1220,6 +1235,12 @@ void ptc_destroy(ptc_ctx *ctx)
     for (void *p : ctx->pathAllocations) { cudaFree(p); }
     for (void *p : ctx->classQueueAllocations) { cudaFree(p); }
     cudaFree(ctx->counters); cudaFree(ctx->totals); cudaFree(ctx->accumScratch);
+    for (ptc_ctx::Lane &lane : ctx->extraLanes) {
+        if (lane.stream) { cudaStreamDestroy(lane.stream); } if (lane.shadowStream) { cudaStreamDestroy(lane.shadowStream); }
+        for (cudaEvent_t e : {lane.shadeDone, lane.shadowDone, lane.done}) { if (e) { cudaEventDestroy(e); } }
+        cudaFree(lane.counters);
+    }
+    if (ctx->laneFork) { cudaEventDestroy(ctx->laneFork); }
     cudaFree(ctx->framebuffer); cudaFree(ctx->gatherStage);
     for (float *snapshot : ctx->snapshots) { cudaFree(snapshot); }
     for (auto &g : ctx->gathers) { cudaFree(g.device); if (g.pinned) { cudaFreeHost(g.pinned); } if (g.done) { cudaEventDestroy(g.done); } }
@@ -1916,73 +1937,131 @@ static int runBeforeAccumulate(ptc_ctx *ctx)
     return f();
 }
 
-// one wave = fixed launch sequence; all queue sizes stay on the device
-static int launchWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream, const CheckpointPlan &plan)
+// The arrays of lane `lane`: every array of the wave's path state starts `offset` paths further on
+static PathBuffers laneBuffers(const PathBuffers &all, size_t offset)
+{
+    PathBuffers pb = all;
+    pb.ray += 2 * offset; pb.nRay += 2 * offset; pb.modThr += 2 * offset; pb.nModThr += 2 * offset; pb.nee += 2 * offset;
+    pb.hit += offset; pb.result += offset; pb.nResult += offset; pb.occluded += offset; pb.out += offset; pb.shadowQueue += offset;
+    for (int t = 0; t < PTC_MATERIAL_CLASSES; t++) { if (pb.classQueue[t]) { pb.classQueue[t] += offset; } }
+    return pb;
+}
+
+static int ensureLanes(ptc_ctx *ctx, int lanes)
+{
+    if (!ctx->laneFork) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->laneFork, cudaEventDisableTiming)); }
+    while ((int)ctx->extraLanes.size() < lanes - 1) {
+        ptc_ctx::Lane lane;
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&lane.shadowStream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&lane.shadeDone, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&lane.shadowDone, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaMalloc((void **)&lane.counters, CNT_STRIDE * sizeof(BounceCounters)));
+        ctx->extraLanes.push_back(lane);
+    }
+    return PTC_OK;
+}
+
+// One wave = fixed launch sequence; all queue sizes stay on the device.  The wave's samples are traced as nLanes part-waves (wps[i]:
+// consecutive sample blocks, plans[i]: the checkpoints that fall into them) whose launch sequences are issued bounce by bounce on one
+// stream per lane, so that the stages of different lanes share the SMs (ptc_ctx::lanes); nLanes = 1 is the plain sequence.
+static int launchWave(ptc_ctx *ctx, const WaveParams *wps, const CheckpointPlan *plans, int nLanes, float *accumDevice, cudaStream_t stream)
 {
     const DScene &s = ctx->scene;
-    PathBuffers pb = ctx->paths; // by value: the current / next buffers swap after every bounce
-    BounceCounters *cnt = ctx->counters;
-    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(BounceCounters), stream));
-    const uint32_t nPaths = wp.nPixels * wp.sppWave;
-    unsigned long long *work = ctx->totals + 2;
-    {
-        StageTimer t(ctx, stream, STAGE_OTHER);
-        generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    struct LaneState { PathBuffers pb; BounceCounters *cnt; cudaStream_t stream, shadowStream; cudaEvent_t shadeDone, shadowDone; };
+    LaneState lanes[PTC_MAX_LANES];
+    if (nLanes > 1) {
+        const int rc = ensureLanes(ctx, nLanes);
+        if (rc) { return rc; }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->laneFork, stream)); // the other lanes start behind whatever the caller's stream holds so far
     }
-    ctx->launches++;
+    size_t offset = 0;
+    for (int i = 0; i < nLanes; i++) {
+        LaneState &l = lanes[i];
+        l.pb = laneBuffers(ctx->paths, offset); // by value: the current / next buffers swap after every bounce
+        offset += (size_t)wps[i].nPixels * wps[i].sppWave;
+        if (i == 0) { l.cnt = ctx->counters; l.stream = stream; l.shadowStream = ctx->shadowStream; l.shadeDone = ctx->shadeDone; l.shadowDone = ctx->shadowDone; }
+        else {
+            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
+            l.cnt = x.counters; l.stream = x.stream; l.shadowStream = x.shadowStream; l.shadeDone = x.shadeDone; l.shadowDone = x.shadowDone;
+            CUDA_TRY(ctx, cudaStreamWaitEvent(l.stream, ctx->laneFork, 0));
+        }
+        CUDA_TRY(ctx, cudaMemsetAsync(l.cnt, 0, CNT_STRIDE * sizeof(BounceCounters), l.stream));
+        const uint32_t nPaths = wps[i].nPixels * wps[i].sppWave;
+        {
+            StageTimer t(ctx, l.stream, STAGE_OTHER);
+            generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, l.stream>>>(s, l.pb, wps[i], l.cnt);
+        }
+        ctx->launches++;
+    }
+    unsigned long long *work = ctx->totals + 2;
+    const int lastBounce = wps[0].lastBounce;
     // ray k leaves vertex k (k = 0: camera ray).  Ray k feeds direct() of vertex k and creates vertex k + 1, so rays
     // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
-    for (int k = 0; k <= wp.lastBounce; k++) {
-        BounceCounters *bc = cnt + k;
-        // shadow rays cast at vertex k (queued by material(k - 1)) go to the second stream, behind everything enqueued so far
-        const bool overlap = ctx->overlapShadow && k > 0;
-        cudaStream_t shadowOn = overlap ? ctx->shadowStream : stream;
-        if (overlap) {
-            CUDA_TRY(ctx, cudaEventRecord(ctx->shadeDone, stream));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->shadowStream, ctx->shadeDone, 0));
+    for (int k = 0; k <= lastBounce; k++) {
+        for (int i = 0; i < nLanes; i++) {
+            LaneState &l = lanes[i];
+            const WaveParams &wp = wps[i];
+            PathBuffers &pb = l.pb;
+            cudaStream_t stream = l.stream;
+            BounceCounters *bc = l.cnt + k;
+            // shadow rays cast at vertex k (queued by material(k - 1)) go to the second stream, behind everything enqueued so far
+            const bool overlap = ctx->overlapShadow && k > 0;
+            cudaStream_t shadowOn = overlap ? l.shadowStream : stream;
+            if (overlap) {
+                CUDA_TRY(ctx, cudaEventRecord(l.shadeDone, stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(l.shadowStream, l.shadeDone, 0));
+            }
+            {
+                StageTimer t(ctx, stream, STAGE_EXTEND);
+                // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
+                if (s.bvh.placements) { traverseKernel<false, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+                else if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            }
+            if (k > 0) {
+                StageTimer t(ctx, shadowOn, STAGE_SHADOW);
+                if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+            }
+            if (overlap) { // the logic stage reads the occlusion bytes
+                CUDA_TRY(ctx, cudaEventRecord(l.shadowDone, l.shadowStream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(stream, l.shadowDone, 0));
+            }
+            {
+                StageTimer t(ctx, stream, STAGE_SHADE);
+                logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, k);
+                if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
+                const int g = ctx->gridShade;
+                if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+                if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
+            }
+            ctx->launches += k > 0 ? 3 : 2;
+            // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
+            std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
         }
-        {
-            StageTimer t(ctx, stream, STAGE_EXTEND);
-            // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
-            if (s.bvh.placements) { traverseKernel<false, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-            else if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-            else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-        }
-        if (k > 0) {
-            StageTimer t(ctx, shadowOn, STAGE_SHADOW);
-            if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-        }
-        if (overlap) { // the logic stage reads the occlusion bytes
-            CUDA_TRY(ctx, cudaEventRecord(ctx->shadowDone, ctx->shadowStream));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->shadowDone, 0));
-        }
-        {
-            StageTimer t(ctx, stream, STAGE_SHADE);
-            logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, k);
-            if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
-            const int g = ctx->gridShade;
-            if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-        }
-        ctx->launches += k > 0 ? 3 : 2;
-        // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
-        std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
     }
     { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
-    {
+    // radianceLookup += in sample order: the lanes' samples are added one lane after the other on the caller's stream
+    for (int i = 0; i < nLanes; i++) {
+        if (i > 0) {
+            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
+            CUDA_TRY(ctx, cudaEventRecord(x.done, x.stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, x.done, 0));
+        }
         StageTimer t(ctx, stream, STAGE_OTHER);
-        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
-        tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+        accumulateKernel<<<std::min<uint32_t>((wps[i].nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(lanes[i].pb, wps[i], accumDevice, (uint32_t)s.width, (uint32_t)s.height, plans[i]);
+        tallyKernel<<<1, 32, 0, stream>>>(lanes[i].cnt, ctx->totals);
+        ctx->launches += 2;
     }
-    ctx->launches += 2;
     if (ctx->pending.size() > 4096) { collectTimings(ctx); }
     CUDA_TRY(ctx, cudaGetLastError());
     return PTC_OK;
@@ -2150,7 +2229,17 @@ static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uin
             if ((rc = launchVolumeWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
             continue;
         }
-        if ((rc = launchWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
+        // lanes: consecutive blocks of the wave's samples (the stage and traversal counters describe one launch sequence at a time)
+        const int nLanes = (ctx->stageTiming || ctx->countTraversal) ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->lanes, wp.sppWave);
+        WaveParams wps[PTC_MAX_LANES]; CheckpointPlan plans[PTC_MAX_LANES];
+        const uint32_t perLane = (wp.sppWave + (uint32_t)nLanes - 1) / (uint32_t)nLanes;
+        int used = 0;
+        for (uint32_t at = 0; at < wp.sppWave; at += perLane, used++) {
+            WaveParams &w = wps[used]; w = wp;
+            w.firstSample = wp.firstSample + at; w.sppWave = std::min(perLane, wp.sppWave - at); w.groupShift = groupShiftFor(w.sppWave);
+            plans[used] = planFor(checkpoints, w.firstSample, w.sppWave, done == 0 && at == 0, done + sppWave >= nSpp && at + perLane >= wp.sppWave);
+        }
+        if ((rc = launchWave(ctx, wps, plans, used, accumDevice, stream))) { return rc; }
     }
     ctx->samples += (uint64_t)nPixels * nSpp;
     return PTC_OK;
@@ -2609,6 +2698,10 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
     if (!strcmp(name, "overlap_shadow")) { ctx->overlapShadow = value != 0; return PTC_OK; }
+    if (!strcmp(name, "lanes")) { // part-waves traced side by side (ptc_ctx::lanes)
+        if (value < 1 || value > PTC_MAX_LANES) { CTX_FAIL(ctx, PTC_ERR_INVALID, "lanes must be in [1, %d]", PTC_MAX_LANES); }
+        ctx->lanes = (int)value; return PTC_OK;
+    }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }
     if (!strcmp(name, "volume_megakernel")) { ctx->volumeMegakernel = value != 0; return PTC_OK; }
     if (!strcmp(name, "bvh_builder")) { // before ptc_commit; 1 = device (default), 0 = host binned SAH

@@ -106,11 +106,16 @@ def test_framebuffer_gather_sums_contexts_and_resolves():
     assert not a.framebuffer_gather([], divisor=1).any()
 
 
-def test_checkpoint_snapshots_equal_renders_that_stopped_there():
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_checkpoint_snapshots_equal_renders_that_stopped_there(lanes):
     """ptc_framebuffer_render_checkpoints: the K7 resolve keeps the running sums after 1, 2, 4, 8 of a 12-sample wave -- the very
     floats of renders that ended there (src/integrator.cpp:87-92 without ending waves at the checkpoints); with the samples split
-    over two contexts a checkpoint is the sum of both contexts' snapshots, also where it lies outside a context's block"""
-    fresh = lambda: load_scene("scenes/cornell-glass.json", 40, 40)
+    over two contexts a checkpoint is the sum of both contexts' snapshots, also where it lies outside a context's block.
+    lanes = 3: the wave is traced as three part-waves of 4 samples (ptc_set_option("lanes")), the checkpoints fall inside and between them"""
+    def fresh():
+        ctx = load_scene("scenes/cornell-glass.json", 40, 40)
+        ctx.set_option("lanes", lanes)
+        return ctx
     counts = [1, 2, 4, 8]
     a = fresh()
     a.framebuffer_clear()
