@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--paths-per-wave", type=int, default=0, help="override the library's wave size (paths resident per wave)")
     ap.add_argument("--bvh-builder", type=int, default=1, choices=[0, 1], help="1: device builder (default), 0: host binned-SAH builder")
+    ap.add_argument("--lanes", type=int, default=0, help="part-waves traced side by side (ptc_set_option lanes); 0: the library's choice per wave")
     args = ap.parse_args()
     args.spp_per_step_given = args.spp_per_step is not None
     if args.spp_per_step is None:
@@ -264,6 +265,8 @@ def main():
     tst0 = ctx.stats()
     if args.paths_per_wave:
         ctx.set_option("paths_per_wave", args.paths_per_wave)
+    if args.lanes:
+        ctx.set_option("lanes", args.lanes)
     n_pix = width * height
     local = torch.zeros(height * width * 3, dtype=torch.float32, device="cuda")    # this rank's cumulative radianceLookup
     staging = torch.zeros_like(local) if distributed else None                     # what the per-step reduce works on
@@ -494,6 +497,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "setup": {"scene_build_s": build_s,
+                      "lanes": args.lanes or "chosen per wave: 4 part-waves side by side for waves of <= 2^25 paths, else 2 (stage / counter passes: 1)",
                       "bvh_build": {"builder": "device (Morton sort + PLOC + wide collapse kernels)" if tst0.bvh_builder else "host binned SAH",
                                     "ms": tst0.bvh_build_ms, "ms_second_build_in_process": warm_build_ms, "triangles": tst0.bvh_triangles, "nodes": tst0.bvh_nodes, "depth": tst0.bvh_depth}},
             "mrays_per_s": rays * world / (ms * 1e-3) * 1e-6, "rays_per_sample": rays / (samples_total / world),

@@ -308,12 +308,15 @@ int ptc_num_lights(ptc_ctx *ctx, uint32_t *out); /* Scene::lights().size() */
 int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out);
 int ptc_reset_stats(ptc_ctx *ctx);
 /* queue sizes of the most recent wave: extend_counts[k] = rays that left vertex k (k = 0: camera rays), shadow_counts[k] =
- * NEE shadow rays cast at vertex k; up to `capacity` (<= PTC_MAX_BOUNCES + 2) entries each */
+ * NEE shadow rays cast at vertex k; up to `capacity` (<= PTC_MAX_BOUNCES + 2) entries each (of the wave's first lane when it was
+ * traced as several, see "lanes") */
 int ptc_get_wave_counts(ptc_ctx *ctx, uint32_t *extend_counts, uint32_t *shadow_counts, uint32_t capacity);
 int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value); /* "stage_timing", "count_traversal", "paths_per_wave",
                                                                       "overlap_shadow", "bvh_builder" (before ptc_commit: 1 device,
                                                                       0 host), "volume_megakernel" (1: VolumePathTracer as one
-                                                                      thread per path instead of wavefront stages) */
+                                                                      thread per path instead of wavefront stages), "lanes" (a
+                                                                      wave traced as n part-waves side by side on n streams; 0,
+                                                                      the default: chosen per wave; the image does not depend on n) */
 /* scalar reference traversal of the device BVH on the host side of the library: counts inner-node
  * visits and triangle tests per ray (algorithmic bytes per ray) */
 int ptc_count_traversal(ptc_ctx *ctx, const ptc_ray *rays, uint32_t n, uint64_t *inner_visits, uint64_t *triangle_tests);

@@ -1089,6 +1089,7 @@ struct ptc_ctx {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int numSMs = 148;
     int gridTraverse = 0, gridShade = 0, gridLogic = 0, gridSimple = 0;
+    int gridTraverseShared = 0, gridVolumeTraverseShared = 0; // traversal grids of a wave traced as several lanes: two CTAs per SM fewer
     // options / stats
     int64_t pathsPerWave = 1 << 26; // 67 M paths x 156 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
                                     // keep 148 SMs busy; measured 648 vs 613 Msamples/s against 2^24 on the dragon workload, 653 with 2^27
@@ -1102,7 +1103,7 @@ struct ptc_ctx {
     // slots idle) another lane's rays are in a traversal stage (issue-bound, hardly any DRAM traffic), and the SMs hold CTAs of both.
     // Lane 0 runs on the caller's stream; the samples are still added to the image in sample order (launchWave), so the result does
     // not depend on the number of lanes.
-    int lanes = 1;
+    int lanes = 0; // 0 = chosen per wave (renderInternal)
     struct Lane { cudaStream_t stream = nullptr, shadowStream = nullptr; cudaEvent_t shadeDone = nullptr, shadowDone = nullptr, done = nullptr; BounceCounters *counters = nullptr; };
     std::vector<Lane> extraLanes; // lanes 1 ..
     cudaEvent_t laneFork = nullptr;
@@ -1216,9 +1217,12 @@ int ptc_create(int device, ptc_ctx **out)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, volumeMaterialKernel<PTC_PLASTIC>, 128, 0);
     ctx->gridVolumeShade = ctx->numSMs * std::max(perSM, 1);
     ctx->gridSimple = ctx->numSMs * 8;
+    ctx->gridTraverseShared = std::max(ctx->numSMs, ctx->gridTraverse - 2 * ctx->numSMs);
+    ctx->gridVolumeTraverseShared = std::max(ctx->numSMs, ctx->gridVolumeTraverse - 2 * ctx->numSMs);
     // tuning hooks (tools/sweep_lanes.sh): number of interleaved lanes and CTAs per SM of the persistent grids
-    if (const char *e = getenv("PTC_LANES")) { ctx->lanes = std::min(PTC_MAX_LANES, std::max(1, atoi(e))); }
-    if (const char *e = getenv("PTC_TRAVERSE_PER_SM")) { ctx->gridTraverse = ctx->numSMs * std::max(1, atoi(e)); }
+    if (const char *e = getenv("PTC_LANES")) { ctx->lanes = std::min(PTC_MAX_LANES, std::max(0, atoi(e))); }
+    if (const char *e = getenv("PTC_TRAVERSE_PER_SM")) { ctx->gridTraverse = ctx->gridTraverseShared = ctx->numSMs * std::max(1, atoi(e)); }
+    if (const char *e = getenv("PTC_VOLUME_TRAVERSE_PER_SM")) { ctx->gridVolumeTraverse = ctx->gridVolumeTraverseShared = ctx->numSMs * std::max(1, atoi(e)); }
     if (const char *e = getenv("PTC_LOGIC_PER_SM")) { ctx->gridLogic = ctx->numSMs * std::max(1, atoi(e)); }
     if (const char *e = getenv("PTC_SHADE_PER_SM")) { ctx->gridShade = ctx->numSMs * std::max(1, atoi(e)); }
     *out = ctx;
@@ -1828,7 +1832,7 @@ int ptc_replicate(ptc_ctx *src, int device, ptc_ctx **out)
     memcpy(dst->bvh.sceneLo, src->bvh.sceneLo, sizeof(dst->bvh.sceneLo)); memcpy(dst->bvh.sceneHi, src->bvh.sceneHi, sizeof(dst->bvh.sceneHi));
     dst->bvhNodeCount = src->bvhNodeCount; dst->bvhTriangleCount = src->bvhTriangleCount; dst->hostBvhFetched = false;
     dst->nLights = src->nLights; dst->classMask = src->classMask;
-    dst->pathsPerWave = src->pathsPerWave; dst->stageTiming = src->stageTiming; dst->countTraversal = src->countTraversal; dst->volumeMegakernel = src->volumeMegakernel;
+    dst->pathsPerWave = src->pathsPerWave; dst->stageTiming = src->stageTiming; dst->countTraversal = src->countTraversal; dst->volumeMegakernel = src->volumeMegakernel; dst->lanes = src->lanes;
     dst->bvhBuilder = src->bvhBuilder; dst->bvhBuildMs = 0.f; dst->bvhPlocIterations = src->bvhPlocIterations;
     dst->deviceMaterials = src->deviceMaterials;
     dst->scene = src->scene;
@@ -1963,111 +1967,14 @@ static int ensureLanes(ptc_ctx *ctx, int lanes)
     return PTC_OK;
 }
 
-// One wave = fixed launch sequence; all queue sizes stay on the device.  The wave's samples are traced as nLanes part-waves (wps[i]:
-// consecutive sample blocks, plans[i]: the checkpoints that fall into them) whose launch sequences are issued bounce by bounce on one
-// stream per lane, so that the stages of different lanes share the SMs (ptc_ctx::lanes); nLanes = 1 is the plain sequence.
-static int launchWave(ptc_ctx *ctx, const WaveParams *wps, const CheckpointPlan *plans, int nLanes, float *accumDevice, cudaStream_t stream)
+static VolumeBuffers laneVolumeBuffers(const VolumeBuffers &all, size_t offset)
 {
-    const DScene &s = ctx->scene;
-    struct LaneState { PathBuffers pb; BounceCounters *cnt; cudaStream_t stream, shadowStream; cudaEvent_t shadeDone, shadowDone; };
-    LaneState lanes[PTC_MAX_LANES];
-    if (nLanes > 1) {
-        const int rc = ensureLanes(ctx, nLanes);
-        if (rc) { return rc; }
-        CUDA_TRY(ctx, cudaEventRecord(ctx->laneFork, stream)); // the other lanes start behind whatever the caller's stream holds so far
-    }
-    size_t offset = 0;
-    for (int i = 0; i < nLanes; i++) {
-        LaneState &l = lanes[i];
-        l.pb = laneBuffers(ctx->paths, offset); // by value: the current / next buffers swap after every bounce
-        offset += (size_t)wps[i].nPixels * wps[i].sppWave;
-        if (i == 0) { l.cnt = ctx->counters; l.stream = stream; l.shadowStream = ctx->shadowStream; l.shadeDone = ctx->shadeDone; l.shadowDone = ctx->shadowDone; }
-        else {
-            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
-            l.cnt = x.counters; l.stream = x.stream; l.shadowStream = x.shadowStream; l.shadeDone = x.shadeDone; l.shadowDone = x.shadowDone;
-            CUDA_TRY(ctx, cudaStreamWaitEvent(l.stream, ctx->laneFork, 0));
-        }
-        CUDA_TRY(ctx, cudaMemsetAsync(l.cnt, 0, CNT_STRIDE * sizeof(BounceCounters), l.stream));
-        const uint32_t nPaths = wps[i].nPixels * wps[i].sppWave;
-        {
-            StageTimer t(ctx, l.stream, STAGE_OTHER);
-            generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, l.stream>>>(s, l.pb, wps[i], l.cnt);
-        }
-        ctx->launches++;
-    }
-    unsigned long long *work = ctx->totals + 2;
-    const int lastBounce = wps[0].lastBounce;
-    // ray k leaves vertex k (k = 0: camera ray).  Ray k feeds direct() of vertex k and creates vertex k + 1, so rays
-    // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
-    for (int k = 0; k <= lastBounce; k++) {
-        for (int i = 0; i < nLanes; i++) {
-            LaneState &l = lanes[i];
-            const WaveParams &wp = wps[i];
-            PathBuffers &pb = l.pb;
-            cudaStream_t stream = l.stream;
-            BounceCounters *bc = l.cnt + k;
-            // shadow rays cast at vertex k (queued by material(k - 1)) go to the second stream, behind everything enqueued so far
-            const bool overlap = ctx->overlapShadow && k > 0;
-            cudaStream_t shadowOn = overlap ? l.shadowStream : stream;
-            if (overlap) {
-                CUDA_TRY(ctx, cudaEventRecord(l.shadeDone, stream));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(l.shadowStream, l.shadeDone, 0));
-            }
-            {
-                StageTimer t(ctx, stream, STAGE_EXTEND);
-                // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue
-                if (s.bvh.placements) { traverseKernel<false, false, false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-                else if (ctx->countTraversal) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-            }
-            if (k > 0) {
-                StageTimer t(ctx, shadowOn, STAGE_SHADOW);
-                if (s.bvh.placements) { traverseKernel<true, false, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-                else if (s.hasFilter) { traverseKernel<true, false, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-                else if (ctx->countTraversal) { traverseKernel<true, true><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-                else { traverseKernel<true, false><<<ctx->gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
-            }
-            if (overlap) { // the logic stage reads the occlusion bytes
-                CUDA_TRY(ctx, cudaEventRecord(l.shadowDone, l.shadowStream));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(stream, l.shadowDone, 0));
-            }
-            {
-                StageTimer t(ctx, stream, STAGE_SHADE);
-                logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, k);
-                if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
-                const int g = ctx->gridShade;
-                if (ctx->classMask & (1u << PTC_LAMBERTIAN)) { materialKernel<PTC_LAMBERTIAN><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_OREN_NAYAR)) { materialKernel<PTC_OREN_NAYAR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_MIRROR)) { materialKernel<PTC_MIRROR><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_GLASS)) { materialKernel<PTC_GLASS><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_MICROFACET)) { materialKernel<PTC_MICROFACET><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_PLASTIC)) { materialKernel<PTC_PLASTIC><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-                if (ctx->classMask & (1u << PTC_PASSTHROUGH)) { materialKernel<PTC_PASSTHROUGH><<<g, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
-            }
-            ctx->launches += k > 0 ? 3 : 2;
-            // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
-            std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
-        }
-    }
-    { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
-    // radianceLookup += in sample order: the lanes' samples are added one lane after the other on the caller's stream
-    for (int i = 0; i < nLanes; i++) {
-        if (i > 0) {
-            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
-            CUDA_TRY(ctx, cudaEventRecord(x.done, x.stream));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, x.done, 0));
-        }
-        StageTimer t(ctx, stream, STAGE_OTHER);
-        accumulateKernel<<<std::min<uint32_t>((wps[i].nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(lanes[i].pb, wps[i], accumDevice, (uint32_t)s.width, (uint32_t)s.height, plans[i]);
-        tallyKernel<<<1, 32, 0, stream>>>(lanes[i].cnt, ctx->totals);
-        ctx->launches += 2;
-    }
-    if (ctx->pending.size() > 4096) { collectTimings(ctx); }
-    CUDA_TRY(ctx, cudaGetLastError());
-    return PTC_OK;
+    VolumeBuffers vb = all;
+    if (vb.probeHit) { vb.probeHit += offset; vb.shadowTr += offset; vb.scatter += 3 * offset; vb.scatterTr += offset; vb.extendQueue += offset; vb.scatterQueue += offset; }
+    return vb;
 }
 
-// VolumePathTracer, wavefront form (volume_wavefront.cuh): the launch sequence of one wave
+// VolumePathTracer, wavefront form (volume_wavefront.cuh)
 static int ensureVolumeBuffers(ptc_ctx *ctx, uint32_t capacity)
 {
     if (capacity <= ctx->volumeBufferCapacity) { return PTC_OK; }
@@ -2084,86 +1991,141 @@ static int ensureVolumeBuffers(ptc_ctx *ctx, uint32_t capacity)
     return PTC_OK;
 }
 
+#define LAUNCH_MATERIAL(TYPE) \
+    if (ctx->classMask & (1u << TYPE)) { materialKernel<TYPE><<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc, bc + 1); ctx->launches++; }
 #define LAUNCH_VOLUME_MATERIAL(TYPE) \
     if (ctx->classMask & (1u << TYPE)) { volumeMaterialKernel<TYPE><<<ctx->gridVolumeShade, 128, 0, stream>>>(s, pb, vb, wp, bc, bc + 1); ctx->launches++; }
 
-static int launchVolumeWave(ptc_ctx *ctx, const WaveParams &wp, float *accumDevice, cudaStream_t stream, const CheckpointPlan &plan)
+// One wave = fixed launch sequence; all queue sizes stay on the device.  The wave's samples are traced as nLanes part-waves (wps[i]:
+// consecutive sample blocks, plans[i]: the checkpoints that fall into them) whose launch sequences are issued bounce by bounce on one
+// stream per lane, so that the stages of different lanes share the SMs (ptc_ctx::lanes); nLanes = 1 is the plain sequence.
+// volume: the VolumePathTracer's stages (volume_wavefront.cuh) -- merged probe / continuation rays, two kinds of shadow rays, its own
+// logic and material kernels; bounce 0 is the PathTracer's.
+static int launchWave(ptc_ctx *ctx, const WaveParams *wps, const CheckpointPlan *plans, int nLanes, float *accumDevice, cudaStream_t callerStream, bool volume)
 {
     const DScene &s = ctx->scene;
-    PathBuffers pb = ctx->paths;
-    const VolumeBuffers &vb = ctx->volumeBuffers;
-    BounceCounters *cnt = ctx->counters;
-    CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(BounceCounters), stream));
-    const uint32_t nPaths = wp.nPixels * wp.sppWave;
-    unsigned long long *work = ctx->totals + 2;
-    const bool count = ctx->countTraversal;
-    {
-        StageTimer t(ctx, stream, STAGE_OTHER);
-        generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(s, pb, wp, cnt);
+    struct LaneState { PathBuffers pb; VolumeBuffers vb; BounceCounters *cnt; cudaStream_t stream, shadowStream; cudaEvent_t shadeDone, shadowDone; };
+    LaneState lanes[PTC_MAX_LANES];
+    if (nLanes > 1) {
+        const int rc = ensureLanes(ctx, nLanes);
+        if (rc) { return rc; }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->laneFork, callerStream)); // the other lanes start behind whatever the caller's stream holds so far
     }
-    ctx->launches++;
-    for (int k = 0; k <= wp.lastBounce; k++) {
-        BounceCounters *bc = cnt + k;
-        // both kinds of shadow rays of bounce k go to the second stream, next to the bounce's merged rays (as in launchWave)
-        const bool overlap = ctx->overlapShadow && k > 0;
-        cudaStream_t shadowOn = overlap ? ctx->shadowStream : stream;
-        if (overlap) {
-            CUDA_TRY(ctx, cudaEventRecord(ctx->shadeDone, stream));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->shadowStream, ctx->shadeDone, 0));
+    // lanes share the SMs: the persistent traversal grids leave room for the CTAs of another lane's stage (profiles/r02_sweep_lanes.txt)
+    const int gridTraverse = nLanes > 1 ? ctx->gridTraverseShared : ctx->gridTraverse;
+    const int gridVolumeTraverse = nLanes > 1 ? ctx->gridVolumeTraverseShared : ctx->gridVolumeTraverse;
+    size_t offset = 0;
+    for (int i = 0; i < nLanes; i++) {
+        LaneState &l = lanes[i];
+        l.pb = laneBuffers(ctx->paths, offset); // by value: the current / next buffers swap after every bounce
+        l.vb = laneVolumeBuffers(ctx->volumeBuffers, offset);
+        offset += (size_t)wps[i].nPixels * wps[i].sppWave;
+        if (i == 0) { l.cnt = ctx->counters; l.stream = callerStream; l.shadowStream = ctx->shadowStream; l.shadeDone = ctx->shadeDone; l.shadowDone = ctx->shadowDone; }
+        else {
+            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
+            l.cnt = x.counters; l.stream = x.stream; l.shadowStream = x.shadowStream; l.shadeDone = x.shadeDone; l.shadowDone = x.shadowDone;
+            CUDA_TRY(ctx, cudaStreamWaitEvent(l.stream, ctx->laneFork, 0));
         }
+        CUDA_TRY(ctx, cudaMemsetAsync(l.cnt, 0, CNT_STRIDE * sizeof(BounceCounters), l.stream));
+        const uint32_t nPaths = wps[i].nPixels * wps[i].sppWave;
         {
-            StageTimer t(ctx, stream, STAGE_EXTEND);
-            if (k == 0) { // camera rays: Scene::testIntersect, every slot
-                if (count) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
-            } else if (s.hasFilter) { // probe + continuation ray in one traversal
-                if (count) { volumeTraverseKernel<VOL_EXTEND, true><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
-                else { volumeTraverseKernel<VOL_EXTEND, false><<<ctx->gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
-            } else {                  // no container surface: the two rules coincide
-                if (count) { traverseKernel<false, true><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
-                else { traverseKernel<false, false><<<ctx->gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
-            }
+            StageTimer t(ctx, l.stream, STAGE_OTHER);
+            generateKernel<<<std::min<uint32_t>((nPaths + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, l.stream>>>(s, l.pb, wps[i], l.cnt);
         }
         ctx->launches++;
-        if (k > 0) {
-            StageTimer t(ctx, shadowOn, STAGE_SHADOW);
-            if (count) {
-                volumeTraverseKernel<VOL_SHADOW, true><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
-                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, true><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
-            } else {
-                volumeTraverseKernel<VOL_SHADOW, false><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
-                if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, false><<<ctx->gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+    }
+    unsigned long long *work = ctx->totals + 2;
+    const bool count = ctx->countTraversal;
+    const int lastBounce = wps[0].lastBounce;
+    // ray k leaves vertex k (k = 0: camera ray).  Ray k feeds direct() of vertex k and creates vertex k + 1, so rays
+    // 0 .. lastBounce are traced; shadow rays cast at vertex k are traced alongside ray k.
+    for (int k = 0; k <= lastBounce; k++) {
+        for (int i = 0; i < nLanes; i++) {
+            LaneState &l = lanes[i];
+            const WaveParams &wp = wps[i];
+            PathBuffers &pb = l.pb;
+            const VolumeBuffers &vb = l.vb;
+            cudaStream_t stream = l.stream;
+            BounceCounters *bc = l.cnt + k;
+            // shadow rays cast at vertex k (queued by material(k - 1)) go to the second stream, behind everything enqueued so far
+            const bool overlap = ctx->overlapShadow && k > 0;
+            cudaStream_t shadowOn = overlap ? l.shadowStream : stream;
+            if (overlap) {
+                CUDA_TRY(ctx, cudaEventRecord(l.shadeDone, stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(l.shadowStream, l.shadeDone, 0));
             }
-            ctx->launches += s.nMedia ? 2 : 1;
-        }
-        if (overlap) { // the logic stage reads the shadow outcomes
-            CUDA_TRY(ctx, cudaEventRecord(ctx->shadowDone, ctx->shadowStream));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->shadowDone, 0));
-        }
-        {
-            StageTimer t(ctx, stream, STAGE_SHADE);
-            if (k == 0) { // SampleIntegrator::samplePixel's own terms, as in the PathTracer wavefront
-                logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, 0);
-                if (s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
-            } else { volumeLogicKernel<<<ctx->gridVolumeLogic, 256, 0, stream>>>(s, pb, vb, wp, bc, ctx->classMask); }
+            {
+                StageTimer t(ctx, stream, STAGE_EXTEND);
+                if (volume && k > 0) {
+                    if (s.hasFilter) { // probe + continuation ray in one traversal
+                        if (count) { volumeTraverseKernel<VOL_EXTEND, true><<<gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                        else { volumeTraverseKernel<VOL_EXTEND, false><<<gridVolumeTraverse, 128, 0, stream>>>(s, pb, vb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                    } else {           // no container surface: the two rules coincide
+                        if (count) { traverseKernel<false, true><<<gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                        else { traverseKernel<false, false><<<gridTraverse, 128, 0, stream>>>(s, pb, vb.extendQueue, &bc->extendCount, &bc->extendCursor, work); }
+                    }
+                }
+                // the rays of bounce k are the current buffers' slots 0 .. extendCount - 1: no queue (camera rays of either integrator: Scene::testIntersect)
+                else if (s.bvh.placements) { traverseKernel<false, false, false, true><<<gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+                else if (count) { traverseKernel<false, true><<<gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+                else { traverseKernel<false, false><<<gridTraverse, 128, 0, stream>>>(s, pb, nullptr, &bc->extendCount, &bc->extendCursor, work); }
+            }
             ctx->launches++;
-            LAUNCH_VOLUME_MATERIAL(PTC_LAMBERTIAN)
-            LAUNCH_VOLUME_MATERIAL(PTC_OREN_NAYAR)
-            LAUNCH_VOLUME_MATERIAL(PTC_MIRROR)
-            LAUNCH_VOLUME_MATERIAL(PTC_GLASS)
-            LAUNCH_VOLUME_MATERIAL(PTC_MICROFACET)
-            LAUNCH_VOLUME_MATERIAL(PTC_PLASTIC)
-            LAUNCH_VOLUME_MATERIAL(PTC_PASSTHROUGH)
+            if (k > 0 && volume) { // both kinds of shadow rays of bounce k, next to the bounce's merged rays
+                StageTimer t(ctx, shadowOn, STAGE_SHADOW);
+                if (count) {
+                    volumeTraverseKernel<VOL_SHADOW, true><<<gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                    if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, true><<<gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+                } else {
+                    volumeTraverseKernel<VOL_SHADOW, false><<<gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2);
+                    if (s.nMedia) { volumeTraverseKernel<VOL_SCATTER, false><<<gridVolumeTraverse, 128, 0, shadowOn>>>(s, pb, vb, vb.scatterQueue, &bc->scatterCount, &bc->scatterCursor, work + 2); }
+                }
+                ctx->launches += s.nMedia ? 2 : 1;
+            } else if (k > 0) {
+                StageTimer t(ctx, shadowOn, STAGE_SHADOW);
+                if (s.bvh.placements) { traverseKernel<true, false, false, true><<<gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else if (s.hasFilter) { traverseKernel<true, false, true><<<gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else if (count) { traverseKernel<true, true><<<gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                else { traverseKernel<true, false><<<gridTraverse, 128, 0, shadowOn>>>(s, pb, pb.shadowQueue, &bc->shadowCount, &bc->shadowCursor, work + 2); }
+                ctx->launches++;
+            }
+            if (overlap) { // the logic stage reads the occlusion bytes / shadow outcomes
+                CUDA_TRY(ctx, cudaEventRecord(l.shadowDone, l.shadowStream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(stream, l.shadowDone, 0));
+            }
+            {
+                StageTimer t(ctx, stream, STAGE_SHADE);
+                if (volume && k > 0) { volumeLogicKernel<<<ctx->gridVolumeLogic, 256, 0, stream>>>(s, pb, vb, wp, bc, ctx->classMask); }
+                else { // k = 0 of the VolumePathTracer: SampleIntegrator::samplePixel's own terms, as in the PathTracer wavefront
+                    logicKernel<<<ctx->gridLogic, 256, 0, stream>>>(s, pb, wp, bc, ctx->classMask, k);
+                    if (k == 0 && s.hasFilter) { containerKernel<<<ctx->gridShade, 128, 0, stream>>>(s, pb, wp, bc); ctx->launches++; }
+                }
+                ctx->launches++;
+                if (volume) {
+                    LAUNCH_VOLUME_MATERIAL(PTC_LAMBERTIAN) LAUNCH_VOLUME_MATERIAL(PTC_OREN_NAYAR) LAUNCH_VOLUME_MATERIAL(PTC_MIRROR) LAUNCH_VOLUME_MATERIAL(PTC_GLASS)
+                    LAUNCH_VOLUME_MATERIAL(PTC_MICROFACET) LAUNCH_VOLUME_MATERIAL(PTC_PLASTIC) LAUNCH_VOLUME_MATERIAL(PTC_PASSTHROUGH)
+                } else {
+                    LAUNCH_MATERIAL(PTC_LAMBERTIAN) LAUNCH_MATERIAL(PTC_OREN_NAYAR) LAUNCH_MATERIAL(PTC_MIRROR) LAUNCH_MATERIAL(PTC_GLASS)
+                    LAUNCH_MATERIAL(PTC_MICROFACET) LAUNCH_MATERIAL(PTC_PLASTIC) LAUNCH_MATERIAL(PTC_PASSTHROUGH)
+                }
+            }
+            // the material stage moved every surviving path to its slot of bounce k + 1 in the `next` buffers
+            std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
         }
-        std::swap(pb.ray, pb.nRay); std::swap(pb.modThr, pb.nModThr); std::swap(pb.result, pb.nResult);
     }
     { const int rcUpload = runBeforeAccumulate(ctx); if (rcUpload) { return rcUpload; } }
-    {
-        StageTimer t(ctx, stream, STAGE_OTHER);
-        accumulateKernel<<<std::min<uint32_t>((wp.nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, stream>>>(pb, wp, accumDevice, (uint32_t)s.width, (uint32_t)s.height, plan);
-        tallyKernel<<<1, 32, 0, stream>>>(cnt, ctx->totals);
+    // radianceLookup += in sample order: the lanes' samples are added one lane after the other on the caller's stream
+    for (int i = 0; i < nLanes; i++) {
+        if (i > 0) {
+            const ptc_ctx::Lane &x = ctx->extraLanes[(size_t)i - 1];
+            CUDA_TRY(ctx, cudaEventRecord(x.done, x.stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(callerStream, x.done, 0));
+        }
+        StageTimer t(ctx, callerStream, STAGE_OTHER);
+        accumulateKernel<<<std::min<uint32_t>((wps[i].nPixels + 255) / 256, (uint32_t)ctx->gridSimple * 4), 256, 0, callerStream>>>(lanes[i].pb, wps[i], accumDevice, (uint32_t)s.width, (uint32_t)s.height, plans[i]);
+        tallyKernel<<<1, 32, 0, callerStream>>>(lanes[i].cnt, ctx->totals);
+        ctx->launches += 2;
     }
-    ctx->launches += 2;
     if (ctx->pending.size() > 4096) { collectTimings(ctx); }
     CUDA_TRY(ctx, cudaGetLastError());
     return PTC_OK;
@@ -2225,12 +2187,11 @@ static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uin
         WaveParams wp;
         wp.seed = seed; wp.firstSample = firstSample + done; wp.sppWave = std::min(sppWave, nSpp - done); wp.nPixels = nPixels; wp.groupShift = groupShiftFor(wp.sppWave);
         wp.startBounce = start; wp.lastBounce = last;
-        if (volume) {
-            if ((rc = launchVolumeWave(ctx, wp, accumDevice, stream, planFor(checkpoints, wp.firstSample, wp.sppWave, done == 0, done + sppWave >= nSpp)))) { return rc; }
-            continue;
-        }
-        // lanes: consecutive blocks of the wave's samples (the stage and traversal counters describe one launch sequence at a time)
-        const int nLanes = (ctx->stageTiming || ctx->countTraversal) ? 1 : (int)std::min<uint32_t>((uint32_t)ctx->lanes, wp.sppWave);
+        // lanes: consecutive blocks of the wave's samples.  Two lanes, four when the wave is small (measured on five scenes,
+        // profiles/r02_sweep_lanes.txt); one while a stage or traversal counter pass describes one launch sequence at a time
+        int nLanes = ctx->lanes > 0 ? ctx->lanes : ((uint64_t)nPixels * wp.sppWave <= (1u << 25) ? 4 : 2);
+        if (ctx->stageTiming || ctx->countTraversal) { nLanes = 1; }
+        nLanes = (int)std::min<uint32_t>((uint32_t)nLanes, wp.sppWave);
         WaveParams wps[PTC_MAX_LANES]; CheckpointPlan plans[PTC_MAX_LANES];
         const uint32_t perLane = (wp.sppWave + (uint32_t)nLanes - 1) / (uint32_t)nLanes;
         int used = 0;
@@ -2239,7 +2200,7 @@ static int renderInternal(ptc_ctx *ctx, uint64_t seed, uint32_t firstSample, uin
             w.firstSample = wp.firstSample + at; w.sppWave = std::min(perLane, wp.sppWave - at); w.groupShift = groupShiftFor(w.sppWave);
             plans[used] = planFor(checkpoints, w.firstSample, w.sppWave, done == 0 && at == 0, done + sppWave >= nSpp && at + perLane >= wp.sppWave);
         }
-        if ((rc = launchWave(ctx, wps, plans, used, accumDevice, stream))) { return rc; }
+        if ((rc = launchWave(ctx, wps, plans, used, accumDevice, stream, volume))) { return rc; }
     }
     ctx->samples += (uint64_t)nPixels * nSpp;
     return PTC_OK;
@@ -2699,7 +2660,7 @@ int ptc_set_option(ptc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "stage_timing")) { ctx->stageTiming = value != 0; return PTC_OK; }
     if (!strcmp(name, "overlap_shadow")) { ctx->overlapShadow = value != 0; return PTC_OK; }
     if (!strcmp(name, "lanes")) { // part-waves traced side by side (ptc_ctx::lanes)
-        if (value < 1 || value > PTC_MAX_LANES) { CTX_FAIL(ctx, PTC_ERR_INVALID, "lanes must be in [1, %d]", PTC_MAX_LANES); }
+        if (value < 0 || value > PTC_MAX_LANES) { CTX_FAIL(ctx, PTC_ERR_INVALID, "lanes must be in [0, %d] (0: chosen per wave)", PTC_MAX_LANES); }
         ctx->lanes = (int)value; return PTC_OK;
     }
     if (!strcmp(name, "count_traversal")) { ctx->countTraversal = value != 0; return PTC_OK; }

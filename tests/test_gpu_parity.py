@@ -219,20 +219,21 @@ def test_render_is_deterministic_and_splits_over_samples():
     assert np.array_equal(a, d)
 
 
-@pytest.mark.parametrize("scene,size,last", [("cornell_glass", 48, 10), ("mis", 40, 6), ("cornell_medium_pt", 40, 6)])
+@pytest.mark.parametrize("scene,size,last", [("cornell_glass", 48, 10), ("mis", 40, 6), ("cornell_medium_pt", 40, 6), ("instanced", 40, 5),
+                                             ("cornell_medium", 40, 6), ("medium_sphere", 40, 6)])
 def test_interleaved_lanes_render_the_same_image(scene, size, last):
     """ptc_set_option("lanes", n): the wave's samples are traced as n part-waves on n streams and added in sample order -- the image is
-    the one-lane image bit for bit, for sample counts the lanes divide and for ragged ones, over several waves, and with checkpoints"""
+    the one-lane image bit for bit, for sample counts the lanes divide and for ragged ones, over several waves (PathTracer and the
+    VolumePathTracer's wavefront stages; 0 = the library's own choice, the default)"""
     ctx = gpu_scene(scene, size, size)
     ctx.set_option("lanes", 1)
     one = {spp: ctx.render(21, 3, spp, 0, last) for spp in (1, 5, 8)}
-    for lanes in (2, 3, 4, 8):
+    for lanes in (0, 2, 3, 4, 8):
         ctx.set_option("lanes", lanes)
         for spp, image in one.items():
             assert np.array_equal(ctx.render(21, 3, spp, 0, last), image, equal_nan=True), (lanes, spp)
     ctx.set_option("paths_per_wave", size * size * 3)  # 8 spp = three waves of 3, 3, 2 samples, each split over the lanes
     assert np.array_equal(ctx.render(21, 3, 8, 0, last), one[8], equal_nan=True)
-    ctx.set_option("lanes", 1)
 
 
 def test_render_into_page_locked_memory_equals_the_staged_copy():
