@@ -6,7 +6,7 @@
 Workload (config.workload): scenes/dragon.json, 1024 x 1024, PathTracer, startBounce 0, lastBounce 10 — the
 configuration the north-star target is quoted on (">= 100x the reference CPU Msamples/s on dragon.json on 1 B200").
 One step = one pass of the hot path over one batch = SPP_PER_STEP samples per pixel over the whole image
-(64 spp -> 67.1 M samples = one wave of the wavefront; 4 steps = the config's 256 spp).  Synthetic data: the dragon mesh and the environment
+(64 spp -> 67.1 M samples = one wave of the wavefront, traced as two part-waves side by side on two streams; 4 steps = the config's 256 spp).  Synthetic data: the dragon mesh and the environment
 map are seeded procedural stand-ins (tools/make_assets.py) because the reference's assets/ are not in its repo.
 
 Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + synchronize on both sides):
@@ -14,7 +14,9 @@ Timed legs (all on the device with CUDA events, >= 3 warm-up steps, barrier + sy
   e2e       ptc_render: the reference-facing call with a HOST radianceLookup buffer (H2D + D2H of the fp32
             framebuffer inside the timed region), i.e. what Integrator::run's sampleImage loop would call
   roofline  the extend (closest-hit traversal) kernel: algorithmic bytes per launch from counted node visits and
-            triangle tests (SURVEY 8(d)) / mean launch duration measured live with CUDA events on the launch stream;
+            triangle tests / mean launch duration measured live with CUDA events on the launch stream, in a
+            pass of the same steps with the stages one after the other (in the `value` region launches of the two part-waves
+            and the shadow-ray launches run concurrently, so a launch's duration there is not its own);
             `traffic` = DRAM bytes per launch of the same kernel from the ncu capture of THIS build (profiles/traffic.json carries
             the hash of the CUDA sources it was taken from; a capture of another build is reported as null, never scaled)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/pathed_ref_headless, Embree) on the host cores, bounded sample
@@ -136,7 +138,7 @@ def workload_config(args, world):
     """`config` of the JSON line: a pure function of the command line, so that both arms print the same object"""
     w = WORKLOADS[args.workload]
     n_pix = w["width"] * w["height"]
-    ppw = args.paths_per_wave or (1 << 26)
+    ppw = args.paths_per_wave or (1 << 27)  # the library's default wave size
     spp_rank = rank_spp(args, world)
     waves = max(1, -(-spp_rank // max(1, ppw // n_pix)))
     if world > 1:

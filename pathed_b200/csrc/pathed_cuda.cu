@@ -1091,8 +1091,9 @@ struct ptc_ctx {
     int gridTraverse = 0, gridShade = 0, gridLogic = 0, gridSimple = 0;
     int gridTraverseShared = 0, gridVolumeTraverseShared = 0; // traversal grids of a wave traced as several lanes: two CTAs per SM fewer
     // options / stats
-    int64_t pathsPerWave = 1 << 26; // 67 M paths x 156 B = 10.5 GB of path state per wave (of 180 GB): the queues of the late bounces (1 % of the paths) stay long enough to
-                                    // keep 148 SMs busy; measured 648 vs 613 Msamples/s against 2^24 on the dragon workload, 653 with 2^27
+    int64_t pathsPerWave = 1 << 27; // up to 134 M paths x 237 B = 31.8 GB of path state per wave (of 180 GB; allocated for the paths a render call needs):
+                                    // the queues of the late bounces (1 % of the paths) stay long enough to keep 148 SMs busy.  Dragon workload: 613 / 648 / 653
+                                    // Msamples/s with 2^24 / 2^26 / 2^27; teapot 1920x1080, 64-spp steps: 2306 (two waves of 32 spp at 2^26) vs 2374 (one wave)
     bool stageTiming = false, countTraversal = false;
     // the shadow rays of a bounce are traced on a second stream, concurrently with the bounce's extend rays: both grids fill the GPU, so
     // the shadow CTAs become resident as the extend kernel drains -- the tail of one launch is filled with the head of the other

@@ -23,6 +23,9 @@ def main():
     from pathed_b200 import load_scene
     w = bench.WORKLOADS[workload]
     ctx = load_scene(w["scene"], w["width"], w["height"], integrator=1 if w.get("integrator") == "VolumePathTracer" else 0)
+    # one launch sequence (under ncu the launches run one after the other anyway): per-bounce ray counts pair with the launches, and the
+    # launches are the ones bench.py's stage-timed pass measures
+    ctx.set_option("lanes", int(sys.argv[4]) if len(sys.argv) > 4 else 1)
     accum = torch.zeros(w["width"] * w["height"] * 3, dtype=torch.float32, device="cuda")
     ctx.render_device(0x5EED, 0, spp, 0, w["last_bounce"], accum.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
