@@ -96,8 +96,11 @@ struct BuildArrays {
     float4 *clusterLo[2], *clusterHi[2];
     uint32_t *nearest;
     uint64_t *scanIn, *scanOut; // packed counters: high word / low word scanned together
-    uint4 *topTasks;            // task stack of the top-level SAH pass
-    uint32_t *topResults;
+    // top-level SAH pass: one segment (first cluster, cluster count, node index) per inner node, level after level; per segment and
+    // axis the best split (cost, bin, lower centroid bound, bins per unit length); state = {segments appended so far, next free node index}
+    uint4 *topSegments;
+    float4 *topAxis;
+    uint32_t *topMid, *topState;
     // emission
     uint32_t *items[2];     // binary node of every wide node of the current / next level
     uint32_t *itemChildren; // 8 per item, slot order, kInvalid = empty
@@ -258,91 +261,138 @@ struct MergeOp {
 // ---- step 3b: top of the tree ----------------------------------------------------------------------------------------------
 // Agglomerative clustering decides well near the leaves but the last few hundred merges (the top of the tree, visited by every
 // ray) are taken between whatever clusters happen to be left.  So PLOC stops at `count` clusters and the top is built over them
-// top-down with a 16-bin SAH over all three axes (the host builder's split rule), by one thread: a few thousand clusters.
-struct TopDownOp {
+// top-down with a 16-bin SAH over all three axes (the host builder's split rule), level by level: every inner node of the top is a
+// segment [first, first + count) of the cluster list.  Per level
+//   TopAxisOp   one thread per (segment, axis): centroid bounds, binning, sweep -> the best split on that axis
+//   TopSplitOp  one thread per segment: picks the axis, partitions the segment's clusters in place
+//   TopEmitOp   one thread: numbers the children (root = last node index, the others downwards in creation order, so that a level's
+//               nodes are consecutive), links them, appends the segments of the next level
+// and once the segments have run out TopFinishOp, one thread per node, deepest level first: box and collapse table from the children.
+// The serial chain is one pass over the largest segment per level (512 + 256 + ... clusters) instead of one thread walking every
+// segment of every level.
+constexpr int kTopBins = 16;
+
+struct TopAxisOp {
     BuildArrays a;
     int buffer;
-    uint32_t count, firstNewNode;
+    uint32_t segBase;
+    PTC_HD void operator()(uint32_t i) const
+    {
+        const uint4 seg = a.topSegments[segBase + i / 3u];
+        const int axis = (int)(i % 3u);
+        const float4 *lo = a.clusterLo[buffer], *hi = a.clusterHi[buffer];
+        const uint32_t first = seg.x, end = seg.x + seg.y;
+        float cl = kInf, ch = -kInf;
+        for (uint32_t c = first; c < end; c++) {
+            const float4 l = lo[c], h = hi[c];
+            const float v = 0.5f * (axis == 0 ? l.x + h.x : (axis == 1 ? l.y + h.y : l.z + h.z));
+            cl = fminf(cl, v); ch = fmaxf(ch, v);
+        }
+        float bestCost = kInf; int bestBin = -1;
+        const float extent = ch - cl;
+        const float scale = extent > 0.f ? (float)kTopBins / extent : 0.f;
+        if (extent > 0.f) {
+            float bl[kTopBins][3], bh[kTopBins][3]; uint32_t bn[kTopBins];
+            for (int b = 0; b < kTopBins; b++) { bn[b] = 0; for (int k = 0; k < 3; k++) { bl[b][k] = kInf; bh[b][k] = -kInf; } }
+            for (uint32_t c = first; c < end; c++) {
+                const float4 l = lo[c], h = hi[c];
+                const float v = 0.5f * (axis == 0 ? l.x + h.x : (axis == 1 ? l.y + h.y : l.z + h.z));
+                int b = (int)((v - cl) * scale);
+                b = b < 0 ? 0 : (b >= kTopBins ? kTopBins - 1 : b);
+                bn[b]++;
+                bl[b][0] = fminf(bl[b][0], l.x); bl[b][1] = fminf(bl[b][1], l.y); bl[b][2] = fminf(bl[b][2], l.z);
+                bh[b][0] = fmaxf(bh[b][0], h.x); bh[b][1] = fmaxf(bh[b][1], h.y); bh[b][2] = fmaxf(bh[b][2], h.z);
+            }
+            float rightArea[kTopBins]; uint32_t rightCount[kTopBins];
+            float al[3] = {kInf, kInf, kInf}, ah[3] = {-kInf, -kInf, -kInf}; uint32_t m = 0;
+            for (int b = kTopBins - 1; b > 0; b--) {
+                for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
+                m += bn[b]; rightArea[b] = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]); rightCount[b] = m;
+            }
+            for (int k = 0; k < 3; k++) { al[k] = kInf; ah[k] = -kInf; }
+            m = 0;
+            for (int b = 0; b < kTopBins - 1; b++) {
+                for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
+                m += bn[b];
+                if (m == 0 || rightCount[b + 1] == 0) { continue; }
+                // clusters are not unit cost: weigh a side by its count (every cluster holds a similar number of primitives)
+                const float cost = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]) * (float)m + rightArea[b + 1] * (float)rightCount[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestBin = b; }
+            }
+        }
+        a.topAxis[3u * (segBase + i / 3u) + (uint32_t)axis] = make_float4(bestCost, u2f((uint32_t)bestBin), cl, scale);
+    }
+};
+
+struct TopSplitOp {
+    BuildArrays a;
+    int buffer;
+    uint32_t segBase;
+    PTC_HD void operator()(uint32_t i) const
+    {
+        const uint4 seg = a.topSegments[segBase + i];
+        float4 *lo = a.clusterLo[buffer], *hi = a.clusterHi[buffer];
+        const uint32_t first = seg.x, end = seg.x + seg.y;
+        float bestCost = kInf; int bestAxis = -1; float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int axis = 0; axis < 3; axis++) { // the first axis with the lowest cost, as one loop over axes and bins would find it
+            const float4 c = a.topAxis[3u * (segBase + i) + (uint32_t)axis];
+            if ((int)f2u(c.y) >= 0 && c.x < bestCost) { bestCost = c.x; bestAxis = axis; best = c; }
+        }
+        uint32_t mid = first + seg.y / 2; // identical centroids: split by index
+        if (bestAxis >= 0) {
+            const int bestBin = (int)f2u(best.y);
+            uint32_t c = first, j = end;
+            while (c < j) {
+                const float4 l = lo[c], h = hi[c];
+                const float v = 0.5f * (bestAxis == 0 ? l.x + h.x : (bestAxis == 1 ? l.y + h.y : l.z + h.z));
+                int b = (int)((v - best.z) * best.w);
+                b = b < 0 ? 0 : (b >= kTopBins ? kTopBins - 1 : b);
+                if (b <= bestBin) { c++; }
+                else { j--; lo[c] = lo[j]; hi[c] = hi[j]; lo[j] = l; hi[j] = h; }
+            }
+            if (c != first && c != end) { mid = c; }
+        }
+        a.topMid[segBase + i] = mid;
+    }
+};
+
+struct TopEmitOp {
+    BuildArrays a;
+    int buffer;
+    uint32_t segBase, segCount;
     PTC_HD void operator()(uint32_t) const
     {
-        float4 *lo = a.clusterLo[buffer], *hi = a.clusterHi[buffer];
-        uint4 *tasks = a.topTasks; // first, count, state, mid
-        uint32_t *results = a.topResults;
-        uint32_t sp = 0, rp = 0, nextNode = firstNewNode;
-        tasks[sp++] = make_uint4(0u, count, 0u, 0u);
-        while (sp) {
-            const uint4 t = tasks[sp - 1];
-            if (t.z == 1u) { // both halves are built
-                const uint32_t right = results[--rp], left = results[--rp];
-                const float4 l0 = a.nodeLo[left], h0 = a.nodeHi[left], l1 = a.nodeLo[right], h1 = a.nodeHi[right];
-                const float4 l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), u2f(left));
-                const float4 h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), u2f(right));
-                a.nodeLo[nextNode] = l; a.nodeHi[nextNode] = h;
-                a.dp[nextNode] = combineDP(a.dp[left], a.dp[right], halfArea(l.x, l.y, l.z, h.x, h.y, h.z), a.costPrim);
-                results[rp++] = nextNode++;
-                sp--;
-                continue;
+        const float4 *lo = a.clusterLo[buffer];
+        uint32_t appended = a.topState[0], nextFree = a.topState[1];
+        for (uint32_t i = 0; i < segCount; i++) {
+            const uint4 seg = a.topSegments[segBase + i];
+            const uint32_t mid = a.topMid[segBase + i], end = seg.x + seg.y;
+            uint32_t child[2];
+            const uint32_t firstOf[2] = {seg.x, mid}, countOf[2] = {mid - seg.x, end - mid};
+            for (int side = 0; side < 2; side++) {
+                if (countOf[side] == 1u) { child[side] = f2u(lo[firstOf[side]].w); continue; } // a PLOC cluster: its node exists
+                child[side] = nextFree--;
+                a.topSegments[appended++] = make_uint4(firstOf[side], countOf[side], child[side], 0u);
             }
-            if (t.y == 1u) { results[rp++] = f2u(lo[t.x].w); sp--; continue; }
-            const uint32_t first = t.x, end = t.x + t.y;
-            float cl[3] = {kInf, kInf, kInf}, ch[3] = {-kInf, -kInf, -kInf};
-            for (uint32_t i = first; i < end; i++) {
-                float c[3];
-                centroidOf(lo[i], hi[i], c);
-                for (int k = 0; k < 3; k++) { cl[k] = fminf(cl[k], c[k]); ch[k] = fmaxf(ch[k], c[k]); }
-            }
-            const int BINS = 16;
-            float bestCost = kInf; int bestAxis = -1, bestBin = -1;
-            for (int axis = 0; axis < 3; axis++) {
-                const float extent = ch[axis] - cl[axis];
-                if (!(extent > 0.f)) { continue; }
-                float bl[BINS][3], bh[BINS][3]; uint32_t bn[BINS];
-                for (int b = 0; b < BINS; b++) { bn[b] = 0; for (int k = 0; k < 3; k++) { bl[b][k] = kInf; bh[b][k] = -kInf; } }
-                const float scale = (float)BINS / extent;
-                for (uint32_t i = first; i < end; i++) {
-                    const float4 l = lo[i], h = hi[i];
-                    const float c = 0.5f * (axis == 0 ? l.x + h.x : (axis == 1 ? l.y + h.y : l.z + h.z));
-                    int b = (int)((c - cl[axis]) * scale);
-                    b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
-                    bn[b]++;
-                    bl[b][0] = fminf(bl[b][0], l.x); bl[b][1] = fminf(bl[b][1], l.y); bl[b][2] = fminf(bl[b][2], l.z);
-                    bh[b][0] = fmaxf(bh[b][0], h.x); bh[b][1] = fmaxf(bh[b][1], h.y); bh[b][2] = fmaxf(bh[b][2], h.z);
-                }
-                float rightArea[BINS]; uint32_t rightCount[BINS];
-                float al[3] = {kInf, kInf, kInf}, ah[3] = {-kInf, -kInf, -kInf}; uint32_t m = 0;
-                for (int b = BINS - 1; b > 0; b--) {
-                    for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
-                    m += bn[b]; rightArea[b] = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]); rightCount[b] = m;
-                }
-                for (int k = 0; k < 3; k++) { al[k] = kInf; ah[k] = -kInf; }
-                m = 0;
-                for (int b = 0; b < BINS - 1; b++) {
-                    for (int k = 0; k < 3; k++) { al[k] = fminf(al[k], bl[b][k]); ah[k] = fmaxf(ah[k], bh[b][k]); }
-                    m += bn[b];
-                    if (m == 0 || rightCount[b + 1] == 0) { continue; }
-                    // clusters are not unit cost: weigh a side by its count (every cluster holds a similar number of primitives)
-                    const float cost = halfArea(al[0], al[1], al[2], ah[0], ah[1], ah[2]) * (float)m + rightArea[b + 1] * (float)rightCount[b + 1];
-                    if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
-                }
-            }
-            uint32_t mid = first + t.y / 2; // identical centroids: split by index
-            if (bestAxis >= 0) {
-                const float scale = (float)BINS / (ch[bestAxis] - cl[bestAxis]);
-                uint32_t i = first, j = end;
-                while (i < j) {
-                    const float4 l = lo[i], h = hi[i];
-                    const float c = 0.5f * (bestAxis == 0 ? l.x + h.x : (bestAxis == 1 ? l.y + h.y : l.z + h.z));
-                    int b = (int)((c - cl[bestAxis]) * scale);
-                    b = b < 0 ? 0 : (b >= BINS ? BINS - 1 : b);
-                    if (b <= bestBin) { i++; }
-                    else { j--; lo[i] = lo[j]; hi[i] = hi[j]; lo[j] = l; hi[j] = h; }
-                }
-                if (i != first && i != end) { mid = i; }
-            }
-            tasks[sp - 1] = make_uint4(first, t.y, 1u, mid);
-            tasks[sp++] = make_uint4(mid, end - mid, 0u, 0u);
-            tasks[sp++] = make_uint4(first, mid - first, 0u, 0u); // left half first
+            a.nodeLo[seg.z].w = u2f(child[0]);
+            a.nodeHi[seg.z].w = u2f(child[1]);
         }
+        a.topState[0] = appended; a.topState[1] = nextFree;
+    }
+};
+
+struct TopFinishOp {
+    BuildArrays a;
+    uint32_t segBase;
+    PTC_HD void operator()(uint32_t i) const
+    {
+        const uint32_t node = a.topSegments[segBase + i].z;
+        const uint32_t left = f2u(a.nodeLo[node].w), right = f2u(a.nodeHi[node].w);
+        const float4 l0 = a.nodeLo[left], h0 = a.nodeHi[left], l1 = a.nodeLo[right], h1 = a.nodeHi[right];
+        const float4 l = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), u2f(left));
+        const float4 h = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), u2f(right));
+        a.nodeLo[node] = l; a.nodeHi[node] = h;
+        a.dp[node] = combineDP(a.dp[left], a.dp[right], halfArea(l.x, l.y, l.z, h.x, h.y, h.z), a.costPrim);
     }
 };
 
@@ -630,6 +680,20 @@ struct DeviceExec {
         return tail[0] + tail[1];
     }
     void setItem(uint32_t *items, uint32_t value) { check(cudaMemcpyAsync(items, &value, 4, cudaMemcpyHostToDevice, stream), "root item"); check(cudaStreamSynchronize(stream), "root item"); }
+    void setTop(const BuildArrays &a, uint4 rootSegment, uint32_t appended, uint32_t nextFree)
+    {
+        const uint32_t state[2] = {appended, nextFree};
+        check(cudaMemcpyAsync(a.topSegments, &rootSegment, sizeof(uint4), cudaMemcpyHostToDevice, stream), "top root");
+        check(cudaMemcpyAsync(a.topState, state, sizeof(state), cudaMemcpyHostToDevice, stream), "top state");
+        check(cudaStreamSynchronize(stream), "top state"); // the sources are on this stack frame
+    }
+    uint32_t readWord(const uint32_t *p)
+    {
+        uint32_t v = 0;
+        check(cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, stream), "read back");
+        check(cudaStreamSynchronize(stream), "read back");
+        return v;
+    }
     void sync() { check(cudaStreamSynchronize(stream), "BVH build sync"); }
 };
 
@@ -669,6 +733,8 @@ struct HostExec {
         return sum;
     }
     void setItem(uint32_t *items, uint32_t value) { items[0] = value; }
+    void setTop(const BuildArrays &a, uint4 rootSegment, uint32_t appended, uint32_t nextFree) { a.topSegments[0] = rootSegment; a.topState[0] = appended; a.topState[1] = nextFree; }
+    uint32_t readWord(const uint32_t *p) { return *p; }
     void sync() {}
 };
 
@@ -726,10 +792,26 @@ BuildResult runBuild(Exec &exec, BuildArrays &a)
         nextNode += created; nClusters = survivors; buffer ^= 1;
         result.plocIterations++;
     }
-    if (nClusters > 1) { // top of the tree: SAH over the remaining clusters
-        a.topTasks = exec.template alloc<uint4>(2 * (size_t)nClusters + 2);
-        a.topResults = exec.template alloc<uint32_t>((size_t)nClusters + 2);
-        exec.forEach(1u, TopDownOp{a, buffer, nClusters, nextNode});
+    if (nClusters > 1) { // top of the tree: SAH over the remaining clusters, nClusters - 1 inner nodes = segments
+        a.topSegments = exec.template alloc<uint4>(nClusters);
+        a.topAxis = exec.template alloc<float4>(3 * (size_t)nClusters);
+        a.topMid = exec.template alloc<uint32_t>(nClusters);
+        a.topState = exec.template alloc<uint32_t>(2);
+        const uint32_t rootNode = nextNode + nClusters - 2u;
+        exec.setTop(a, make_uint4(0u, nClusters, rootNode, 0u), 1u, rootNode - 1u);
+        std::vector<std::pair<uint32_t, uint32_t>> levels; // first segment, segment count
+        uint32_t segBase = 0, segCount = 1;
+        while (segCount) {
+            levels.push_back({segBase, segCount});
+            exec.forEach(3u * segCount, TopAxisOp{a, buffer, segBase});
+            exec.forEach(segCount, TopSplitOp{a, buffer, segBase});
+            exec.forEach(1u, TopEmitOp{a, buffer, segBase, segCount});
+            const uint32_t appended = exec.readWord(a.topState);
+            if (appended > nClusters - 1u || appended < segBase + segCount) { throw std::runtime_error("top-level SAH pass lost track of its segments"); }
+            segBase += segCount; segCount = appended - segBase;
+        }
+        if (segBase != nClusters - 1u) { throw std::runtime_error("top-level SAH pass made the wrong number of nodes"); }
+        for (size_t level = levels.size(); level-- > 0;) { exec.forEach(levels[level].second, TopFinishOp{a, levels[level].first}); }
         nextNode += nClusters - 1u;
     }
     exec.sync();
