@@ -19,7 +19,7 @@ for scene, integ in (("scenes/cornell-glass.json", 0), ("scenes/mis-pbrt.json", 
     print(scene, integ, float(img.mean()), float(out.mean()))
     ctx.close()
 PY
-for tool in memcheck racecheck; do
-  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_me.py > gpurun_out/sanitizer_$tool.log 2>&1
+for tool in ${SANITIZER_TOOLS:-memcheck racecheck}; do
+  timeout ${SANITIZER_TIMEOUT:-1500} compute-sanitizer --tool $tool --print-limit 20 python /tmp/sanitize_me.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)"
 done
