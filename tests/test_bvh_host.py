@@ -109,3 +109,30 @@ def test_device_builder_quality_is_close_to_the_host_sah_builder():
     work = lambda st: 80 * st["inner_visits"] + 48 * st["triangle_tests"]
     assert work(dev) < 1.15 * work(host), (host, dev)
     assert dev["slots"] / dev["nodes"] > 5.0
+
+
+@pytest.mark.parametrize("top", [None, 4, 64, 100000])
+def test_top_level_sah_pass_builds_the_recorded_trees(top, monkeypatch):
+    """The SAH pass over the clusters PLOC leaves (bvh_build_gpu.cu: TopAxisOp / TopSplitOp / TopEmitOp / TopFinishOp, level by level)
+    builds the tree the one-thread depth-first pass it replaced built: node, slot and depth counts of the wide BVH recorded with that
+    pass, for the default top size, a tiny one, one between, and one that hands the whole mesh to the SAH pass (no PLOC at all); a mesh with
+    duplicated triangles and a floor 50x its size exercises the median fallback for identical centroids."""
+    if top is None:
+        monkeypatch.delenv("PTC_PLOC_TOP", raising=False)
+    else:
+        monkeypatch.setenv("PTC_PLOC_TOP", str(top))
+    pts, faces = bumpy_sphere(60, 40, 3)
+    faces = np.concatenate([faces, faces[:500]])
+    floor = np.array([[-50, -2, -50], [50, -2, -50], [50, -2, 50], [-50, -2, 50]], np.float32)
+    n = len(pts)
+    pts = np.concatenate([pts, floor])
+    faces = np.concatenate([faces, np.array([[n, n + 1, n + 2], [n, n + 2, n + 3]], np.uint32)]).astype(np.uint32)
+    rays = rays_array(unit_vectors(5, 400) * np.float32(3.0), -unit_vectors(5, 400))
+    t_bvh, p_bvh, t_bf, p_bf, st = selfcheck(pts, faces, rays, 1)
+    # same depths; the same triangle or its duplicate (which of two coincident copies survives the inclusive depth test depends on the
+    # order they are met in: |den| * (T / |den|) may round below T)
+    assert np.array_equal(t_bvh, t_bf)
+    hit = p_bf != 0xFFFFFFFF
+    assert np.array_equal(p_bvh != 0xFFFFFFFF, hit) and np.array_equal(faces[p_bvh[hit]], faces[p_bf[hit]]) and hit.mean() > 0.9
+    recorded = {None: (506, 3811, 6), 4: (496, 3779, 6), 64: (508, 3825, 6), 100000: (496, 3775, 5)}[top]
+    assert (st["nodes"], st["slots"], st["max_depth"]) == recorded, st
