@@ -75,9 +75,8 @@ struct FaceVertex { int vertex, normal, uv; };
 struct Face { FaceVertex v[3]; };
 
 // classifies one whitespace-separated face token: "7", "7/8/9" or "7//9"
-bool parseFaceToken(const std::string &token, int &v, int &t, int &n, int &kind)
+bool parseFaceToken(const char *s, int &v, int &t, int &n, int &kind) // s: zero-terminated (no std::string: one per token was a heap allocation per token)
 {
-    const char *s = token.c_str();
     char *end = nullptr;
     v = (int)strtol(s, &end, 10);
     if (end == s) { return false; }
